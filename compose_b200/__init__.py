@@ -1,0 +1,338 @@
+"""compose_b200 -- B200-native CEDR property preservation (QLT and CAAS).
+
+Python host-side mirror of the reference's `cedr::CDR` interface
+(cedr/cedr_cdr.hpp:16-112) over the C ABI of include/cedr_b200.h. PyTorch is
+used only for device memory and streams; every kernel is in
+compose_b200/libcedr_b200.so (hand-written CUDA, sm_100a). There is no CPU
+fallback: constructing a CDR without the library or without a GPU raises.
+
+    qlt = QLT(ncells)                       # tree::make_tree_over_1d_mesh
+    for t in range(nt): qlt.declare_tracer(CONSERVE | SHAPEPRESERVE | CONSISTENT)
+    qlt.end_tracer_declarations(); qlt.finish_setup()
+    qlt.set_rhom(rhom); qlt.set_Qm(qm, qm_min, qm_max, qm_prev)   # cuda float64
+    qlt.run(); out = qlt.get_Qm()
+"""
+import ctypes as C
+import os
+
+CONSERVE, SHAPEPRESERVE, CONSISTENT, NONNEGATIVE = 1, 2, 4, 8
+CAAS_SUM_TREE, CAAS_SUM_SEQUENTIAL = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcedr_b200.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lp = C.POINTER(C.c_int64)
+_vp = C.c_void_p
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, _vp, C.c_size_t, _vp)
+
+
+class DeviceOp(C.Structure):
+    """cedr_b200_device_op (include/cedr_b200.h)."""
+    _fields_ = [("in_", _vp), ("out", _vp), ("ld", C.c_int64), ("trcr_row", _vp),
+                ("trcr_prob", _vp), ("ntracers", C.c_int), ("nlclcells", C.c_int),
+                ("is_caas", C.c_int), ("reserved", C.c_int)]
+
+
+# Every symbol include/cedr_b200.h declares: (name, restype, argtypes).
+_H = _vp  # opaque cedr_b200_cdr*
+SYMBOLS = [
+    ("cedr_b200_last_error", C.c_char_p, []),
+    ("cedr_b200_version", C.c_int, []),
+    ("cedr_b200_device_available", C.c_int, []),
+    ("cedr_b200_qlt_create", C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.c_int, _ip, _lp,
+                                       _ip, C.c_int, C.c_int, C.c_int]),
+    ("cedr_b200_qlt_create_1d", C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int]),
+    ("cedr_b200_caas_create", C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.c_int64,
+                                        C.c_int64, C.c_int, C.c_int]),
+    ("cedr_b200_destroy", C.c_int, [_H]),
+    ("cedr_b200_declare_tracer", C.c_int, [_H, C.c_int, C.c_int]),
+    ("cedr_b200_end_tracer_declarations", C.c_int, [_H]),
+    ("cedr_b200_get_buffers_sizes", C.c_int, [_H, C.POINTER(C.c_size_t),
+                                              C.POINTER(C.c_size_t)]),
+    ("cedr_b200_set_buffers", C.c_int, [_H, _vp, _vp]),
+    ("cedr_b200_finish_setup", C.c_int, [_H]),
+    ("cedr_b200_get_problem_type", C.c_int, [_H, C.c_int, _ip]),
+    ("cedr_b200_get_num_tracers", C.c_int, [_H, _ip]),
+    ("cedr_b200_run", C.c_int, [_H]),
+    ("cedr_b200_print", C.c_int, [_H, C.c_char_p, C.c_size_t]),
+    ("cedr_b200_nlclcells", C.c_int, [_H, _ip]),
+    ("cedr_b200_get_owned_glblcells", C.c_int, [_H, _lp]),
+    ("cedr_b200_gci2lci", C.c_int, [_H, C.c_int64, _ip]),
+    ("cedr_b200_get_device_op", C.c_int, [_H, C.POINTER(DeviceOp)]),
+    ("cedr_b200_set_rhom_bulk", C.c_int, [_H, _vp]),
+    ("cedr_b200_set_Qm_bulk", C.c_int, [_H, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp,
+                                        _vp]),
+    ("cedr_b200_get_Qm_bulk", C.c_int, [_H, C.c_int, C.c_int, C.c_int64, _vp]),
+    ("cedr_b200_set_stream", C.c_int, [_H, _vp]),
+    ("cedr_b200_synchronize", C.c_int, [_H]),
+    ("cedr_b200_set_allgather", C.c_int, [_H, ALLGATHER_FN, _vp]),
+    ("cedr_b200_last_run_launches", C.c_int, [_H, _ip]),
+    ("cedr_b200_plan_info", C.c_int, [_H, _ip, _ip, _ip, _ip]),
+    ("cedr_b200_set_max_block_leaves", C.c_int, [_H, C.c_int]),
+    ("cedr_b200_plan_probe", C.c_int, [C.c_int, C.c_int, C.c_int, _ip, _lp, C.c_int, _lp,
+                                       _ip, _ip, _ip, _ip, _lp]),
+    ("cedr_b200_make_1d_tree", C.c_int, [C.c_int, C.c_int, _ip, _lp]),
+    ("cedr_b200_fill_headline", C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int, _vp, _vp,
+                                          _vp, _vp, _vp, _vp]),
+]
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the CUDA library and bind every declared symbol. Raises if absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            "compose_b200: %s is missing. Build it with `python -m compose_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % p)
+    lib = C.CDLL(p)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class CedrError(RuntimeError):
+    """A failure reported by the C ABI (the reference throws std::logic_error)."""
+
+
+def _check(rc):
+    if rc:
+        raise CedrError(load_library().cedr_b200_last_error().decode())
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _as_i32(a):
+    import numpy as np
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class CDR:
+    """Host methods of cedr::CDR (cedr_cdr.hpp:47-108), plus bulk DeviceOp forms."""
+
+    def __init__(self):
+        self._lib = load_library()
+        self._h = _H()
+        self._in = self._out = None      # torch tensors backing the buffers
+        self._cb = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.cedr_b200_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- setup
+    def declare_tracer(self, problem_type, rhomidx=0):
+        _check(self._lib.cedr_b200_declare_tracer(self._h, int(problem_type), int(rhomidx)))
+
+    def end_tracer_declarations(self):
+        _check(self._lib.cedr_b200_end_tracer_declarations(self._h))
+
+    def get_buffers_sizes(self):
+        b1, b2 = C.c_size_t(0), C.c_size_t(0)
+        _check(self._lib.cedr_b200_get_buffers_sizes(self._h, C.byref(b1), C.byref(b2)))
+        return b1.value, b2.value
+
+    def set_buffers(self, buf1, buf2):
+        """buf1/buf2: cuda float64 tensors of at least get_buffers_sizes() elements."""
+        self._in, self._out = buf1, buf2
+        _check(self._lib.cedr_b200_set_buffers(self._h, _ptr(buf1), _ptr(buf2)))
+
+    def set_max_block_leaves(self, n):
+        _check(self._lib.cedr_b200_set_max_block_leaves(self._h, int(n)))
+
+    def finish_setup(self):
+        self.use_current_stream()
+        _check(self._lib.cedr_b200_finish_setup(self._h))
+
+    def get_problem_type(self, tracer_idx):
+        v = C.c_int(0)
+        _check(self._lib.cedr_b200_get_problem_type(self._h, int(tracer_idx), C.byref(v)))
+        return v.value
+
+    def get_num_tracers(self):
+        v = C.c_int(0)
+        _check(self._lib.cedr_b200_get_num_tracers(self._h, C.byref(v)))
+        return v.value
+
+    def nlclcells(self):
+        v = C.c_int(0)
+        _check(self._lib.cedr_b200_nlclcells(self._h, C.byref(v)))
+        return v.value
+
+    def get_owned_glblcells(self):
+        import numpy as np
+        out = np.empty(self.nlclcells(), np.int64)
+        _check(self._lib.cedr_b200_get_owned_glblcells(self._h, out.ctypes.data_as(_lp)))
+        return out
+
+    def gci2lci(self, gci):
+        v = C.c_int(0)
+        _check(self._lib.cedr_b200_gci2lci(self._h, int(gci), C.byref(v)))
+        return v.value
+
+    def print(self):
+        buf = C.create_string_buffer(4096)
+        _check(self._lib.cedr_b200_print(self._h, buf, 4096))
+        return buf.value.decode()
+
+    def plan_info(self):
+        a, b, c, d = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(self._lib.cedr_b200_plan_info(self._h, C.byref(a), C.byref(b), C.byref(c),
+                                             C.byref(d)))
+        return {"ntiers": a.value, "nblocks0": b.value, "max_block_leaves": c.value,
+                "nlevels_ref": d.value}
+
+    def get_device_op(self):
+        op = DeviceOp()
+        _check(self._lib.cedr_b200_get_device_op(self._h, C.byref(op)))
+        return op
+
+    # -- streams
+    def use_current_stream(self):
+        _check(self._lib.cedr_b200_set_stream(self._h, _stream_ptr()))
+
+    def synchronize(self):
+        _check(self._lib.cedr_b200_synchronize(self._h))
+
+    # -- per step
+    def set_rhom(self, rhom):
+        """rhom: cuda float64 [nlclcells], indexed by local cell index."""
+        assert rhom.is_cuda and rhom.dtype.is_floating_point and rhom.element_size() == 8
+        _check(self._lib.cedr_b200_set_rhom_bulk(self._h, _ptr(rhom)))
+
+    def set_Qm(self, qm, qm_min, qm_max, qm_prev=None, t0=0):
+        """SoA cuda float64 [nt, lda] arrays, cell (lci) fastest."""
+        nt, lda = qm.shape[0], qm.stride(0) if qm.dim() == 2 else qm.numel()
+        for x in (qm, qm_min, qm_max, qm_prev):
+            assert x is None or (x.is_cuda and x.element_size() == 8 and x.stride(-1) == 1)
+        _check(self._lib.cedr_b200_set_Qm_bulk(self._h, int(t0), int(nt), int(lda), _ptr(qm),
+                                               _ptr(qm_min), _ptr(qm_max), _ptr(qm_prev)))
+
+    def run(self):
+        _check(self._lib.cedr_b200_run(self._h))
+
+    def get_Qm(self, out=None, t0=0, nt=None):
+        import torch
+        nt = self.get_num_tracers() - t0 if nt is None else nt
+        if out is None:
+            out = torch.empty((nt, self.nlclcells()), dtype=torch.float64, device="cuda")
+        lda = out.stride(0) if out.dim() == 2 else out.numel()
+        _check(self._lib.cedr_b200_get_Qm_bulk(self._h, int(t0), int(nt), int(lda),
+                                               _ptr(out)))
+        return out
+
+    def last_run_launches(self):
+        v = C.c_int(0)
+        _check(self._lib.cedr_b200_last_run_launches(self._h, C.byref(v)))
+        return v.value
+
+
+class QLT(CDR):
+    """cedr::qlt::QLT (cedr_qlt.hpp:26-219).
+
+    tree=None builds tree::make_tree_over_1d_mesh(ncells, imbalanced); otherwise
+    `tree` is (kids[2*nnodes], cellidx[nnodes], root) flat arrays of the caller's
+    tree::Node graph.
+    """
+
+    def __init__(self, ncells, tree=None, imbalanced=False,
+                 prefer_numerical_mass_conservation_to_numerical_bounds=False,
+                 rank=0, nranks=1, node_rank=None):
+        super().__init__()
+        import numpy as np
+        prefer = int(bool(prefer_numerical_mass_conservation_to_numerical_bounds))
+        if tree is None:
+            _check(self._lib.cedr_b200_qlt_create_1d(C.byref(self._h), int(ncells),
+                                                     int(bool(imbalanced)), prefer,
+                                                     int(rank), int(nranks)))
+        else:
+            kids, cellidx, root = tree
+            kids = _as_i32(kids).reshape(-1)
+            cellidx = np.ascontiguousarray(cellidx, dtype=np.int64)
+            nr = None if node_rank is None else _as_i32(node_rank)
+            _check(self._lib.cedr_b200_qlt_create(
+                C.byref(self._h), int(ncells), int(cellidx.size), int(root),
+                kids.ctypes.data_as(_ip), cellidx.ctypes.data_as(_lp),
+                None if nr is None else nr.ctypes.data_as(_ip), prefer, int(rank),
+                int(nranks)))
+
+
+class CAAS(CDR):
+    """cedr::caas::CAAS (cedr_caas.hpp:15-118)."""
+
+    def __init__(self, nlclcells, sum_mode=CAAS_SUM_TREE, cell0=0, ncells_global=None,
+                 rank=0, nranks=1):
+        super().__init__()
+        ng = nlclcells if ncells_global is None else ncells_global
+        _check(self._lib.cedr_b200_caas_create(C.byref(self._h), int(nlclcells),
+                                               int(sum_mode), int(cell0), int(ng),
+                                               int(rank), int(nranks)))
+
+
+def fill_headline(ncells, nt, config_id, lda=None):
+    """Synthetic SURVEY 8(d) workload generated on the device. Returns cuda tensors
+    (rhom[ncells], qm_min, qm, qm_max, qm_prev: [nt, lda])."""
+    import torch
+    lib = load_library()
+    lda = ncells if lda is None else lda
+    rhom = torch.empty(ncells, dtype=torch.float64, device="cuda")
+    arrs = [torch.empty((nt, lda), dtype=torch.float64, device="cuda") for _ in range(4)]
+    _check(lib.cedr_b200_fill_headline(int(ncells), int(nt), int(lda), int(config_id),
+                                       _ptr(rhom), _ptr(arrs[0]), _ptr(arrs[1]),
+                                       _ptr(arrs[2]), _ptr(arrs[3]), _stream_ptr()))
+    return (rhom,) + tuple(arrs)
+
+
+def make_1d_tree(ncells, imbalanced=False):
+    """tree::make_tree_over_1d_mesh as flat arrays: (kids, cellidx, root)."""
+    import numpy as np
+    lib = load_library()
+    nn = 2*ncells - 1
+    kids = np.empty(2*nn, np.int32)
+    cellidx = np.empty(nn, np.int64)
+    _check(lib.cedr_b200_make_1d_tree(int(ncells), int(bool(imbalanced)),
+                                      kids.ctypes.data_as(_ip), cellidx.ctypes.data_as(_lp)))
+    return kids, cellidx, 0
+
+
+def plan_probe(ncells, tree, max_block_leaves=1024):
+    """Host-only: build the block plan for `tree` and run its self-check."""
+    import numpy as np
+    lib = load_library()
+    kids, cellidx, root = tree
+    kids = _as_i32(kids).reshape(-1)
+    cellidx = np.ascontiguousarray(cellidx, dtype=np.int64)
+    lci2gci = np.empty(ncells, np.int64)
+    nb = np.zeros(64, np.int32)
+    ntiers, nshapes, nlev, idsum = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int64(0)
+    _check(lib.cedr_b200_plan_probe(int(ncells), int(cellidx.size), int(root),
+                                    kids.ctypes.data_as(_ip), cellidx.ctypes.data_as(_lp),
+                                    int(max_block_leaves), lci2gci.ctypes.data_as(_lp),
+                                    C.byref(ntiers), nb.ctypes.data_as(_ip),
+                                    C.byref(nshapes), C.byref(nlev), C.byref(idsum)))
+    return {"lci2gci": lci2gci, "ntiers": ntiers.value,
+            "nblocks": nb[:ntiers.value].tolist(), "nshapes": nshapes.value,
+            "nlevels_ref": nlev.value, "idsum": idsum.value}

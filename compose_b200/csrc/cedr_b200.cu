@@ -1,0 +1,774 @@
+// C ABI of the B200-native CEDR hot path (see include/cedr_b200.h) and the host
+// orchestration of run(): which kernels are launched, in which order, on which
+// buffers. Host code is plain C++; all arithmetic on tracer data happens in the
+// CUDA kernels of kernels.cuh. There is no CPU fallback.
+#include "cedr_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+#include "tree_plan.h"
+
+namespace {
+
+using namespace cedr_b200;
+
+thread_local std::string g_err;
+
+// Same message shape as the reference's cedr_throw_if (cedr_util.hpp:70-77).
+#define cedr_b200_throw_if(condition, message) do {                     \
+    if (condition) {                                                    \
+      std::stringstream _ss_;                                           \
+      _ss_ << __FILE__ << ":" << __LINE__ << ": The condition:\n"       \
+           << #condition "\nled to the exception\n" << message << "\n"; \
+      throw std::logic_error(_ss_.str());                               \
+    }                                                                   \
+  } while (0)
+
+#define CUDA_CHECK(call) do {                                           \
+    const cudaError_t _e_ = (call);                                     \
+    if (_e_ != cudaSuccess) {                                           \
+      std::stringstream _ss_;                                           \
+      _ss_ << __FILE__ << ":" << __LINE__ << ": CUDA error in " #call ": " \
+           << cudaGetErrorString(_e_);                                  \
+      throw std::runtime_error(_ss_.str());                             \
+    }                                                                   \
+  } while (0)
+
+template <typename F> int guarded (F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::logic_error& e) {
+    g_err = e.what();
+    return 1;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 2;
+  }
+}
+
+template <typename T> struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf () {}
+  DevBuf (const DevBuf&) = delete;
+  DevBuf& operator= (const DevBuf&) = delete;
+  ~DevBuf () { release(); }
+  void release () { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc (size_t n_) {
+    release();
+    n = n_;
+    if (n) CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&p), n*sizeof(T)));
+  }
+  void upload (const std::vector<T>& h) {
+    alloc(h.size());
+    if (n) CUDA_CHECK(cudaMemcpy(p, h.data(), n*sizeof(T), cudaMemcpyHostToDevice));
+  }
+};
+
+long long round_up (long long x, long long m) { return (x + m - 1)/m*m; }
+
+// QLT::MetaData::get_problem_type_idx, cedr_qlt.cpp:85-96.
+int qlt_class_of (int mask) {
+  enum { c = 1, s = 2, t = 4, n = 8 };
+  switch (mask) {
+  case s: case s | t: return CLS_ST;
+  case c | s: case c | s | t: return CLS_CST;
+  case t: return CLS_T;
+  case c | t: return CLS_CT;
+  case n: return CLS_NN;
+  case c | n: return CLS_CNN;
+  default: return -1;
+  }
+}
+// cedr_qlt_inl.hpp:101-108
+int qlt_canonical_type (int cls) {
+  static const int pt[] = {2 | 4, 1 | 2 | 4, 4, 1 | 4, 8, 1 | 8};
+  return pt[cls];
+}
+// cedr_qlt_inl.hpp:109-117
+int qlt_l2r_words (int cls) {
+  static const int w[] = {3, 4, 3, 4, 1, 2};
+  return w[cls];
+}
+
+const int kThreads = 256;
+
+} // namespace
+
+struct cedr_b200_cdr {
+  bool is_caas = false;
+  int rank = 0, nranks = 1;
+  bool prefer_mass_con = false;
+  int caas_sum_mode = CEDR_B200_CAAS_SUM_TREE;
+  bool caas_need_conserve = false;
+
+  // Tree (QLT: the caller's; CAAS: bisection over the cells, for the ordered sums).
+  int ncells = 0;           // global
+  int nlcl = 0;             // owned by this rank (== ncells on one rank)
+  std::vector<int> tree_kids;
+  std::vector<int64_t> tree_cellidx;
+  std::vector<int> tree_rank;
+  int tree_root = 0;
+  int max_block_leaves = 1024;
+  Plan plan;
+  std::unordered_map<int64_t,int> gci2lci;
+
+  // Tracers.
+  bool declaring = true;
+  std::vector<int> trcr_prob;  // canonical type (QLT) / declared type (CAAS)
+  std::vector<int> trcr_cls;
+  std::vector<int> trcr_row;
+  int nrows = 0;               // rows of the `in` buffer, incl. the rhom row
+  std::vector<int> cls_tracers[NCLS];
+
+  // Buffers.
+  long long ld = 0;
+  bool finished = false;
+  bool user_buffers = false;
+  double* in = nullptr;
+  double* out = nullptr;
+  DevBuf<double> in_own, out_own;
+  DevBuf<int> d_trcr_row, d_trcr_prob, d_cls_tracers[NCLS];
+  DevBuf<int> d_lvlptr, d_kid0, d_kid1;
+  std::vector<DevBuf<BlockDev> > d_blocks;   // per tier
+  DevBuf<dev::NodeConst> d_nc;
+  std::vector<DevBuf<double> > d_rhom_tier;  // leaf rhom of tiers >= 1
+  std::vector<DevBuf<double> > d_rec, d_sol; // records / solved masses, tiers >= 1
+  std::vector<long long> tier_ld;            // padded leaf counts per tier
+  DevBuf<double> d_qglob, d_caas_scal;
+
+  cudaStream_t stream = 0;
+  cedr_b200_allgather_fn allgather = nullptr;
+  void* allgather_ctx = nullptr;
+  int last_launches = 0;
+};
+
+namespace {
+
+size_t sweep_smem_bytes (const cedr_b200_cdr& c, int tier) {
+  return sizeof(double)*4*static_cast<size_t>(2*c.plan.tiers[tier].max_nl);
+}
+
+template <int CLS, int MODE>
+void launch_sweep (cedr_b200_cdr& c, int tier, const SweepArgs& a) {
+  if (a.ntr == 0 || a.nblocks == 0) return;
+  const size_t smem = sweep_smem_bytes(c, tier);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(sweep_kernel<CLS, MODE>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(std::max<size_t>(smem, 48*1024))));
+    configured = smem;
+  }
+  const long long grid = static_cast<long long>(a.nblocks)*a.ntr;
+  cedr_b200_throw_if(grid > 0x7fffffffLL, "grid too large");
+  sweep_kernel<CLS, MODE><<<static_cast<unsigned>(grid), kThreads, smem, c.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++c.last_launches;
+}
+
+template <int CLS>
+void launch_sweep_mode (cedr_b200_cdr& c, int tier, int mode, const SweepArgs& a) {
+  switch (mode) {
+  case MODE_UP: launch_sweep<CLS, MODE_UP>(c, tier, a); break;
+  case MODE_TOP: launch_sweep<CLS, MODE_TOP>(c, tier, a); break;
+  case MODE_DOWN: launch_sweep<CLS, MODE_DOWN>(c, tier, a); break;
+  }
+}
+
+void launch_sweep_any (cedr_b200_cdr& c, int cls, int tier, int mode, const SweepArgs& a) {
+  switch (cls) {
+  case CLS_ST: launch_sweep_mode<CLS_ST>(c, tier, mode, a); break;
+  case CLS_CST: launch_sweep_mode<CLS_CST>(c, tier, mode, a); break;
+  case CLS_T: launch_sweep_mode<CLS_T>(c, tier, mode, a); break;
+  case CLS_CT: launch_sweep_mode<CLS_CT>(c, tier, mode, a); break;
+  case CLS_NN: launch_sweep_mode<CLS_NN>(c, tier, mode, a); break;
+  case CLS_CNN: launch_sweep_mode<CLS_CNN>(c, tier, mode, a); break;
+  case CLS_CAAS:
+    if (mode == MODE_UP) launch_sweep<CLS_CAAS, MODE_UP>(c, tier, a);
+    else launch_sweep<CLS_CAAS, MODE_TOP>(c, tier, a);
+    break;
+  }
+}
+
+SweepArgs base_args (cedr_b200_cdr& c, int cls, int tier) {
+  SweepArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.blocks = c.d_blocks[tier].p;
+  a.nblocks = static_cast<int>(c.plan.tiers[tier].blocks.size());
+  a.lvlptr = c.d_lvlptr.p;
+  a.kid0 = c.d_kid0.p;
+  a.kid1 = c.d_kid1.p;
+  a.nc = c.d_nc.p;
+  a.tier0 = tier == 0;
+  if (tier == 0) {
+    a.in = c.in;
+    a.in_ld = c.ld;
+    a.out = c.out;
+    a.out_ld = c.ld;
+  } else {
+    a.in = c.d_rec[tier].p;
+    a.in_ld = c.tier_ld[tier];
+    a.out = c.d_sol[tier].p;
+    a.out_ld = c.tier_ld[tier];
+  }
+  a.trcr_row = c.d_trcr_row.p;
+  a.trcr_prob = c.d_trcr_prob.p;
+  const int ntiers = static_cast<int>(c.plan.tiers.size());
+  if (tier + 1 < ntiers) {
+    a.rec_out = c.d_rec[tier+1].p;
+    a.rec_ld = c.tier_ld[tier+1];
+    a.sol_in = c.d_sol[tier+1].p;
+    a.sol_in_ld = c.tier_ld[tier+1];
+  }
+  a.tracers = c.d_cls_tracers[cls].p;
+  a.ntr = static_cast<int>(c.cls_tracers[cls].size());
+  a.prefer_mass_con = c.prefer_mass_con;
+  a.qglob = c.d_qglob.p;
+  a.caas_scal = c.d_caas_scal.p;
+  return a;
+}
+
+void run_rhom (cedr_b200_cdr& c) {
+  const int ntiers = static_cast<int>(c.plan.tiers.size());
+  for (int k = 0; k < ntiers; ++k) {
+    RhomArgs a;
+    a.blocks = c.d_blocks[k].p;
+    a.nblocks = static_cast<int>(c.plan.tiers[k].blocks.size());
+    a.lvlptr = c.d_lvlptr.p;
+    a.kid0 = c.d_kid0.p;
+    a.kid1 = c.d_kid1.p;
+    a.in = k == 0 ? c.in : c.d_rhom_tier[k].p;
+    a.root_out = k + 1 < ntiers ? c.d_rhom_tier[k+1].p : nullptr;
+    a.nc = c.d_nc.p;
+    const size_t smem = sizeof(double)*2*static_cast<size_t>(c.plan.tiers[k].max_nl);
+    rhom_kernel<<<a.nblocks, kThreads, smem, c.stream>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+    ++c.last_launches;
+  }
+}
+
+void run_qlt (cedr_b200_cdr& c) {
+  cedr_b200_throw_if(c.nranks > 1, "multi-rank QLT::run is not wired up yet");
+  const int ntiers = static_cast<int>(c.plan.tiers.size());
+  const int top = ntiers - 1;
+  run_rhom(c);
+  for (int cls = 0; cls < CLS_CAAS; ++cls) {
+    if (c.cls_tracers[cls].empty()) continue;
+    for (int k = 0; k < top; ++k)
+      launch_sweep_any(c, cls, k, MODE_UP, base_args(c, cls, k));
+    launch_sweep_any(c, cls, top, MODE_TOP, base_args(c, cls, top));
+    for (int k = top - 1; k >= 0; --k)
+      launch_sweep_any(c, cls, k, MODE_DOWN, base_args(c, cls, k));
+  }
+}
+
+void run_caas (cedr_b200_cdr& c) {
+  cedr_b200_throw_if(c.nranks > 1, "multi-rank CAAS::run is not wired up yet");
+  cedr_b200_throw_if(c.caas_sum_mode != CEDR_B200_CAAS_SUM_TREE,
+                     "CAAS sequential-order sums are not implemented yet");
+  const int ntiers = static_cast<int>(c.plan.tiers.size());
+  const int top = ntiers - 1;
+  for (int k = 0; k < top; ++k)
+    launch_sweep_any(c, CLS_CAAS, k, MODE_UP, base_args(c, CLS_CAAS, k));
+  launch_sweep_any(c, CLS_CAAS, top, MODE_TOP, base_args(c, CLS_CAAS, top));
+  const int nt = static_cast<int>(c.trcr_prob.size());
+  const long long n = static_cast<long long>(c.nlcl)*nt;
+  const int grid = static_cast<int>(std::min<long long>((n + kThreads - 1)/kThreads, 148*32));
+  caas_adjust_kernel<<<grid, kThreads, 0, c.stream>>>(c.in, c.ld, c.nlcl, c.d_trcr_row.p,
+                                                      c.d_caas_scal.p, nt);
+  CUDA_CHECK(cudaGetLastError());
+  ++c.last_launches;
+}
+
+void build_plan (cedr_b200_cdr& c) {
+  c.plan.build(c.ncells, static_cast<int>(c.tree_cellidx.size()), c.tree_root,
+               c.tree_kids.data(), c.tree_cellidx.data(),
+               c.tree_rank.empty() ? nullptr : c.tree_rank.data(), c.max_block_leaves);
+  c.gci2lci.clear();
+  c.nlcl = 0;
+  for (int i = 0; i < c.ncells; ++i)
+    if (c.plan.leaf_rank[i] == c.rank) {
+      c.gci2lci[c.plan.lci2gci[i]] = i;
+      ++c.nlcl;
+    }
+}
+
+void get_buffers_sizes (cedr_b200_cdr& c, size_t& b1, size_t& b2) {
+  cedr_b200_throw_if(c.declaring, "end_tracer_declarations must be called first.");
+  b1 = static_cast<size_t>(c.nrows)*c.ld;
+  b2 = c.is_caas ? 0 : c.trcr_prob.size()*static_cast<size_t>(c.ld);
+}
+
+void finish_setup (cedr_b200_cdr& c) {
+  cedr_b200_throw_if(c.declaring, "end_tracer_declarations must be called first.");
+  if (c.finished) return;
+  size_t b1, b2;
+  get_buffers_sizes(c, b1, b2);
+  if (! c.user_buffers) {
+    c.in_own.alloc(b1);
+    c.out_own.alloc(b2);
+    c.in = c.in_own.p;
+    c.out = c.out_own.p;
+    // Rows are padded to ld; keep the padding defined.
+    CUDA_CHECK(cudaMemsetAsync(c.in, 0, b1*sizeof(double), c.stream));
+    if (b2) CUDA_CHECK(cudaMemsetAsync(c.out, 0, b2*sizeof(double), c.stream));
+  }
+  if (c.is_caas) c.out = c.in;
+  const int nt = static_cast<int>(c.trcr_prob.size());
+  c.d_trcr_row.upload(c.trcr_row);
+  c.d_trcr_prob.upload(c.trcr_prob);
+  for (int k = 0; k < NCLS; ++k) c.d_cls_tracers[k].upload(c.cls_tracers[k]);
+  c.d_lvlptr.upload(c.plan.dev_lvlptr);
+  c.d_kid0.upload(c.plan.dev_kid0);
+  c.d_kid1.upload(c.plan.dev_kid1);
+  const int ntiers = static_cast<int>(c.plan.tiers.size());
+  c.d_blocks = std::vector<DevBuf<BlockDev> >(ntiers);
+  c.d_rhom_tier = std::vector<DevBuf<double> >(ntiers);
+  c.d_rec = std::vector<DevBuf<double> >(ntiers);
+  c.d_sol = std::vector<DevBuf<double> >(ntiers);
+  c.tier_ld.assign(ntiers, 0);
+  for (int k = 0; k < ntiers; ++k) {
+    const Tier& tier = c.plan.tiers[k];
+    std::vector<BlockDev> hb(tier.blocks.size());
+    for (size_t b = 0; b < hb.size(); ++b) {
+      const Block& blk = tier.blocks[b];
+      const Shape& sh = c.plan.shapes[blk.shape];
+      hb[b].leaf0 = blk.leaf0;
+      hb[b].nl = blk.nl;
+      hb[b].ni = sh.ni;
+      hb[b].nlev = sh.nlev;
+      hb[b].lvlptr_off = sh.dev_lvlptr_off;
+      hb[b].kid_off = sh.dev_kid_off;
+      hb[b].ibase = blk.ibase;
+      hb[b].pad = 0;
+    }
+    c.d_blocks[k].upload(hb);
+    c.tier_ld[k] = k == 0 ? c.ld : round_up(tier.nleaves, 16);
+    if (k > 0) {
+      c.d_rhom_tier[k].alloc(c.tier_ld[k]);
+      c.d_rec[k].alloc(static_cast<size_t>(4)*nt*c.tier_ld[k]);
+      c.d_sol[k].alloc(static_cast<size_t>(nt)*c.tier_ld[k]);
+    }
+  }
+  c.d_nc.alloc(std::max(1, c.plan.ninternal));
+  c.d_qglob.alloc(2*static_cast<size_t>(nt));
+  c.d_caas_scal.alloc(2*static_cast<size_t>(nt));
+  c.finished = true;
+}
+
+void fill_1d_tree (cedr_b200_cdr& c, int ncells, bool imbalanced) {
+  make_bisection_tree(ncells, imbalanced, c.tree_kids, c.tree_cellidx);
+  c.tree_root = 0;
+  c.tree_rank.assign(c.tree_cellidx.size(), 0);
+  if (c.nranks > 1) {
+    // oned::Mesh::rank, contiguous decomposition (cedr_tree.cpp:366-369).
+    for (size_t i = 0; i < c.tree_cellidx.size(); ++i)
+      if (c.tree_cellidx[i] >= 0)
+        c.tree_rank[i] = std::min<int64_t>(c.nranks - 1,
+                                           c.tree_cellidx[i]/(ncells/c.nranks));
+  }
+}
+
+void require_device () {
+  int n = 0;
+  const cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    throw std::runtime_error("cedr_b200: no usable CUDA device (there is no CPU fallback)");
+}
+
+} // namespace
+
+extern "C" {
+
+const char* cedr_b200_last_error (void) { return g_err.c_str(); }
+
+int cedr_b200_version (void) { return 100; }
+
+int cedr_b200_device_available (void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
+}
+
+int cedr_b200_qlt_create (cedr_b200_cdr** out, int ncells, int nnodes, int root,
+                          const int* kids, const int64_t* cellidx, const int* node_rank,
+                          int prefer, int rank, int nranks) {
+  return guarded([&] {
+    cedr_b200_throw_if(! out, "null output pointer");
+    require_device();
+    std::unique_ptr<cedr_b200_cdr> c(new cedr_b200_cdr);
+    c->rank = rank;
+    c->nranks = nranks;
+    c->prefer_mass_con = prefer != 0;
+    c->ncells = ncells;
+    cedr_b200_throw_if(nnodes < 1 || ! kids || ! cellidx, "bad tree arrays");
+    c->tree_kids.assign(kids, kids + 2*static_cast<size_t>(nnodes));
+    c->tree_cellidx.assign(cellidx, cellidx + nnodes);
+    if (node_rank) c->tree_rank.assign(node_rank, node_rank + nnodes);
+    c->tree_root = root;
+    build_plan(*c);
+    cedr_b200_throw_if(c->nlcl == 0, "QLT does not support 0 cells on a rank.");
+    *out = c.release();
+  });
+}
+
+int cedr_b200_qlt_create_1d (cedr_b200_cdr** out, int ncells, int imbalanced,
+                             int prefer, int rank, int nranks) {
+  return guarded([&] {
+    cedr_b200_throw_if(! out, "null output pointer");
+    require_device();
+    cedr_b200_throw_if(nranks > ncells, "#GIDs < #ranks is not supported.");
+    std::unique_ptr<cedr_b200_cdr> c(new cedr_b200_cdr);
+    c->rank = rank;
+    c->nranks = nranks;
+    c->prefer_mass_con = prefer != 0;
+    c->ncells = ncells;
+    fill_1d_tree(*c, ncells, imbalanced != 0);
+    build_plan(*c);
+    cedr_b200_throw_if(c->nlcl == 0, "QLT does not support 0 cells on a rank.");
+    *out = c.release();
+  });
+}
+
+int cedr_b200_caas_create (cedr_b200_cdr** out, int nlclcells, int sum_mode,
+                           int64_t cell0, int64_t ncells_global, int rank, int nranks) {
+  return guarded([&] {
+    cedr_b200_throw_if(! out, "null output pointer");
+    require_device();
+    cedr_b200_throw_if(nlclcells == 0, "CAAS does not support 0 cells on a rank.");
+    cedr_b200_throw_if(nranks > 1, "multi-rank CAAS is not wired up yet");
+    cedr_b200_throw_if(cell0 != 0 || ncells_global != nlclcells,
+                       "one rank: cell0 must be 0 and ncells_global == nlclcells");
+    std::unique_ptr<cedr_b200_cdr> c(new cedr_b200_cdr);
+    c->is_caas = true;
+    c->rank = rank;
+    c->nranks = nranks;
+    c->caas_sum_mode = sum_mode;
+    c->ncells = nlclcells;
+    fill_1d_tree(*c, nlclcells, false);
+    build_plan(*c);
+    *out = c.release();
+  });
+}
+
+int cedr_b200_destroy (cedr_b200_cdr* c) {
+  return guarded([&] { delete c; });
+}
+
+int cedr_b200_set_max_block_leaves (cedr_b200_cdr* c, int m) {
+  return guarded([&] {
+    cedr_b200_throw_if(c->finished, "set_max_block_leaves must precede finish_setup");
+    cedr_b200_throw_if(m < 2 || m > 2048, "max_block_leaves must be in [2, 2048]");
+    c->max_block_leaves = m;
+    build_plan(*c);
+  });
+}
+
+int cedr_b200_declare_tracer (cedr_b200_cdr* c, int problem_type, int rhomidx) {
+  return guarded([&] {
+    cedr_b200_throw_if(! c->declaring, "end_tracer_declarations was already called; "
+                       "it is an error to call declare_tracer now.");
+    cedr_b200_throw_if(rhomidx > 0, "rhomidx > 0 is not supported yet.");
+    if (c->is_caas) {
+      cedr_b200_throw_if(! (problem_type & CEDR_B200_SHAPEPRESERVE),
+                         "CAAS does not support ! shapepreserve yet.");
+      c->trcr_prob.push_back(problem_type);
+      c->trcr_cls.push_back(CLS_CAAS);
+      if (problem_type & CEDR_B200_CONSERVE) c->caas_need_conserve = true;
+    } else {
+      const int cls = qlt_class_of(problem_type);
+      cedr_b200_throw_if(cls < 0, "Invalid problem type.");
+      c->trcr_prob.push_back(qlt_canonical_type(cls));
+      c->trcr_cls.push_back(cls);
+    }
+  });
+}
+
+int cedr_b200_end_tracer_declarations (cedr_b200_cdr* c) {
+  return guarded([&] {
+    cedr_b200_throw_if(! c->declaring, "end_tracer_declarations was already called.");
+    if (c->is_caas)
+      cedr_b200_throw_if(c->trcr_prob.size() == 0, "#tracers is 0.");
+    const int nt = static_cast<int>(c->trcr_prob.size());
+    c->trcr_row.resize(nt);
+    int row = 1; // row 0 is rhom
+    for (int k = 0; k < NCLS; ++k) c->cls_tracers[k].clear();
+    for (int t = 0; t < nt; ++t) {
+      c->trcr_row[t] = row;
+      const int cls = c->trcr_cls[t];
+      row += c->is_caas ? (c->caas_need_conserve ? 4 : 3) : qlt_l2r_words(cls);
+      c->cls_tracers[cls].push_back(t);
+    }
+    c->nrows = row;
+    c->ld = round_up(c->is_caas ? c->nlcl : c->ncells, 16);
+    c->declaring = false;
+  });
+}
+
+int cedr_b200_get_buffers_sizes (cedr_b200_cdr* c, size_t* b1, size_t* b2) {
+  return guarded([&] { get_buffers_sizes(*c, *b1, *b2); });
+}
+
+int cedr_b200_set_buffers (cedr_b200_cdr* c, double* b1, double* b2) {
+  return guarded([&] {
+    cedr_b200_throw_if(c->declaring, "end_tracer_declarations must be called first.");
+    cedr_b200_throw_if(c->finished, "set_buffers must precede finish_setup");
+    c->in = b1;
+    c->out = b2;
+    c->user_buffers = true;
+  });
+}
+
+int cedr_b200_finish_setup (cedr_b200_cdr* c) {
+  return guarded([&] { finish_setup(*c); });
+}
+
+int cedr_b200_get_problem_type (const cedr_b200_cdr* c, int tracer_idx, int* type) {
+  return guarded([&] {
+    cedr_b200_throw_if(tracer_idx < 0 ||
+                       tracer_idx >= static_cast<int>(c->trcr_prob.size()),
+                       "tracer_idx is out of bounds: " << tracer_idx);
+    *type = c->trcr_prob[tracer_idx];
+  });
+}
+
+int cedr_b200_get_num_tracers (const cedr_b200_cdr* c, int* n) {
+  return guarded([&] { *n = static_cast<int>(c->trcr_prob.size()); });
+}
+
+int cedr_b200_run (cedr_b200_cdr* c) {
+  return guarded([&] {
+    cedr_b200_throw_if(! c->finished, "finish_setup must be called before run.");
+    c->last_launches = 0;
+    if (c->is_caas) run_caas(*c); else run_qlt(*c);
+  });
+}
+
+int cedr_b200_print (const cedr_b200_cdr* c, char* buf, size_t bufsize) {
+  return guarded([&] {
+    std::stringstream ss;
+    ss << (c->is_caas ? "CAAS" : "QLT") << " pid " << c->rank << ": ncells " << c->ncells
+       << " #levels " << c->plan.nlevels_ref << " #tiers " << c->plan.tiers.size();
+    for (size_t k = 0; k < c->plan.tiers.size(); ++k)
+      ss << "\n  tier " << k << ": " << c->plan.tiers[k].nleaves << " leaves, "
+         << c->plan.tiers[k].blocks.size() << " blocks (max "
+         << c->plan.tiers[k].max_nl << " leaves)";
+    ss << "\n";
+    const std::string s = ss.str();
+    if (buf && bufsize) {
+      std::strncpy(buf, s.c_str(), bufsize - 1);
+      buf[bufsize - 1] = 0;
+    }
+  });
+}
+
+int cedr_b200_nlclcells (const cedr_b200_cdr* c, int* n) {
+  return guarded([&] { *n = c->nlcl; });
+}
+
+int cedr_b200_get_owned_glblcells (const cedr_b200_cdr* c, int64_t* gcis) {
+  return guarded([&] {
+    // One rank owns all leaves and lci is the DFS leaf order
+    // (cedr_qlt.cpp:243-256).
+    int k = 0;
+    for (int i = 0; i < c->ncells; ++i)
+      if (c->plan.leaf_rank[i] == c->rank) gcis[k++] = c->plan.lci2gci[i];
+  });
+}
+
+int cedr_b200_gci2lci (const cedr_b200_cdr* c, int64_t gci, int* lci) {
+  return guarded([&] {
+    const auto it = c->gci2lci.find(gci);
+    cedr_b200_throw_if(it == c->gci2lci.end(), "gci " << gci << " not in gci2lci map.");
+    *lci = it->second;
+  });
+}
+
+int cedr_b200_get_device_op (cedr_b200_cdr* c, cedr_b200_device_op* op) {
+  return guarded([&] {
+    cedr_b200_throw_if(! c->finished, "finish_setup must be called first.");
+    op->in = c->in;
+    op->out = c->out;
+    op->ld = c->ld;
+    op->trcr_row = c->d_trcr_row.p;
+    op->trcr_prob = c->d_trcr_prob.p;
+    op->ntracers = static_cast<int>(c->trcr_prob.size());
+    op->nlclcells = c->nlcl;
+    op->is_caas = c->is_caas;
+    op->reserved = c->caas_need_conserve;
+  });
+}
+
+int cedr_b200_set_rhom_bulk (cedr_b200_cdr* c, const double* rhom) {
+  return guarded([&] {
+    cedr_b200_throw_if(! c->finished, "finish_setup must be called first.");
+    CUDA_CHECK(cudaMemcpyAsync(c->in, rhom, sizeof(double)*c->nlcl,
+                               cudaMemcpyDeviceToDevice, c->stream));
+  });
+}
+
+int cedr_b200_set_Qm_bulk (cedr_b200_cdr* c, int t0, int nt, int64_t lda,
+                           const double* qm, const double* qm_min,
+                           const double* qm_max, const double* qm_prev) {
+  return guarded([&] {
+    cedr_b200_throw_if(! c->finished, "finish_setup must be called first.");
+    cedr_b200_throw_if(t0 < 0 || nt < 0 ||
+                       t0 + nt > static_cast<int>(c->trcr_prob.size()),
+                       "tracer range out of bounds");
+    if (nt == 0) return;
+    bool need_prev = c->is_caas && c->caas_need_conserve;
+    for (int t = t0; t < t0 + nt; ++t) need_prev |= (c->trcr_prob[t] & 1) != 0;
+    cedr_b200_throw_if(need_prev && ! qm_prev && ! c->is_caas,
+                       "Qm_prev was not provided to set_Q.");
+    const long long n = static_cast<long long>(c->nlcl)*nt;
+    const int grid = static_cast<int>(std::min<long long>((n + kThreads - 1)/kThreads,
+                                                          148*32));
+    set_qm_bulk_kernel<<<grid, kThreads, 0, c->stream>>>(
+      c->in, c->ld, c->nlcl, c->d_trcr_row.p, c->d_trcr_prob.p, t0, nt, lda, qm,
+      qm_min, qm_max, qm_prev, c->is_caas && c->caas_need_conserve);
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+int cedr_b200_get_Qm_bulk (cedr_b200_cdr* c, int t0, int nt, int64_t lda, double* qm) {
+  return guarded([&] {
+    cedr_b200_throw_if(! c->finished, "finish_setup must be called first.");
+    cedr_b200_throw_if(t0 < 0 || nt < 0 ||
+                       t0 + nt > static_cast<int>(c->trcr_prob.size()),
+                       "tracer range out of bounds");
+    if (nt == 0) return;
+    const long long n = static_cast<long long>(c->nlcl)*nt;
+    const int grid = static_cast<int>(std::min<long long>((n + kThreads - 1)/kThreads,
+                                                          148*32));
+    get_qm_bulk_kernel<<<grid, kThreads, 0, c->stream>>>(
+      c->is_caas ? c->in : c->out, c->ld, c->nlcl, c->d_trcr_row.p, c->is_caas, t0,
+      nt, lda, qm);
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+int cedr_b200_set_stream (cedr_b200_cdr* c, void* s) {
+  return guarded([&] { c->stream = static_cast<cudaStream_t>(s); });
+}
+
+int cedr_b200_synchronize (cedr_b200_cdr* c) {
+  return guarded([&] { CUDA_CHECK(cudaStreamSynchronize(c->stream)); });
+}
+
+int cedr_b200_set_allgather (cedr_b200_cdr* c, cedr_b200_allgather_fn fn, void* ctx) {
+  return guarded([&] { c->allgather = fn; c->allgather_ctx = ctx; });
+}
+
+int cedr_b200_last_run_launches (const cedr_b200_cdr* c, int* n) {
+  return guarded([&] { *n = c->last_launches; });
+}
+
+int cedr_b200_plan_info (const cedr_b200_cdr* c, int* ntiers, int* nblocks0,
+                         int* max_block_leaves, int* nlevels_ref) {
+  return guarded([&] {
+    if (ntiers) *ntiers = static_cast<int>(c->plan.tiers.size());
+    if (nblocks0) *nblocks0 = static_cast<int>(c->plan.tiers[0].blocks.size());
+    if (max_block_leaves) *max_block_leaves = c->plan.tiers[0].max_nl;
+    if (nlevels_ref) *nlevels_ref = c->plan.nlevels_ref;
+  });
+}
+
+int cedr_b200_make_1d_tree (int ncells, int imbalanced, int* kids_host,
+                            int64_t* cellidx_host) {
+  return guarded([&] {
+    std::vector<int> kids;
+    std::vector<int64_t> cellidx;
+    make_bisection_tree(ncells, imbalanced != 0, kids, cellidx);
+    std::copy(kids.begin(), kids.end(), kids_host);
+    std::copy(cellidx.begin(), cellidx.end(), cellidx_host);
+  });
+}
+
+int cedr_b200_plan_probe (int ncells, int nnodes, int root, const int* kids,
+                          const int64_t* cellidx, int max_block_leaves,
+                          int64_t* lci2gci_host, int* ntiers,
+                          int* nblocks_per_tier_host, int* nshapes, int* nlevels_ref,
+                          int64_t* idsum) {
+  return guarded([&] {
+    Plan plan;
+    plan.build(ncells, nnodes, root, kids, cellidx, nullptr, max_block_leaves);
+    if (lci2gci_host) std::copy(plan.lci2gci.begin(), plan.lci2gci.end(), lci2gci_host);
+    if (ntiers) *ntiers = static_cast<int>(plan.tiers.size());
+    if (nshapes) *nshapes = static_cast<int>(plan.shapes.size());
+    if (nlevels_ref) *nlevels_ref = plan.nlevels_ref;
+    cedr_b200_throw_if(plan.tiers.size() > 64, "more than 64 tiers");
+    // Sum the cell ids through the plan, exactly as the sweep kernels walk it.
+    std::vector<int64_t> leaf(plan.lci2gci);
+    std::vector<int> internal_used(std::max(1, plan.ninternal), 0);
+    for (size_t k = 0; k < plan.tiers.size(); ++k) {
+      const Tier& tier = plan.tiers[k];
+      if (nblocks_per_tier_host)
+        nblocks_per_tier_host[k] = static_cast<int>(tier.blocks.size());
+      cedr_b200_throw_if(static_cast<int>(leaf.size()) != tier.nleaves,
+                         "tier leaf count mismatch");
+      std::vector<int> leaf_used(tier.nleaves, 0);
+      std::vector<int64_t> next(tier.blocks.size());
+      for (size_t b = 0; b < tier.blocks.size(); ++b) {
+        const Block& blk = tier.blocks[b];
+        const Shape& sh = plan.shapes[blk.shape];
+        cedr_b200_throw_if(sh.nl != blk.nl || sh.ni != blk.nl - 1, "shape mismatch");
+        std::vector<int64_t> v(sh.nl + sh.ni);
+        std::vector<int> used(sh.nl + sh.ni, 0);
+        for (int i = 0; i < sh.nl; ++i) {
+          v[i] = leaf[blk.leaf0 + i];
+          ++leaf_used[blk.leaf0 + i];
+        }
+        for (int l = 0; l < sh.nlev; ++l)
+          for (int j = sh.lvlptr[l]; j < sh.lvlptr[l+1]; ++j) {
+            cedr_b200_throw_if(sh.kid0[j] >= sh.nl + j || sh.kid1[j] >= sh.nl + j,
+                               "kid not computed before its parent");
+            v[sh.nl + j] = v[sh.kid0[j]] + v[sh.kid1[j]];
+            ++used[sh.kid0[j]];
+            ++used[sh.kid1[j]];
+            ++internal_used[blk.ibase + j];
+          }
+        for (int i = 0; i + 1 < sh.nl + sh.ni; ++i)
+          cedr_b200_throw_if(used[i] != 1, "block node not used exactly once");
+        next[b] = v[sh.nl + sh.ni - 1];
+      }
+      for (int i = 0; i < tier.nleaves; ++i)
+        cedr_b200_throw_if(leaf_used[i] != 1, "tier leaf not used exactly once");
+      leaf.swap(next);
+    }
+    cedr_b200_throw_if(leaf.size() != 1, "top tier must have one block");
+    for (int i = 0; i < plan.ninternal; ++i)
+      cedr_b200_throw_if(internal_used[i] != 1, "internal node not used exactly once");
+    if (idsum) *idsum = leaf[0];
+  });
+}
+
+int cedr_b200_fill_headline (int ncells, int nt, int64_t lda, int config_id,
+                             double* rhom, double* qm_min, double* qm, double* qm_max,
+                             double* qm_prev, void* stream) {
+  return guarded([&] {
+    require_device();
+    const long long n = static_cast<long long>(ncells)*nt;
+    const int grid = static_cast<int>(std::min<long long>((n + kThreads - 1)/kThreads,
+                                                          148*32));
+    fill_headline_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      ncells, nt, lda, 0xCED20000ull + static_cast<unsigned long long>(config_id),
+      rhom, qm_min, qm, qm_max, qm_prev);
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+} // extern "C"

@@ -1,0 +1,385 @@
+// Sweep kernels of the B200 CEDR hot path (generic-shape version).
+//
+// One CTA sweeps one BLOCK (a subtree of <= max_block_leaves leaves, see
+// tree_plan.h) for one tracer, entirely in shared memory:
+//   UP    leaves -> block-root record            (QLT::l2r_combine_kid_data,
+//                                                 cedr_qlt.cpp:339-430)
+//   TOP   UP + root_compute (cedr_qlt.cpp:441-476) + the block's down-sweep
+//   DOWN  recompute the block's up-sweep, then solve every node problem from the
+//         block root's solved mass down to the leaves (QLT::r2l_solve_qp,
+//         cedr_qlt.cpp:490-604)
+// The reference runs one launch per tree level over a slot-major AoS buffer
+// (cedr_qlt.cpp:349-387, 538-566). Here leaf data are SoA with the cell index
+// fastest, so a block's leaves are one contiguous, coalesced segment per field,
+// and the whole subtree lives in shared memory between its up- and down-sweep.
+#ifndef CEDR_B200_KERNELS_CUH
+#define CEDR_B200_KERNELS_CUH
+
+#include <cstdint>
+
+#include "node_solve.cuh"
+
+namespace cedr_b200 {
+
+struct BlockDev {
+  int leaf0, nl, ni, nlev;
+  int lvlptr_off, kid_off, ibase, pad;
+};
+
+// Tracer classes: the six canonical QLT problem classes in the reference's
+// order (cedr_qlt_inl.hpp:101-108), plus CAAS.
+enum { CLS_ST = 0, CLS_CST = 1, CLS_T = 2, CLS_CT = 3, CLS_NN = 4, CLS_CNN = 5,
+       CLS_CAAS = 6, NCLS = 7 };
+enum { MODE_UP = 0, MODE_TOP = 1, MODE_DOWN = 2 };
+
+struct SweepArgs {
+  const BlockDev* blocks;
+  int nblocks;
+  const int* lvlptr;
+  const int* kid0;
+  const int* kid1;
+  const dev::NodeConst* nc;
+  // Leaf input: tier 0 reads the caller-facing rows (row r of cell c at
+  // in[r*in_ld + c], first row of tracer t = trcr_row[t]); higher tiers read the
+  // records written by the tier below, field f of tracer t at
+  // in[(4*t + f)*in_ld + leaf].
+  const double* in;
+  long long in_ld;
+  int tier0;
+  const int* trcr_row;
+  const int* trcr_prob;
+  // UP: block-root records for the next tier, [(4*t + f)*rec_ld + block].
+  double* rec_out;
+  long long rec_ld;
+  // DOWN: the next tier's solved masses, [t*sol_in_ld + block].
+  const double* sol_in;
+  long long sol_in_ld;
+  // TOP/DOWN: solved leaf masses, [t*out_ld + leaf] (tier 0: the r2l buffer).
+  double* out;
+  long long out_ld;
+  const int* tracers;   // tracer ids of this launch's class
+  int ntr;
+  int prefer_mass_con;
+  double* qglob;        // [2*t], [2*t+1]: global q_min, q_max (consistent-only)
+  double* caas_scal;    // [2*t]: mode (-1, 0, +1), [2*t+1]: fac
+};
+
+template <int CLS, int MODE>
+__global__ void __launch_bounds__(256)
+sweep_kernel (const SweepArgs a) {
+  extern __shared__ double sm[];
+  constexpr bool caas = CLS == CLS_CAAS;
+  constexpr bool nonneg = CLS == CLS_NN || CLS == CLS_CNN;
+  constexpr bool consistent_only = CLS == CLS_T || CLS == CLS_CT;
+  constexpr bool has_prev = CLS == CLS_CST || CLS == CLS_CT || CLS == CLS_CNN || caas;
+  // Which fields this mode needs in shared memory. The down-sweep of the
+  // bounded classes needs (min, Qm, max); consistent-only and nonnegative
+  // classes need only Qm (their bounds are global q * rhom, resp. [0, b]).
+  constexpr bool need_bounds = ! nonneg && (MODE != MODE_DOWN || ! consistent_only);
+  constexpr bool need_prev = has_prev && MODE != MODE_DOWN;
+
+  const int b = blockIdx.x % a.nblocks;
+  const int t = a.tracers[blockIdx.x / a.nblocks];
+  const BlockDev B = a.blocks[b];
+  const int nn = B.nl + B.ni;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  double* const f0 = sm;
+  double* const f1 = f0 + nn;
+  double* const f2 = f1 + nn;
+  double* const f3 = f2 + nn; // Qm_prev sums on the way up, solved masses down
+
+  { // Leaves.
+    const double* p0, * p1, * p2, * p3;
+    if (a.tier0) {
+      const double* base = a.in + (long long) a.trcr_row[t]*a.in_ld + B.leaf0;
+      if (nonneg) {
+        p1 = base; p3 = base + a.in_ld; p0 = p2 = nullptr;
+      } else {
+        p0 = base; p1 = base + a.in_ld; p2 = base + 2*a.in_ld; p3 = base + 3*a.in_ld;
+      }
+    } else {
+      const double* base = a.in + (long long) t*4*a.in_ld + B.leaf0;
+      p0 = base; p1 = base + a.in_ld; p2 = base + 2*a.in_ld; p3 = base + 3*a.in_ld;
+    }
+    if (caas && a.tier0) {
+      // CAAS::reduce_locally, cedr_caas.cpp:129-201 through calc_Qm_scalars
+      // (cedr_caas_inl.hpp:44-57): clip, and the four summands. Each enters the
+      // reduction as 0 + value (accumulator start, cedr_caas.cpp:145-151).
+      const bool conserve = a.trcr_prob[t] & 1;
+      for (int i = tid; i < B.nl; i += nth) {
+        const double lo = p0[i], q = p1[i], hi = p2[i];
+        const double term = conserve ? p3[i] : q;
+        const double clip = dev::rmin(hi, dev::rmax(lo, q));
+        f0[i] = 0.0 + lo;
+        f1[i] = 0.0 + clip;
+        f2[i] = 0.0 + hi;
+        f3[i] = 0.0 + term;
+      }
+    } else {
+      for (int i = tid; i < B.nl; i += nth) {
+        if (need_bounds) { f0[i] = p0[i]; f2[i] = p2[i]; }
+        f1[i] = p1[i];
+        if (need_prev) f3[i] = p3[i];
+      }
+    }
+  }
+  __syncthreads();
+
+  // Up-sweep inside the block, level by level (kids before parents).
+  const int* const lvlptr = a.lvlptr + B.lvlptr_off;
+  const int* const kid0 = a.kid0 + B.kid_off;
+  const int* const kid1 = a.kid1 + B.kid_off;
+  for (int l = 0; l < B.nlev; ++l) {
+    const int je = lvlptr[l+1];
+    for (int j = lvlptr[l] + tid; j < je; j += nth) {
+      const int k0 = kid0[j], k1 = kid1[j], me = B.nl + j;
+      if (caas) {
+        // BfbTreeAllReducer: d = 0; d += kid0; d += kid1
+        // (cedr_bfb_tree_allreduce.cpp:115-124).
+        f0[me] = (0.0 + f0[k0]) + f0[k1];
+        f1[me] = (0.0 + f1[k0]) + f1[k1];
+        f2[me] = (0.0 + f2[k0]) + f2[k1];
+        f3[me] = (0.0 + f3[k0]) + f3[k1];
+      } else {
+        if (need_bounds) {
+          if (consistent_only) {
+            f0[me] = dev::rmin(f0[k0], f0[k1]);
+            f2[me] = dev::rmax(f2[k0], f2[k1]);
+          } else {
+            f0[me] = f0[k0] + f0[k1];
+            f2[me] = f2[k0] + f2[k1];
+          }
+        }
+        f1[me] = f1[k0] + f1[k1];
+        if (need_prev) f3[me] = f3[k0] + f3[k1];
+      }
+    }
+    __syncthreads();
+  }
+  const int root = B.ni ? nn - 1 : 0;
+
+  if (MODE == MODE_UP) {
+    if (tid == 0) {
+      double* r = a.rec_out + (long long) t*4*a.rec_ld + b;
+      if (need_bounds) { r[0] = f0[root]; r[2*a.rec_ld] = f2[root]; }
+      r[a.rec_ld] = f1[root];
+      if (need_prev) r[3*a.rec_ld] = f3[root];
+    }
+    return;
+  }
+
+  if (caas) {
+    // MODE_TOP: the four global sums are at the root. CAAS::finish_locally,
+    // cedr_caas.cpp:211-253, scalar part.
+    if (tid == 0) {
+      const double clip_sum = f1[root], term_sum = f3[root];
+      const double m = term_sum - clip_sum;
+      double mode = 0, fac = 0;
+      if (m < 0) {
+        fac = clip_sum - f0[root];
+        if (fac > 0) { fac = m/fac; mode = -1; }
+      } else if (m > 0) {
+        fac = f2[root] - clip_sum;
+        if (fac > 0) { fac = m/fac; mode = 1; }
+      }
+      a.caas_scal[2*t] = mode;
+      a.caas_scal[2*t+1] = fac;
+    }
+    return;
+  }
+
+  double qmin = 0, qmax = 0;
+  if (MODE == MODE_TOP) {
+    // root_compute, cedr_qlt.cpp:441-476.
+    if (consistent_only) {
+      qmin = f0[root];
+      qmax = f2[root];
+      if (tid == 0) { a.qglob[2*t] = qmin; a.qglob[2*t+1] = qmax; }
+    }
+    __syncthreads();
+    if (tid == 0 && ! has_prev) f3[root] = f1[root];
+  } else {
+    if (consistent_only) { qmin = a.qglob[2*t]; qmax = a.qglob[2*t+1]; }
+    if (tid == 0) f3[root] = a.sol_in[(long long) t*a.sol_in_ld + b];
+  }
+  __syncthreads();
+
+  // Down-sweep: parents before kids.
+  const dev::NodeConst* const nc = a.nc + B.ibase;
+  const bool prefer = a.prefer_mass_con != 0;
+  for (int l = B.nlev - 1; l >= 0; --l) {
+    const int je = lvlptr[l+1];
+    for (int j = lvlptr[l] + tid; j < je; j += nth) {
+      const int k0 = kid0[j], k1 = kid1[j], me = B.nl + j;
+      const dev::NodeConst& c = nc[j];
+      const double bm = f3[me];
+      double x0, x1;
+      if (nonneg) {
+        dev::solve_node_nonneg(c, bm, f1[k0], f1[k1], x0, x1);
+      } else if (consistent_only) {
+        // cedr_qlt_inl.hpp:181-188: q bounds scaled by each node's rhom.
+        const double rh0 = c.rh0, rh1 = c.rh1, rh = rh0 + rh1;
+        dev::solve_node_bounded(c, prefer, qmin*rh, f1[me], qmax*rh, bm,
+                                qmin*rh0, f1[k0], qmax*rh0,
+                                qmin*rh1, f1[k1], qmax*rh1, x0, x1);
+      } else {
+        dev::solve_node_bounded(c, prefer, f0[me], f1[me], f2[me], bm,
+                                f0[k0], f1[k0], f2[k0], f0[k1], f1[k1], f2[k1],
+                                x0, x1);
+      }
+      f3[k0] = x0;
+      f3[k1] = x1;
+    }
+    __syncthreads();
+  }
+  double* const o = a.out + (long long) t*a.out_ld + B.leaf0;
+  for (int i = tid; i < B.nl; i += nth) o[i] = f3[i];
+}
+
+// rhom sweep: word 0 of every slot in the reference (cedr_qlt.cpp:356-360),
+// summed kid0 + kid1 up the tree, plus the per-node constants of
+// node_solve.cuh. One CTA per block.
+struct RhomArgs {
+  const BlockDev* blocks;
+  int nblocks;
+  const int* lvlptr;
+  const int* kid0;
+  const int* kid1;
+  const double* in;    // this tier's leaf rhom
+  double* root_out;    // next tier's leaf rhom, [block] (may be null at the top)
+  dev::NodeConst* nc;
+};
+
+__global__ void __launch_bounds__(256)
+rhom_kernel (const RhomArgs a) {
+  extern __shared__ double sm[];
+  const BlockDev B = a.blocks[blockIdx.x];
+  const int nn = B.nl + B.ni;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int i = tid; i < B.nl; i += nth) sm[i] = a.in[B.leaf0 + i];
+  __syncthreads();
+  const int* const lvlptr = a.lvlptr + B.lvlptr_off;
+  const int* const kid0 = a.kid0 + B.kid_off;
+  const int* const kid1 = a.kid1 + B.kid_off;
+  for (int l = 0; l < B.nlev; ++l) {
+    const int je = lvlptr[l+1];
+    for (int j = lvlptr[l] + tid; j < je; j += nth) {
+      const double rh0 = sm[kid0[j]], rh1 = sm[kid1[j]];
+      sm[B.nl + j] = rh0 + rh1;
+      dev::NodeConst c;
+      c.w0 = 1/rh0;
+      c.w1 = 1/rh1;
+      c.q0 = 1/c.w0;
+      c.q1 = 1/c.w1;
+      c.rh0 = rh0;
+      c.rh1 = rh1;
+      a.nc[B.ibase + j] = c;
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && a.root_out) a.root_out[blockIdx.x] = sm[B.ni ? nn - 1 : 0];
+}
+
+// CAAS::finish_locally, cedr_caas.cpp:211-253, per-cell part; also writes the
+// clipped value the reference stores in place during reduce_locally
+// (cedr_caas.cpp:177).
+__global__ void __launch_bounds__(256)
+caas_adjust_kernel (double* data, const long long ld, const int ncells,
+                    const int* trcr_row, const double* scal, const int nt) {
+  const long long n = (long long) ncells*nt;
+  for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
+       k += (long long) gridDim.x*blockDim.x) {
+    const int t = (int) (k / ncells), i = (int) (k % ncells);
+    double* row = data + (long long) trcr_row[t]*ld + i;
+    const double lo = row[0], hi = row[2*ld];
+    double q = dev::rmin(hi, dev::rmax(lo, row[ld]));
+    const double mode = scal[2*t], fac = scal[2*t+1];
+    if (mode < 0) {
+      q += fac*(q - lo);
+      q = dev::rmax(lo, q);
+    } else if (mode > 0) {
+      q += fac*(hi - q);
+      q = dev::rmin(hi, q);
+    }
+    row[ld] = q;
+  }
+}
+
+// Bulk DeviceOp::set_Qm (cedr_qlt_inl.hpp:21-58, cedr_caas_inl.hpp:21-34) from
+// SoA caller arrays a[t*lda + lci].
+__global__ void __launch_bounds__(256)
+set_qm_bulk_kernel (double* in, const long long ld, const int ncells,
+                    const int* trcr_row, const int* trcr_prob, const int t0,
+                    const int nt, const long long lda, const double* qm,
+                    const double* qm_min, const double* qm_max, const double* qm_prev,
+                    const int caas_store_prev) {
+  const long long n = (long long) ncells*nt;
+  for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
+       k += (long long) gridDim.x*blockDim.x) {
+    const int tl = (int) (k / ncells), i = (int) (k % ncells), t = t0 + tl;
+    const long long s = (long long) tl*lda + i;
+    const int pt = trcr_prob[t];
+    double* bd = in + (long long) trcr_row[t]*ld + i;
+    int next;
+    if (pt & 2) {
+      bd[0] = qm_min[s]; bd[ld] = qm[s]; bd[2*ld] = qm_max[s]; next = 3;
+    } else if (pt & 4) {
+      const double rhom = in[i];
+      bd[0] = qm_min[s]/rhom; bd[ld] = qm[s]; bd[2*ld] = qm_max[s]/rhom; next = 3;
+    } else {
+      bd[0] = qm[s]; next = 1;
+    }
+    if ((pt & 1) || caas_store_prev)
+      bd[next*ld] = qm_prev ? qm_prev[s] : __longlong_as_double(0x7ff0000000000000LL);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+get_qm_bulk_kernel (const double* src, const long long ld, const int ncells,
+                    const int* trcr_row, const int is_caas, const int t0,
+                    const int nt, const long long lda, double* qm) {
+  const long long n = (long long) ncells*nt;
+  for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
+       k += (long long) gridDim.x*blockDim.x) {
+    const int tl = (int) (k / ncells), i = (int) (k % ncells), t = t0 + tl;
+    qm[(long long) tl*lda + i] =
+      is_caas ? src[((long long) trcr_row[t] + 1)*ld + i] : src[(long long) t*ld + i];
+  }
+}
+
+// Synthetic workload of SURVEY.md 8(d): splitmix64, U = (z >> 11) * 2^-53.
+__device__ __forceinline__ double splitmix_u (const unsigned long long seed,
+                                              const unsigned long long k) {
+  unsigned long long z = seed + (k + 1ull)*0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30))*0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27))*0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (double) (z >> 11)*0x1.0p-53;
+}
+
+__global__ void __launch_bounds__(256)
+fill_headline_kernel (const int ncells, const int nt, const long long lda,
+                      const unsigned long long seed, double* rhom, double* qm_min,
+                      double* qm, double* qm_max, double* qm_prev) {
+  const long long n = (long long) ncells*nt;
+  for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
+       k += (long long) gridDim.x*blockDim.x) {
+    const int t = (int) (k / ncells), i = (int) (k % ncells);
+    const double rh = 0.5*(1 + splitmix_u(seed, i));
+    if (t == 0) rhom[i] = rh;
+    const unsigned long long p = (unsigned long long) ncells + 4ull*k;
+    const double q_min = 0.1*splitmix_u(seed, p);
+    const double q_max = q_min + splitmix_u(seed, p + 1);
+    const double q = q_min + (q_max - q_min)*(1.4*splitmix_u(seed, p + 2) - 0.2);
+    const double q_prev = q_min + (q_max - q_min)*splitmix_u(seed, p + 3);
+    const long long s = (long long) t*lda + i;
+    qm_min[s] = q_min*rh;
+    qm_max[s] = q_max*rh;
+    qm[s] = q*rh;
+    qm_prev[s] = q_prev*rh;
+  }
+}
+
+} // namespace cedr_b200
+
+#endif

@@ -1,0 +1,269 @@
+#include "tree_plan.h"
+
+#include <algorithm>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+
+namespace cedr_b200 {
+
+namespace {
+
+[[noreturn]] void fail (const std::string& msg) {
+  throw std::logic_error("cedr_b200 tree plan: " + msg);
+}
+
+void bisect (int cs, int ce, bool imbalanced, std::vector<int>& kids,
+             std::vector<int64_t>& cellidx) {
+  // Iterative pre-order emission; a frame remembers where to patch kid links.
+  struct Frame { int cs, ce, parent, which; };
+  std::vector<Frame> st;
+  st.push_back({cs, ce, -1, 0});
+  while (!st.empty()) {
+    const Frame f = st.back();
+    st.pop_back();
+    const int me = static_cast<int>(cellidx.size());
+    kids.push_back(-1);
+    kids.push_back(-1);
+    cellidx.push_back(-1);
+    if (f.parent >= 0) kids[2*f.parent + f.which] = me;
+    const int cn = f.ce - f.cs;
+    if (cn == 1) {
+      cellidx[me] = f.cs;
+      continue;
+    }
+    // cedr_tree.cpp:393-397
+    const int cn0 = (imbalanced && cn > 2) ? cn/3 : cn/2;
+    // Push right first so the left subtree is emitted first (pre-order).
+    st.push_back({f.cs + cn0, f.ce, me, 1});
+    st.push_back({f.cs, f.cs + cn0, me, 0});
+  }
+}
+
+} // namespace
+
+void make_bisection_tree (int ncells, bool imbalanced, std::vector<int>& kids,
+                          std::vector<int64_t>& cellidx) {
+  if (ncells < 1) fail("ncells must be >= 1");
+  kids.clear();
+  cellidx.clear();
+  kids.reserve(2*(2*static_cast<size_t>(ncells) - 1));
+  cellidx.reserve(2*static_cast<size_t>(ncells) - 1);
+  bisect(0, ncells, imbalanced, kids, cellidx);
+}
+
+void Plan::build (int ncells_, int nnodes, int root, const int* kids,
+                  const int64_t* cellidx, const int* rank, int max_block_leaves_) {
+  if (ncells_ < 1) fail("ncells must be >= 1");
+  if (nnodes != 2*ncells_ - 1) fail("a binary tree over ncells leaves has 2*ncells-1 nodes");
+  if (root < 0 || root >= nnodes) fail("root out of range");
+  if (max_block_leaves_ < 2) fail("max_block_leaves must be >= 2");
+  ncells = ncells_;
+  max_block_leaves = max_block_leaves_;
+  tiers.clear();
+  shapes.clear();
+  dev_lvlptr.clear();
+  dev_kid0.clear();
+  dev_kid1.clear();
+
+  // ---- DFS: leaf order (= the reference's lci), post-order, heights.
+  std::vector<int> post;
+  post.reserve(nnodes);
+  std::vector<int> height(nnodes, 0), seen(nnodes, 0);
+  lci2gci.assign(ncells, -1);
+  leaf_rank.assign(ncells, 0);
+  std::vector<int> node_lci(nnodes, -1);
+  {
+    int nleaf = 0;
+    std::vector<std::pair<int,int> > st; // (node, state)
+    st.push_back(std::make_pair(root, 0));
+    while (!st.empty()) {
+      const int n = st.back().first;
+      int& state = st.back().second;
+      const int k0 = kids[2*n], k1 = kids[2*n+1];
+      if (state == 0) {
+        if (seen[n]++) fail("node reachable twice (not a tree)");
+        if ((k0 < 0) != (k1 < 0))
+          fail("every internal node must have exactly 2 kids (cedr_qlt.cpp:355)");
+        if (k0 < 0) {
+          if (nleaf >= ncells) fail("more leaves than ncells");
+          node_lci[n] = nleaf;
+          lci2gci[nleaf] = cellidx[n];
+          leaf_rank[nleaf] = rank ? rank[n] : 0;
+          ++nleaf;
+          post.push_back(n);
+          st.pop_back();
+          continue;
+        }
+        if (k0 >= nnodes || k1 >= nnodes) fail("kid index out of range");
+        state = 1;
+        st.push_back(std::make_pair(k0, 0));
+      } else if (state == 1) {
+        state = 2;
+        st.push_back(std::make_pair(k1, 0));
+      } else {
+        height[n] = 1 + std::max(height[k0], height[k1]);
+        post.push_back(n);
+        st.pop_back();
+      }
+    }
+    if (nleaf != ncells) fail("tree does not have ncells leaves");
+    if (static_cast<int>(post.size()) != nnodes) fail("tree does not reach every node");
+  }
+  nlevels_ref = height[root] + 1;
+
+  // ---- Tiers.
+  // vleaf[n] >= 0: node n is leaf number vleaf[n] of the current tier.
+  std::vector<int> vleaf = node_lci;
+  std::vector<int> vrank(nnodes, 0);
+  for (int n = 0; n < nnodes; ++n)
+    if (node_lci[n] >= 0) vrank[n] = leaf_rank[node_lci[n]];
+  std::vector<int> cnt(nnodes), first(nnodes), local_id(nnodes, -1);
+  std::map<std::vector<int>, int> shape_index;
+  ninternal = 0;
+  int nvleaves = ncells;
+
+  for (int tier_idx = 0; ; ++tier_idx) {
+    if (tier_idx > 256) fail("tree is too deep/unbalanced for the block plan");
+    // cnt/first over the current virtual tree, bottom-up along the post-order.
+    for (size_t i = 0; i < post.size(); ++i) {
+      const int n = post[i];
+      if (vleaf[n] >= 0) { cnt[n] = 1; first[n] = vleaf[n]; }
+      else if (kids[2*n] >= 0 && cnt[kids[2*n]] >= 0 && vleaf[n] != -2) {
+        cnt[n] = cnt[kids[2*n]] + cnt[kids[2*n+1]];
+        first[n] = first[kids[2*n]];
+      }
+    }
+    Tier tier;
+    tier.nleaves = nvleaves;
+    // Cut: maximal subtrees with <= max_block_leaves current-tier leaves, DFS.
+    std::vector<int> block_roots;
+    {
+      std::vector<int> st;
+      st.push_back(root);
+      while (!st.empty()) {
+        const int n = st.back();
+        st.pop_back();
+        if (cnt[n] <= max_block_leaves) { block_roots.push_back(n); continue; }
+        st.push_back(kids[2*n+1]);
+        st.push_back(kids[2*n]);
+      }
+    }
+    for (size_t b = 0; b < block_roots.size(); ++b) {
+      const int broot = block_roots[b];
+      Block blk;
+      blk.leaf0 = first[broot];
+      blk.nl = cnt[broot];
+      // Local topology: DFS inside the block down to the tier's leaves.
+      std::vector<int> internal_post;   // internal nodes, post-order
+      std::vector<int> lheight;         // local heights, parallel to internal_post
+      std::map<int,int> hmap;
+      int nleaf_local = 0;
+      int owner = -2;
+      bool bis = true;
+      {
+        std::vector<std::pair<int,int> > st;
+        st.push_back(std::make_pair(broot, 0));
+        while (!st.empty()) {
+          const int n = st.back().first;
+          int& state = st.back().second;
+          if (vleaf[n] >= 0) {
+            local_id[n] = nleaf_local++;
+            hmap[n] = 0;
+            owner = (owner == -2) ? vrank[n] : (owner == vrank[n] ? owner : -1);
+            st.pop_back();
+            continue;
+          }
+          if (state == 0) { state = 1; st.push_back(std::make_pair(kids[2*n], 0)); }
+          else if (state == 1) { state = 2; st.push_back(std::make_pair(kids[2*n+1], 0)); }
+          else {
+            const int h = 1 + std::max(hmap[kids[2*n]], hmap[kids[2*n+1]]);
+            hmap[n] = h;
+            internal_post.push_back(n);
+            lheight.push_back(h);
+            if (cnt[kids[2*n]] != cnt[n]/2) bis = false;
+            st.pop_back();
+          }
+        }
+      }
+      blk.owner = owner;
+      const int ni = static_cast<int>(internal_post.size());
+      // Order internal nodes by (height, post-order position): stable sort.
+      std::vector<int> ord(ni);
+      for (int i = 0; i < ni; ++i) ord[i] = i;
+      std::stable_sort(ord.begin(), ord.end(),
+                       [&] (int a, int c) { return lheight[a] < lheight[c]; });
+      for (int j = 0; j < ni; ++j) local_id[internal_post[ord[j]]] = blk.nl + j;
+      Shape sh;
+      sh.nl = blk.nl;
+      sh.ni = ni;
+      sh.nlev = ni ? lheight[ord[ni-1]] : 0;
+      sh.bisection = bis;
+      sh.lvlptr.assign(sh.nlev + 1, 0);
+      sh.kid0.resize(ni);
+      sh.kid1.resize(ni);
+      for (int j = 0; j < ni; ++j) {
+        const int n = internal_post[ord[j]];
+        sh.kid0[j] = local_id[kids[2*n]];
+        sh.kid1[j] = local_id[kids[2*n+1]];
+        ++sh.lvlptr[lheight[ord[j]]];
+      }
+      for (int l = 0; l < sh.nlev; ++l) sh.lvlptr[l+1] += sh.lvlptr[l];
+      // Dedupe.
+      std::vector<int> key;
+      key.reserve(2*ni + 1);
+      key.push_back(sh.nl);
+      key.insert(key.end(), sh.kid0.begin(), sh.kid0.end());
+      key.insert(key.end(), sh.kid1.begin(), sh.kid1.end());
+      std::map<std::vector<int>, int>::iterator it = shape_index.find(key);
+      if (it == shape_index.end()) {
+        sh.dev_lvlptr_off = static_cast<int>(dev_lvlptr.size());
+        sh.dev_kid_off = static_cast<int>(dev_kid0.size());
+        dev_lvlptr.insert(dev_lvlptr.end(), sh.lvlptr.begin(), sh.lvlptr.end());
+        dev_kid0.insert(dev_kid0.end(), sh.kid0.begin(), sh.kid0.end());
+        dev_kid1.insert(dev_kid1.end(), sh.kid1.begin(), sh.kid1.end());
+        blk.shape = static_cast<int>(shapes.size());
+        shape_index[key] = blk.shape;
+        shapes.push_back(sh);
+      } else {
+        blk.shape = it->second;
+      }
+      blk.ibase = ninternal;
+      ninternal += ni;
+      tier.max_nl = std::max(tier.max_nl, blk.nl);
+      tier.blocks.push_back(blk);
+    }
+    const bool last = block_roots.size() == 1 && block_roots[0] == root;
+    // The block roots become the next tier's leaves. Nodes strictly inside a
+    // block are retired (marked -2 so cnt is no longer recomputed for them).
+    for (size_t b = 0; b < block_roots.size(); ++b) {
+      std::vector<int> st;
+      st.push_back(block_roots[b]);
+      while (!st.empty()) {
+        const int n = st.back();
+        st.pop_back();
+        if (vleaf[n] < 0 && kids[2*n] >= 0) {
+          st.push_back(kids[2*n]);
+          st.push_back(kids[2*n+1]);
+        }
+        vleaf[n] = -2;
+        cnt[n] = -1;
+      }
+    }
+    for (size_t b = 0; b < block_roots.size(); ++b) {
+      vleaf[block_roots[b]] = static_cast<int>(b);
+      vrank[block_roots[b]] = tier.blocks[b].owner;
+    }
+    nvleaves = static_cast<int>(block_roots.size());
+    tiers.push_back(tier);
+    if (last) break;
+  }
+  if (ninternal != ncells - 1) {
+    std::stringstream ss;
+    ss << "internal error: counted " << ninternal << " internal nodes, expected "
+       << ncells - 1;
+    fail(ss.str());
+  }
+}
+
+} // namespace cedr_b200

@@ -1,0 +1,211 @@
+/* cedr_b200 -- C ABI of the B200-native CEDR property-preservation hot path.
+ *
+ * This is the drop-in boundary for COMPOSE's `cedr::CDR` interface as realised
+ * by QLT (cedr/cedr_qlt.{hpp,cpp}) and CAAS (cedr/cedr_caas.{hpp,cpp}). Each
+ * entry point names the reference interface it replaces; `file:line` are
+ * relative to the reference's cedr/ directory. The C++ mirror of the
+ * reference's classes (compose_b200/cxx/) and the Python front end
+ * (compose_b200/__init__.py) are thin layers over exactly these symbols.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a nonzero code on failure;
+ *     cedr_b200_last_error() then returns a message formatted like the
+ *     reference's cedr_throw_if (cedr_util.hpp:70-77). The C++ mirror re-throws
+ *     it as std::logic_error.
+ *   - all `double*` data pointers are DEVICE pointers unless the name says
+ *     `host`. Sizes are counts of doubles, as in the reference.
+ *   - work is enqueued on the CDR's stream (cedr_b200_set_stream, default: the
+ *     legacy default stream). cedr_b200_run() is asynchronous; the reference's
+ *     run() is synchronous, so the C++ mirror follows it with
+ *     cedr_b200_synchronize().
+ *   - there is no CPU fallback: if no CUDA device is usable, creation fails.
+ */
+#ifndef CEDR_B200_H
+#define CEDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cedr.hpp:29-39, ProblemType */
+enum {
+  CEDR_B200_CONSERVE = 1,
+  CEDR_B200_SHAPEPRESERVE = 2,
+  CEDR_B200_CONSISTENT = 4,
+  CEDR_B200_NONNEGATIVE = 8
+};
+
+/* How CAAS forms its four per-tracer global sums (cedr_caas.cpp:129-209). */
+enum {
+  /* Pairwise in the order of a recursive-bisection tree over the cells: what
+   * the reference computes when its UserAllReducer is backed by
+   * BfbTreeAllReducer (cedr_bfb_tree_allreduce.cpp:86-124). Deterministic and
+   * independent of the GPU decomposition. Default. */
+  CEDR_B200_CAAS_SUM_TREE = 0,
+  /* Sequential over cells 0..n-1: what the reference's own reduce_locally
+   * computes on a host backend (team size 1, cedr_kokkos.hpp:118). One rank. */
+  CEDR_B200_CAAS_SUM_SEQUENTIAL = 1
+};
+
+typedef struct cedr_b200_cdr cedr_b200_cdr;
+
+/* Message of the last failure on this thread. */
+const char* cedr_b200_last_error(void);
+/* Library/ABI version, and whether a usable CUDA device is present (0/1). */
+int cedr_b200_version(void);
+int cedr_b200_device_available(void);
+
+/* ---- construction ------------------------------------------------------ */
+
+/* QLT<ES>::QLT(p, ncells, tree, options), cedr_qlt.cpp:229-236.
+ * The caller's tree::Node graph (cedr_tree_caller.hpp:12-24) is passed
+ * flattened: node i has kids[2*i], kids[2*i+1] (both -1 for a leaf);
+ * cellidx[i] is the global cell of leaf i; node_rank[i] the owning rank of leaf
+ * i (NULL: all 0). `rank`/`nranks` identify this process (Parallel::rank/size,
+ * cedr_mpi.hpp:17-27). Fails if this rank owns no cell (cedr_qlt.cpp:235). */
+int cedr_b200_qlt_create(cedr_b200_cdr** cdr, int ncells, int nnodes, int root,
+                         const int* kids, const int64_t* cellidx,
+                         const int* node_rank,
+                         int prefer_numerical_mass_conservation_to_numerical_bounds,
+                         int rank, int nranks);
+
+/* Same, over tree::make_tree_over_1d_mesh(p, ncells, imbalanced)
+ * (cedr_tree_caller.hpp:26-29, cedr_tree.cpp:350-353) with the contiguous
+ * cell->rank map of oned::Mesh (cedr_tree.cpp:366-369). */
+int cedr_b200_qlt_create_1d(cedr_b200_cdr** cdr, int ncells, int imbalanced,
+                            int prefer_numerical_mass_conservation_to_numerical_bounds,
+                            int rank, int nranks);
+
+/* CAAS<ES>::CAAS(p, nlclcells, UserAllReducer::Ptr), cedr_caas.cpp:37-48.
+ * `sum_mode` is one of CEDR_B200_CAAS_SUM_*. `cell0`/`ncells_global` place this
+ * rank's cells in the global cell order (tree-ordered sums need it); one rank:
+ * cell0 = 0, ncells_global = nlclcells. */
+int cedr_b200_caas_create(cedr_b200_cdr** cdr, int nlclcells, int sum_mode,
+                          int64_t cell0, int64_t ncells_global, int rank,
+                          int nranks);
+
+/* ~CDR */
+int cedr_b200_destroy(cedr_b200_cdr* cdr);
+
+/* ---- CDR interface, cedr_cdr.hpp:16-112 -------------------------------- */
+
+/* CDR::declare_tracer (cedr_qlt.cpp:276-285, cedr_caas.cpp:50-58) */
+int cedr_b200_declare_tracer(cedr_b200_cdr* cdr, int problem_type, int rhomidx);
+/* CDR::end_tracer_declarations (cedr_qlt.cpp:287-291, cedr_caas.cpp:60-73) */
+int cedr_b200_end_tracer_declarations(cedr_b200_cdr* cdr);
+/* CDR::get_buffers_sizes (cedr_qlt.cpp:293-298, cedr_caas.cpp:75-90) */
+int cedr_b200_get_buffers_sizes(cedr_b200_cdr* cdr, size_t* buf1, size_t* buf2);
+/* CDR::set_buffers (cedr_qlt.cpp:300-305, cedr_caas.cpp:92-99): device memory of
+ * at least the sizes above; must outlive the CDR. */
+int cedr_b200_set_buffers(cedr_b200_cdr* cdr, double* buf1, double* buf2);
+/* CDR::finish_setup (cedr_qlt.cpp:307-313, cedr_caas.cpp:101-116) */
+int cedr_b200_finish_setup(cedr_b200_cdr* cdr);
+/* CDR::get_problem_type: the canonical type (cedr_qlt.cpp:315-320) */
+int cedr_b200_get_problem_type(const cedr_b200_cdr* cdr, int tracer_idx, int* type);
+/* CDR::get_num_tracers */
+int cedr_b200_get_num_tracers(const cedr_b200_cdr* cdr, int* ntracers);
+/* CDR::run (cedr_qlt.cpp:618-640, cedr_caas.cpp:258-270). Asynchronous. */
+int cedr_b200_run(cedr_b200_cdr* cdr);
+/* CDR::print */
+int cedr_b200_print(const cedr_b200_cdr* cdr, char* buf, size_t bufsize);
+
+/* QLT::nlclcells / get_owned_glblcells / gci2lci, cedr_qlt.cpp:241-274 */
+int cedr_b200_nlclcells(const cedr_b200_cdr* cdr, int* n);
+int cedr_b200_get_owned_glblcells(const cedr_b200_cdr* cdr, int64_t* gcis_host);
+int cedr_b200_gci2lci(const cedr_b200_cdr* cdr, int64_t gci, int* lci);
+
+/* ---- DeviceOp, cedr_cdr.hpp:67-102 ------------------------------------- */
+
+/* Trivially copyable view of the CDR's device buffers. Caller kernels copy it
+ * by value and call the inline set_rhom / set_Qm / get_Qm of
+ * include/cedr_b200_device_op.h on it, exactly as they copy the reference's
+ * concrete DeviceOp into Kokkos lambdas (cedr_test_randomized_inl.hpp:27-58).
+ * Layout: SoA, cell fastest: word `row` of local cell `lci` is data[row*ld + lci].
+ * Row 0 of `in` is rhom; tracer t owns rows trcr_row[t]..: Qm_min (or q_min),
+ * Qm, Qm_max (or q_max), Qm_prev as its problem type needs
+ * (cedr_qlt_inl.hpp:21-58). QLT results land in out[t*ld + lci]; CAAS works in
+ * place (out aliases the Qm rows of `in`), like the reference. */
+typedef struct cedr_b200_device_op {
+  double* in;
+  double* out;
+  int64_t ld;
+  const int* trcr_row;   /* device, ntracers entries */
+  const int* trcr_prob;  /* device, canonical problem types */
+  int ntracers;
+  int nlclcells;
+  int is_caas;
+  int reserved;
+} cedr_b200_device_op;
+
+int cedr_b200_get_device_op(cedr_b200_cdr* cdr, cedr_b200_device_op* op);
+
+/* Bulk forms of DeviceOp::set_rhom / set_Qm / get_Qm over SoA caller arrays
+ * (SURVEY.md section 8f-1): a[t*lda + lci] for t in [t0, t0+nt). Device
+ * pointers; qm_prev may be NULL when none of the tracers conserves. */
+int cedr_b200_set_rhom_bulk(cedr_b200_cdr* cdr, const double* rhom);
+int cedr_b200_set_Qm_bulk(cedr_b200_cdr* cdr, int t0, int nt, int64_t lda,
+                          const double* qm, const double* qm_min,
+                          const double* qm_max, const double* qm_prev);
+int cedr_b200_get_Qm_bulk(cedr_b200_cdr* cdr, int t0, int nt, int64_t lda,
+                          double* qm);
+
+/* ---- streams, multi-GPU exchange --------------------------------------- */
+
+/* All work of this CDR is enqueued on `cuda_stream` (a cudaStream_t). */
+int cedr_b200_set_stream(cedr_b200_cdr* cdr, void* cuda_stream);
+int cedr_b200_synchronize(cedr_b200_cdr* cdr);
+
+/* The one exchange step of a multi-GPU run() (replaces the per-level MPI
+ * messages of cedr_qlt.cpp:327-337, 432-439, 478-488, 606-613 and CAAS's
+ * MPI_Allreduce, cedr_caas.cpp:203-209): an all-gather, enqueued on `stream`,
+ * of `count` doubles from every rank's `send` into `recv` (rank-major). The
+ * plug-in point mirrors CAAS::UserAllReducer (cedr_caas.hpp:27-49): the host
+ * side supplies NCCL (torch.distributed in Python, ncclAllGather in C++).
+ * Must be set on every rank when nranks > 1. */
+typedef int (*cedr_b200_allgather_fn)(void* ctx, const double* send, double* recv,
+                                      size_t count, void* cuda_stream);
+int cedr_b200_set_allgather(cedr_b200_cdr* cdr, cedr_b200_allgather_fn fn, void* ctx);
+
+/* ---- introspection for tests / benches --------------------------------- */
+
+/* Number of kernels launched by the last run() on this CDR. */
+int cedr_b200_last_run_launches(const cedr_b200_cdr* cdr, int* n);
+/* Tree plan facts: tiers, blocks in tier 0, max leaves per block, reference level
+ * count (tree height + 1, cedr_tree.cpp:215-231). Any pointer may be NULL. */
+int cedr_b200_plan_info(const cedr_b200_cdr* cdr, int* ntiers, int* nblocks0,
+                        int* max_block_leaves, int* nlevels_ref);
+/* Tuning knob, before finish_setup: maximum leaves per block (power users /
+ * tests that want to force multi-tier plans on small trees). */
+int cedr_b200_set_max_block_leaves(cedr_b200_cdr* cdr, int max_block_leaves);
+
+/* Host-only probe of the tree plan (no device needed): flattens the tree, cuts it
+ * into blocks and checks the plan the way the reference checks its comm plan
+ * (tree::unittest -> test_comm_pattern, cedr_tree.cpp:279-348): the cell ids are
+ * summed through the plan's block topology, tier by tier, and must give
+ * ncells*(ncells-1)/2 at the root; every leaf and internal node must be used
+ * exactly once. Outputs (any may be NULL): lci2gci_host[ncells], *ntiers,
+ * nblocks_per_tier_host[<=64], *nshapes, *nlevels_ref, *idsum (the sum found). */
+int cedr_b200_plan_probe(int ncells, int nnodes, int root, const int* kids,
+                         const int64_t* cellidx, int max_block_leaves,
+                         int64_t* lci2gci_host, int* ntiers,
+                         int* nblocks_per_tier_host, int* nshapes, int* nlevels_ref,
+                         int64_t* idsum);
+/* tree::make_tree_over_1d_mesh as flat arrays (host): kids_host[2*(2*ncells-1)],
+ * cellidx_host[2*ncells-1]; root is node 0. */
+int cedr_b200_make_1d_tree(int ncells, int imbalanced, int* kids_host,
+                           int64_t* cellidx_host);
+
+/* Synthetic workload of SURVEY.md section 8(d), generated on the device:
+ * splitmix64 stream seeded 0xCED20000 + config_id; fills rhom[ncells] and the
+ * four [nt][lda] arrays. Bit-identical to compose_b200.workloads.headline(). */
+int cedr_b200_fill_headline(int ncells, int nt, int64_t lda, int config_id,
+                            double* rhom, double* qm_min, double* qm, double* qm_max,
+                            double* qm_prev, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

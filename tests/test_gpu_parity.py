@@ -1,0 +1,179 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle, bit for bit.
+
+The contract (BASELINE.json north_star): results match the reference's CDR on
+identical inputs within 1e-13 relative per cell, and bit-for-bit in the
+deterministic-order mode. QLT's arithmetic order is fixed by the tree, and CAAS
+runs in tree-ordered mode, so every comparison here demands EXACT equality
+(np.array_equal); the 1e-13 tolerance is therefore met with margin 0.
+"""
+import numpy as np
+import pytest
+
+import randomized as R
+from oracle.oracle_py import Oracle, Tree
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return Oracle()
+
+
+def random_tree(rng, ncells):
+    perm = rng.permutation(ncells)
+    kids, cellidx = [], []
+
+    def rec(lo, hi):
+        me = len(cellidx)
+        kids.extend([-1, -1])
+        cellidx.append(-1)
+        if hi - lo == 1:
+            cellidx[me] = int(perm[lo])
+            return me
+        cut = int(rng.integers(lo + 1, hi))
+        k0 = rec(lo, cut)
+        k1 = rec(cut, hi)
+        kids[2*me], kids[2*me + 1] = k0, k1
+        return me
+
+    rec(0, ncells)
+    return Tree(np.array(kids, np.int32), np.array(cellidx, np.int64), 0)
+
+
+def test_library_is_loaded_and_device_present():
+    import compose_b200 as cb
+    lib = cb.load_library()
+    assert lib.cedr_b200_device_available() == 1
+
+
+def test_fill_headline_matches_numpy():
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    ncells, nt = 777, 5
+    dev = cb.fill_headline(ncells, nt, 7)
+    host = W.headline(ncells, nt, 7)
+    for d, h in zip(dev, host):
+        assert np.array_equal(d.cpu().numpy(), h)
+
+
+@pytest.mark.parametrize("ncells", [1, 2, 7, 21, 111, 1000, 2731])
+@pytest.mark.parametrize("imbalanced", [False, True])
+@pytest.mark.parametrize("prefer", [False, True])
+def test_qlt_randomized_bitwise(oracle, ncells, imbalanced, prefer):
+    from gpu_util import run_qlt_gpu
+    ts, v = R.generate(ncells, seed=31*ncells + 2*imbalanced + prefer)
+    pts = [t.problem_type for t in ts]
+    tree = oracle.bisection_tree(ncells, imbalanced)
+    ref = oracle.qlt(tree, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev, prefer)
+    got, q = run_qlt_gpu(ncells, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev,
+                         imbalanced=imbalanced, prefer=prefer,
+                         external_buffers=imbalanced)
+    assert np.array_equal(got, ref)
+    assert R.check(ts, v, got, prefer) == []
+    # get_problem_type reports the canonical type (cedr_qlt.cpp:707-713)
+    assert [q.get_problem_type(i) for i in range(len(pts))] == \
+        [oracle.canonical_problem_type(p) for p in pts]
+
+
+@pytest.mark.parametrize("ncells,mbl", [(7, 2), (21, 4), (111, 16), (1000, 32),
+                                        (1000, 2), (5400, 128)])
+def test_qlt_multi_tier_plans_bitwise(oracle, ncells, mbl):
+    """Small max_block_leaves forces 3+ tier plans; results must not change."""
+    from gpu_util import run_qlt_gpu
+    ts, v = R.generate(ncells, seed=ncells + mbl)
+    pts = [t.problem_type for t in ts]
+    for imb in (False, True):
+        tree = oracle.bisection_tree(ncells, imb)
+        ref = oracle.qlt(tree, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev)
+        got, q = run_qlt_gpu(ncells, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev,
+                             imbalanced=imb, max_block_leaves=mbl)
+        assert q.plan_info()["ntiers"] >= 2
+        assert np.array_equal(got, ref)
+
+
+def test_qlt_random_trees_bitwise(oracle):
+    from gpu_util import run_qlt_gpu
+    rng = np.random.default_rng(17)
+    for ncells, mbl in ((2, None), (3, None), (9, 4), (64, 8), (257, None), (1500, 64)):
+        tree = random_tree(rng, ncells)
+        ts, v = R.generate(ncells, seed=ncells)
+        pts = [t.problem_type for t in ts]
+        ref = oracle.qlt(tree, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev)
+        got, q = run_qlt_gpu(ncells, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev,
+                             tree=(tree.kids, tree.cellidx, tree.root),
+                             max_block_leaves=mbl)
+        lo, _ = oracle.leaf_order(tree)
+        assert np.array_equal(q.get_owned_glblcells(), lo)
+        assert np.array_equal(got, ref)
+
+
+def test_qlt_headline_inputs_bitwise(oracle):
+    """ne30-shaped tree (5,400 cells), a slice of the headline tracers, all `cst`."""
+    from compose_b200 import workloads as W
+    from gpu_util import run_qlt_gpu
+    ncells, nt = 5400, 48
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, 1)
+    pts = [7]*nt
+    tree = oracle.bisection_tree(ncells)
+    ref = oracle.qlt(tree, pts, rhom, lo, q, hi, prev)
+    got, qlt = run_qlt_gpu(ncells, pts, rhom, lo, q, hi, prev, nrun=2)
+    assert np.array_equal(got, ref)
+    # properties: bounds exact, mass to 100 eps
+    assert np.all(got >= lo) and np.all(got <= hi)
+    rel = np.abs(got.sum(1) - prev.sum(1))/np.abs(prev).sum(1)
+    assert rel.max() <= 100*np.finfo(float).eps
+
+
+def caas_tracers():
+    return [t for t in R.tracers_vector()
+            if (t.problem_type & R.S) and t.local_should_hold]
+
+
+@pytest.mark.parametrize("ncells", [1, 2, 4, 11, 111, 1000, 5400])
+def test_caas_tree_sums_bitwise(oracle, ncells):
+    from gpu_util import run_caas_gpu
+    ts, v = R.generate(ncells, seed=5 + ncells)
+    sel = caas_tracers()
+    idx = [t.idx for t in sel]
+    pts = [t.problem_type for t in sel]
+    a = [x[idx] for x in (v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev)]
+    tree = oracle.bisection_tree(ncells)
+    ref = oracle.caas(ncells, pts, *a, tree=tree)
+    for mbl, ext in ((None, False), (8, True)):
+        if mbl and ncells < 3:
+            continue
+        got, c = run_caas_gpu(ncells, pts, v.rhom, a[0], a[1], a[2], a[3],
+                              max_block_leaves=mbl, external_buffers=ext)
+        assert np.array_equal(got, ref)
+    assert R.check(sel, v, got) == []
+
+
+def test_caas_headline_inputs_bitwise(oracle):
+    from compose_b200 import workloads as W
+    from gpu_util import run_caas_gpu
+    ncells, nt = 5400, 48
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, 1)
+    pts = [7]*nt
+    ref = oracle.caas(ncells, pts, lo, q, hi, prev, tree=oracle.bisection_tree(ncells))
+    got, _ = run_caas_gpu(ncells, pts, rhom, lo, q, hi, prev)
+    assert np.array_equal(got, ref)
+    assert np.all(got >= lo) and np.all(got <= hi)
+
+
+def test_errors_mirror_reference():
+    import compose_b200 as cb
+    q = cb.QLT(8)
+    with pytest.raises(cb.CedrError, match="rhomidx > 0 is not supported"):
+        q.declare_tracer(7, 1)
+    with pytest.raises(cb.CedrError, match="Invalid problem type"):
+        q.declare_tracer(1, 0)   # conservation alone (cedr_qlt.hpp:82-83)
+    q.declare_tracer(7)
+    q.end_tracer_declarations()
+    with pytest.raises(cb.CedrError, match="end_tracer_declarations was already called"):
+        q.declare_tracer(7)
+    c = cb.CAAS(4)
+    with pytest.raises(cb.CedrError, match="does not support ! shapepreserve"):
+        c.declare_tracer(cb.CONSERVE | cb.CONSISTENT)
+    with pytest.raises(cb.CedrError, match="0 cells"):
+        cb.CAAS(0)
