@@ -121,6 +121,15 @@ def _stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _row_stride(x):
+    """Leading dimension of a [nt, n] SoA tensor whose rows are unit-stride."""
+    assert x.dim() == 2 and (x.shape[1] == 1 or x.stride(1) == 1)
+    if x.shape[0] == 1 or x.shape[1] == 1:
+        # strides of size-1 dimensions are arbitrary
+        return max(x.shape[1], x.stride(0) if x.shape[0] > 1 and x.shape[1] > 1 else 0)
+    return x.stride(0)
+
+
 def _as_i32(a):
     import numpy as np
     return np.ascontiguousarray(a, dtype=np.int32)
@@ -225,9 +234,10 @@ class CDR:
 
     def set_Qm(self, qm, qm_min, qm_max, qm_prev=None, t0=0):
         """SoA cuda float64 [nt, lda] arrays, cell (lci) fastest."""
-        nt, lda = qm.shape[0], qm.stride(0) if qm.dim() == 2 else qm.numel()
+        nt, lda = qm.shape[0], _row_stride(qm)
         for x in (qm, qm_min, qm_max, qm_prev):
-            assert x is None or (x.is_cuda and x.element_size() == 8 and x.stride(-1) == 1)
+            assert x is None or (x.is_cuda and x.element_size() == 8 and
+                                 x.shape == qm.shape and _row_stride(x) == lda)
         _check(self._lib.cedr_b200_set_Qm_bulk(self._h, int(t0), int(nt), int(lda), _ptr(qm),
                                                _ptr(qm_min), _ptr(qm_max), _ptr(qm_prev)))
 
@@ -239,7 +249,7 @@ class CDR:
         nt = self.get_num_tracers() - t0 if nt is None else nt
         if out is None:
             out = torch.empty((nt, self.nlclcells()), dtype=torch.float64, device="cuda")
-        lda = out.stride(0) if out.dim() == 2 else out.numel()
+        lda = _row_stride(out)
         _check(self._lib.cedr_b200_get_Qm_bulk(self._h, int(t0), int(nt), int(lda),
                                                _ptr(out)))
         return out
