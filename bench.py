@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- CDR::run throughput (QLT + CAAS) on synthetic cubed-sphere workloads.
+
+Metric (BASELINE.json): cell.tracer updates/s of CDR::run, and the fraction of the
+HBM roofline at 40 algorithmic bytes per update.
+
+A STEP is one pass of the hot path over the whole workload: one QLT::run() plus one
+CAAS::run() over the same ncells x nt inputs (2*ncells*nt updates). set_Qm/get_Qm
+are outside the timed region, as in the reference API where they are caller kernels;
+CAAS clips in place, so its inputs are restored between steps, untimed.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ne120x128x40]
+    python bench.py --impl reference ...   # the reference's own CPU path (oracle/_ref)
+
+Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CDR::run cell.tracer updates/s (QLT + CAAS)"
+UNIT = "updates/s"
+BYTES_PER_UPDATE = 40.0          # read min, Qm, max, prev; write Qm
+CST = 7                          # conserve | shapepreserve | consistent
+REF_SAMPLE_NT = 640              # tracer batch of the CPU baseline (16 levels x 40)
+
+
+def workload_dims(name):
+    from compose_b200.workloads import CONFIGS
+    return CONFIGS[name]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            for k, nme in enumerate(names):
+                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": sm[len(sm)//2] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_reference_step(ncells, config_id, nt_sample, nrep, warm):
+    """Time the reference's own QLT::run + CAAS::run (oracle/_ref, all host threads) on a
+    tracer batch of the workload. Returns (per-step seconds list, info dict)."""
+    from oracle.oracle_py import Oracle, Ref, ref_available
+    o = Oracle()
+    rhom, lo, q, hi, prev = o.fill_headline(ncells, config_id, 0, nt_sample)
+    pts = [CST]*nt_sample
+    if ref_available(omp=True):
+        r = Ref(omp=True)
+        cores = r.num_threads()
+        _, _, sq = r.qlt(ncells, ("bisect", False), pts, rhom, lo, q, hi, prev, nrep=warm + nrep)
+        _, sc = r.caas(ncells, pts, rhom, lo, q, hi, prev, nrep=warm + nrep)
+        kind = "reference"
+        secs = [float(a + b) for a, b in zip(sq[warm:], sc[warm:])]
+        split = {"qlt_s": float(min(sq[warm:])), "caas_s": float(min(sc[warm:]))}
+    else:
+        # The plain-C restatement, OpenMP over tracers.
+        tree = o.bisection_tree(ncells)
+        cores = os.cpu_count()
+        secs, split = [], {}
+        for i in range(warm + nrep):
+            t0 = time.perf_counter()
+            o.qlt(tree, pts, rhom, lo, q, hi, prev)
+            t1 = time.perf_counter()
+            o.caas(ncells, pts, lo, q, hi, prev, tree=tree)
+            t2 = time.perf_counter()
+            if i >= warm:
+                secs.append(t2 - t0)
+                split = {"qlt_s": t1 - t0, "caas_s": t2 - t1}
+        kind = "port"
+    info = {"cores": cores, "kind": kind,
+            "sample": "%d cells x %d of the workload's tracers (one tracer batch; tracers are "
+                      "independent problems), QLT::run + CAAS::run only, %d warm-up + %d reps, "
+                      "reference sources + stand-in Kokkos/MPI runtime, -O2 -fopenmp"
+                      % (ncells, nt_sample, warm, nrep)}
+    info.update(split)
+    return secs, info
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncells, nt, cid = workload_dims(args.workload)
+    nts = min(REF_SAMPLE_NT, nt)
+    secs, info = cpu_reference_step(ncells, cid, nts, args.steps, args.warmup)
+    ms = 1e3*sum(secs)/len(secs)
+    value = 2.0*ncells*nts/(ms*1e-3)
+    info["value"] = value
+    info["unit"] = UNIT
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, ncells, nt),
+        "cpu_baseline": info,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def config_dict(args, ncells, nt):
+    return {"workload": args.workload, "ncells": ncells, "cdr_tracers": nt,
+            "problem_type": "conserve|shapepreserve|consistent",
+            "tree": "recursive bisection (make_tree_over_1d_mesh)",
+            "step": "QLT::run + CAAS::run (tree-ordered sums), 2*ncells*nt updates",
+            "l2": "inputs (>= 0.6 GB per reconstructor) exceed the 126 MB L2; no flush",
+            "parallelism": ("single GPU" if args.gpus == 1 else
+                            "%d GPUs, tracers partitioned (interim; subtree partition next)"
+                            % args.gpus)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ne120x128x40")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-launches", action="store_true",
+                    help="extra untimed step with per-launch CUDA events")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import compose_b200 as cb
+    from compose_b200.pipeline import HostStepPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ncells, nt, cid = workload_dims(args.workload)
+    # Interim multi-GPU decomposition: each rank takes a contiguous slice of tracers.
+    nt_lcl = nt//world + (1 if rank < nt % world else 0)
+    t_first = rank*(nt//world) + min(rank, nt % world)
+
+    # ---- inputs, resident in HBM before any timed region
+    rhom, lo, q, hi, prev = cb.fill_headline(ncells, nt, cid)
+    if world > 1:
+        lo, q, hi, prev = (x[t_first:t_first + nt_lcl].contiguous() for x in (lo, q, hi, prev))
+
+    def make(kind):
+        c = cb.QLT(ncells) if kind == "qlt" else cb.CAAS(ncells)
+        for _ in range(nt_lcl):
+            c.declare_tracer(CST)
+        c.end_tracer_declarations()
+        c.finish_setup()
+        c.set_rhom(rhom)
+        c.set_Qm(q, lo, hi, prev)
+        return c
+
+    qlt, caas = make("qlt"), make("caas")
+    torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def one_step(timed):
+        caas.set_Qm(q, lo, hi, prev)          # restore (CAAS clips in place); untimed
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        qlt.run()
+        e1.record()
+        caas.run()
+        e2.record()
+        return e0, e1, e2
+
+    for _ in range(args.warmup):
+        one_step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [one_step(True) for _ in range(args.steps)]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_qlt = [a.elapsed_time(b) for a, b, _ in evs]
+    t_caas = [b.elapsed_time(c) for _, b, c in evs]
+    ms_step = (sum(t_qlt) + sum(t_caas))/args.steps
+    launches = (qlt.last_run_launches() + caas.last_run_launches())*args.steps
+    t = torch.tensor([ms_step, sum(t_qlt)/args.steps, sum(t_caas)/args.steps],
+                     dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_qlt, ms_caas = (float(x) for x in t.cpu())
+    updates = float(ncells)*nt
+    value = 2.0*updates/(ms_step*1e-3)
+
+    # ---- per-launch breakdown (untimed extra step)
+    kernels = None
+    if args.profile_launches or True:
+        for c in (qlt, caas):
+            c.set_profiling(True)
+        one_step(False)
+        kernels = {"qlt": [(n, tr, round(ms, 4)) for n, tr, ms in qlt.launch_times()],
+                   "caas": [(n, tr, round(ms, 4)) for n, tr, ms in caas.launch_times()]}
+        for c in (qlt, caas):
+            c.set_profiling(False)
+
+    # ---- roofline of the dominant reconstructor pass (QLT run())
+    peak, peak_src = measured_peaks()
+    ach = BYTES_PER_UPDATE*(updates/world)/(ms_qlt*1e-3)/1e9
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach/peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "QLT::run() = rhom + up + top + down sweeps (per GPU)",
+                "algorithmic_bytes_per_update": BYTES_PER_UPDATE,
+                "caas": {"achieved": BYTES_PER_UPDATE*(updates/world)/(ms_caas*1e-3)/1e9,
+                         "frac": BYTES_PER_UPDATE*(updates/world)/(ms_caas*1e-3)/1e9/peak}}
+
+    # ---- end to end through the public API with HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        del qlt, caas
+        torch.cuda.empty_cache()
+        pipe = HostStepPipeline(ncells, nt_lcl)
+        pin = lambda x: x.cpu().pin_memory()
+        rhom_h, lo_h, q_h, hi_h, prev_h = (pin(x) for x in (rhom, lo, q, hi, prev))
+        out_h = {k: torch.empty((nt_lcl, ncells), dtype=torch.float64).pin_memory()
+                 for k in pipe.kinds}
+        pipe.step(rhom_h, lo_h, q_h, hi_h, prev_h, out_h)       # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(args.steps):
+            pipe.step(rhom_h, lo_h, q_h, hi_h, prev_h, out_h)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms_e2e = max(e0.elapsed_time(e1), 0.0)/args.steps
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.cpu()[0])
+        e2e = {"value": 2.0*updates/(ms_e2e*1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": pipe.h2d_bytes_per_step*world,
+               "d2h_bytes_per_step": pipe.d2h_bytes_per_step*world,
+               "ms_per_step": ms_e2e, "wall_ms_per_step": 1e3*wall/args.steps,
+               "how": "pinned host SoA arrays -> chunked H2D / set_Qm / run / get_Qm / D2H "
+                      "pipeline over %d tracer chunks on %d streams (compose_b200.pipeline)"
+                      % (pipe.nchunks, len(pipe.slots))}
+        launches += pipe.launches_per_step*args.steps
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        nts = min(REF_SAMPLE_NT, nt)
+        secs, cpu = cpu_reference_step(ncells, cid, nts, 3, 1)
+        cpu["value"] = 2.0*ncells*nts/(sum(secs)/len(secs))
+        cpu["unit"] = UNIT
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, ncells, nt),
+            "qlt": {"value": updates/(ms_qlt*1e-3), "ms_per_run": ms_qlt},
+            "caas": {"value": updates/(ms_caas*1e-3), "ms_per_run": ms_caas},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks, "kernels_ms": kernels,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -71,6 +71,9 @@ SYMBOLS = [
     ("cedr_b200_synchronize", C.c_int, [_H]),
     ("cedr_b200_set_allgather", C.c_int, [_H, ALLGATHER_FN, _vp]),
     ("cedr_b200_last_run_launches", C.c_int, [_H, _ip]),
+    ("cedr_b200_set_profiling", C.c_int, [_H, C.c_int]),
+    ("cedr_b200_get_launch_times", C.c_int, [_H, C.c_int, C.POINTER(C.c_float), _ip, _ip,
+                                             _ip]),
     ("cedr_b200_plan_info", C.c_int, [_H, _ip, _ip, _ip, _ip]),
     ("cedr_b200_set_max_block_leaves", C.c_int, [_H, C.c_int]),
     ("cedr_b200_plan_probe", C.c_int, [C.c_int, C.c_int, C.c_int, _ip, _lp, C.c_int, _lp,
@@ -253,6 +256,19 @@ class CDR:
         _check(self._lib.cedr_b200_get_Qm_bulk(self._h, int(t0), int(nt), int(lda),
                                                _ptr(out)))
         return out
+
+    def set_profiling(self, on=True):
+        _check(self._lib.cedr_b200_set_profiling(self._h, int(bool(on))))
+
+    def launch_times(self):
+        """[(tag, tier, ms)] of the last run() (profiling must be on)."""
+        cap = 4096
+        ms = (C.c_float*cap)()
+        tags, tiers, n = (C.c_int*cap)(), (C.c_int*cap)(), C.c_int(0)
+        _check(self._lib.cedr_b200_get_launch_times(self._h, cap, ms, tags, tiers,
+                                                    C.byref(n)))
+        names = ["rhom", "up", "top", "down", "caas_adjust", "exchange"]
+        return [(names[tags[i]], tiers[i], ms[i]) for i in range(n.value)]
 
     def last_run_launches(self):
         v = C.c_int(0)

@@ -155,7 +155,38 @@ struct cedr_b200_cdr {
   cedr_b200_allgather_fn allgather = nullptr;
   void* allgather_ctx = nullptr;
   int last_launches = 0;
+
+  // Optional per-launch timing (cedr_b200_set_profiling).
+  bool profiling = false;
+  struct Timed { cudaEvent_t e0, e1; int tag, tier; };
+  std::vector<Timed> timed;
+  size_t ntimed = 0;
+  ~cedr_b200_cdr () {
+    for (auto& t : timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  }
 };
+
+namespace {
+// RAII bracket around one launch when profiling is on.
+struct LaunchTimer {
+  cedr_b200_cdr& c;
+  cedr_b200_cdr::Timed* t = nullptr;
+  LaunchTimer (cedr_b200_cdr& c_, int tag, int tier) : c(c_) {
+    if (! c.profiling) return;
+    if (c.ntimed == c.timed.size()) {
+      cedr_b200_cdr::Timed n;
+      cudaEventCreate(&n.e0);
+      cudaEventCreate(&n.e1);
+      c.timed.push_back(n);
+    }
+    t = &c.timed[c.ntimed++];
+    t->tag = tag;
+    t->tier = tier;
+    cudaEventRecord(t->e0, c.stream);
+  }
+  ~LaunchTimer () { if (t) cudaEventRecord(t->e1, c.stream); }
+};
+}
 
 namespace {
 
@@ -176,6 +207,8 @@ void launch_sweep (cedr_b200_cdr& c, int tier, const SweepArgs& a) {
   }
   const long long grid = static_cast<long long>(a.nblocks)*a.ntr;
   cedr_b200_throw_if(grid > 0x7fffffffLL, "grid too large");
+  LaunchTimer lt(c, MODE == MODE_UP ? CEDR_B200_TAG_UP : MODE == MODE_TOP ?
+                 CEDR_B200_TAG_TOP : CEDR_B200_TAG_DOWN, tier);
   sweep_kernel<CLS, MODE><<<static_cast<unsigned>(grid), kThreads, smem, c.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++c.last_launches;
@@ -256,6 +289,7 @@ void run_rhom (cedr_b200_cdr& c) {
     a.root_out = k + 1 < ntiers ? c.d_rhom_tier[k+1].p : nullptr;
     a.nc = c.d_nc.p;
     const size_t smem = sizeof(double)*2*static_cast<size_t>(c.plan.tiers[k].max_nl);
+    LaunchTimer lt(c, CEDR_B200_TAG_RHOM, k);
     rhom_kernel<<<a.nblocks, kThreads, smem, c.stream>>>(a);
     CUDA_CHECK(cudaGetLastError());
     ++c.last_launches;
@@ -289,6 +323,7 @@ void run_caas (cedr_b200_cdr& c) {
   const int nt = static_cast<int>(c.trcr_prob.size());
   const long long n = static_cast<long long>(c.nlcl)*nt;
   const int grid = static_cast<int>(std::min<long long>((n + kThreads - 1)/kThreads, 148*32));
+  LaunchTimer lt(c, CEDR_B200_TAG_CAAS_ADJUST, 0);
   caas_adjust_kernel<<<grid, kThreads, 0, c.stream>>>(c.in, c.ld, c.nlcl, c.d_trcr_row.p,
                                                       c.d_caas_scal.p, nt);
   CUDA_CHECK(cudaGetLastError());
@@ -554,6 +589,7 @@ int cedr_b200_run (cedr_b200_cdr* c) {
   return guarded([&] {
     cedr_b200_throw_if(! c->finished, "finish_setup must be called before run.");
     c->last_launches = 0;
+    c->ntimed = 0;
     if (c->is_caas) run_caas(*c); else run_qlt(*c);
   });
 }
@@ -675,6 +711,24 @@ int cedr_b200_set_allgather (cedr_b200_cdr* c, cedr_b200_allgather_fn fn, void* 
 
 int cedr_b200_last_run_launches (const cedr_b200_cdr* c, int* n) {
   return guarded([&] { *n = c->last_launches; });
+}
+
+int cedr_b200_set_profiling (cedr_b200_cdr* c, int on) {
+  return guarded([&] { c->profiling = on != 0; c->ntimed = 0; });
+}
+
+int cedr_b200_get_launch_times (cedr_b200_cdr* c, int cap, float* ms, int* tags,
+                                int* tiers, int* n) {
+  return guarded([&] {
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const int m = static_cast<int>(std::min<size_t>(c->ntimed, cap));
+    for (int i = 0; i < m; ++i) {
+      CUDA_CHECK(cudaEventElapsedTime(&ms[i], c->timed[i].e0, c->timed[i].e1));
+      tags[i] = c->timed[i].tag;
+      tiers[i] = c->timed[i].tier;
+    }
+    *n = m;
+  });
 }
 
 int cedr_b200_plan_info (const cedr_b200_cdr* c, int* ntiers, int* nblocks0,

@@ -1,0 +1,70 @@
+"""End-to-end (host-buffer) driver for CDR::run.
+
+A caller whose tracer fields live in HOST memory runs one CDR step as: copy the
+step's inputs to the device, set_rhom/set_Qm, run(), get_Qm, copy the result back.
+Done naively that serialises ~40 B/update over PCIe around a ~ms kernel, so this
+class tiles the tracers into chunks and pipelines chunk k's H2D copy, chunk k-1's
+kernels and chunk k-2's D2H copy on separate CUDA streams (tracers are
+independent problems, so chunking does not change any result). It uses only the
+public CDR API of compose_b200 (declare/finish_setup once, then bulk
+set_Qm/run/get_Qm per chunk).
+"""
+import torch
+
+import compose_b200 as cb
+
+
+class HostStepPipeline:
+    def __init__(self, ncells, nt, problem_type=7, chunk_nt=640, nslots=3,
+                 reconstructors=("qlt", "caas")):
+        self.ncells, self.nt = ncells, nt
+        self.chunk_nt = min(chunk_nt, nt)
+        self.nchunks = (nt + self.chunk_nt - 1)//self.chunk_nt
+        self.kinds = tuple(reconstructors)
+        self.slots = []
+        for _ in range(min(nslots, self.nchunks)):
+            s = {"stream": torch.cuda.Stream()}
+            with torch.cuda.stream(s["stream"]):
+                s["in"] = [torch.empty((self.chunk_nt, ncells), dtype=torch.float64,
+                                       device="cuda") for _ in range(4)]
+                s["rhom"] = torch.empty(ncells, dtype=torch.float64, device="cuda")
+                s["out"] = {k: torch.empty((self.chunk_nt, ncells), dtype=torch.float64,
+                                           device="cuda") for k in self.kinds}
+                s["cdr"] = {}
+                for k in self.kinds:
+                    c = cb.QLT(ncells) if k == "qlt" else cb.CAAS(ncells)
+                    for _t in range(self.chunk_nt):
+                        c.declare_tracer(problem_type)
+                    c.end_tracer_declarations()
+                    c.finish_setup()   # binds the slot's stream
+                    s["cdr"][k] = c
+            self.slots.append(s)
+        torch.cuda.synchronize()
+        self.h2d_bytes_per_step = 8*(4*nt*ncells + self.nchunks*ncells)
+        self.d2h_bytes_per_step = 8*len(self.kinds)*nt*ncells
+        self.launches_per_step = 0
+
+    def step(self, rhom_h, qm_min_h, qm_h, qm_max_h, qm_prev_h, out_h):
+        """Inputs: pinned host tensors [nt, ncells] (rhom_h [ncells]); out_h: dict
+        kind -> pinned host tensor [nt, ncells]. Returns after all copies landed."""
+        launches = 0
+        for ci in range(self.nchunks):
+            s = self.slots[ci % len(self.slots)]
+            t0 = ci*self.chunk_nt
+            n = min(self.chunk_nt, self.nt - t0)
+            with torch.cuda.stream(s["stream"]):
+                s["rhom"].copy_(rhom_h, non_blocking=True)
+                for dst, src in zip(s["in"], (qm_min_h, qm_h, qm_max_h, qm_prev_h)):
+                    dst[:n].copy_(src[t0:t0+n], non_blocking=True)
+                lo, q, hi, prev = s["in"]
+                for k in self.kinds:
+                    c = s["cdr"][k]
+                    c.set_rhom(s["rhom"])
+                    c.set_Qm(q, lo, hi, prev)
+                    c.run()
+                    c.get_Qm(out=s["out"][k])
+                    out_h[k][t0:t0+n].copy_(s["out"][k][:n], non_blocking=True)
+                    launches += c.last_run_launches() + 2
+        for s in self.slots:
+            s["stream"].synchronize()
+        self.launches_per_step = launches

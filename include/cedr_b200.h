@@ -173,6 +173,18 @@ int cedr_b200_set_allgather(cedr_b200_cdr* cdr, cedr_b200_allgather_fn fn, void*
 
 /* Number of kernels launched by the last run() on this CDR. */
 int cedr_b200_last_run_launches(const cedr_b200_cdr* cdr, int* n);
+/* Per-launch device times of run(): with profiling on, every kernel launch of
+ * run() is bracketed by CUDA events on the CDR's stream (measurement aid for
+ * bench.py's roofline line; off by default). After a synchronize,
+ * cedr_b200_get_launch_times returns up to `cap` entries: ms_host[i] and a
+ * kernel tag names_host[i] (see CEDR_B200_TAG_*). */
+enum {
+  CEDR_B200_TAG_RHOM = 0, CEDR_B200_TAG_UP = 1, CEDR_B200_TAG_TOP = 2,
+  CEDR_B200_TAG_DOWN = 3, CEDR_B200_TAG_CAAS_ADJUST = 4, CEDR_B200_TAG_EXCHANGE = 5
+};
+int cedr_b200_set_profiling(cedr_b200_cdr* cdr, int on);
+int cedr_b200_get_launch_times(cedr_b200_cdr* cdr, int cap, float* ms_host,
+                               int* tags_host, int* tiers_host, int* n);
 /* Tree plan facts: tiers, blocks in tier 0, max leaves per block, reference level
  * count (tree height + 1, cedr_tree.cpp:215-231). Any pointer may be NULL. */
 int cedr_b200_plan_info(const cedr_b200_cdr* cdr, int* ntiers, int* nblocks0,

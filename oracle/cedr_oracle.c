@@ -756,3 +756,37 @@ int oracle_caas_run(int ncells, int reducer, int nnodes, int root, const int* ki
   if (reducer == 1) sched_free(&s);
   return err;
 }
+
+/* --------------------------------------------------------------- workload */
+
+/* The synthetic inputs of SURVEY.md 8(d) (same stream as
+ * compose_b200/workloads.py::headline), for tracers [t0, t1). */
+static double splitmix_u(uint64_t seed, uint64_t k) {
+  uint64_t z = seed + (k + 1u)*0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30))*0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27))*0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (double) (z >> 11)*0x1.0p-53;
+}
+
+void oracle_fill_headline(int ncells, int config_id, int t0, int t1, double* rhom,
+                          double* qm_min, double* qm, double* qm_max, double* qm_prev) {
+  const uint64_t seed = 0xCED20000ull + (uint64_t) config_id;
+  for (int i = 0; i < ncells; ++i) rhom[i] = 0.5*(1 + splitmix_u(seed, (uint64_t) i));
+#ifdef _OPENMP
+# pragma omp parallel for schedule(static)
+#endif
+  for (int t = t0; t < t1; ++t)
+    for (int i = 0; i < ncells; ++i) {
+      const uint64_t p = (uint64_t) ncells + 4ull*((uint64_t) t*ncells + i);
+      const double q_min = 0.1*splitmix_u(seed, p);
+      const double q_max = q_min + splitmix_u(seed, p + 1);
+      const double q = q_min + (q_max - q_min)*(1.4*splitmix_u(seed, p + 2) - 0.2);
+      const double q_prev = q_min + (q_max - q_min)*splitmix_u(seed, p + 3);
+      const size_t s = (size_t) (t - t0)*ncells + i;
+      qm_min[s] = q_min*rhom[i];
+      qm_max[s] = q_max*rhom[i];
+      qm[s] = q*rhom[i];
+      qm_prev[s] = q_prev*rhom[i];
+    }
+}

@@ -88,6 +88,10 @@ void oracle_solve_node_problem(int problem_type, double rhom, const double* pd,
                                double* Qm0, double rhom1, const double* k1d,
                                double* Qm1, int prefer_mass_con);
 
+/* Synthetic inputs of SURVEY.md section 8(d) for tracers [t0, t1). */
+void oracle_fill_headline(int ncells, int config_id, int t0, int t1, double* rhom,
+                          double* qm_min, double* qm, double* qm_max, double* qm_prev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,16 @@ class Oracle:
                                                 C.c_double, _dp, _dp, C.c_double, _dp,
                                                 _dp, C.c_int]
         L.oracle_solve_node_problem.restype = None
+        L.oracle_fill_headline.argtypes = [C.c_int]*4 + [_dp]*5
+        L.oracle_fill_headline.restype = None
+
+    def fill_headline(self, ncells, config_id, t0, t1):
+        """(rhom, qm_min, qm, qm_max, qm_prev) of SURVEY 8(d) for tracers [t0, t1)."""
+        rhom = np.empty(ncells)
+        a = [np.empty((t1 - t0, ncells)) for _ in range(4)]
+        self.lib.oracle_fill_headline(ncells, config_id, t0, t1, _d(rhom), _d(a[0]),
+                                      _d(a[1]), _d(a[2]), _d(a[3]))
+        return (rhom,) + tuple(a)
 
     def bisection_tree(self, ncells, imbalanced=False):
         nn = 2*ncells - 1
