@@ -71,6 +71,8 @@ SYMBOLS = [
     ("cedr_b200_synchronize", C.c_int, [_H]),
     ("cedr_b200_set_allgather", C.c_int, [_H, ALLGATHER_FN, _vp]),
     ("cedr_b200_last_run_launches", C.c_int, [_H, _ip]),
+    ("cedr_b200_set_fast_path", C.c_int, [_H, C.c_int]),
+    ("cedr_b200_uses_fast_path", C.c_int, [_H, _ip]),
     ("cedr_b200_set_profiling", C.c_int, [_H, C.c_int]),
     ("cedr_b200_get_launch_times", C.c_int, [_H, C.c_int, C.POINTER(C.c_float), _ip, _ip,
                                              _ip]),
@@ -256,6 +258,14 @@ class CDR:
         _check(self._lib.cedr_b200_get_Qm_bulk(self._h, int(t0), int(nt), int(lda),
                                                _ptr(out)))
         return out
+
+    def set_fast_path(self, on=True):
+        _check(self._lib.cedr_b200_set_fast_path(self._h, int(bool(on))))
+
+    def uses_fast_path(self):
+        v = C.c_int(0)
+        _check(self._lib.cedr_b200_uses_fast_path(self._h, C.byref(v)))
+        return bool(v.value)
 
     def set_profiling(self, on=True):
         _check(self._lib.cedr_b200_set_profiling(self._h, int(bool(on))))

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -19,6 +20,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "fast_kernels.cuh"
 #include "tree_plan.h"
 
 namespace {
@@ -144,6 +146,11 @@ struct cedr_b200_cdr {
   DevBuf<double> in_own, out_own;
   DevBuf<int> d_trcr_row, d_trcr_prob, d_cls_tracers[NCLS];
   DevBuf<int> d_lvlptr, d_kid0, d_kid1;
+  DevBuf<unsigned short> d_dtab, d_ptab, d_fpos;
+  DevBuf<FastWQ> d_fwq;
+  DevBuf<FastRh> d_frh;
+  bool fast_enabled = true;   // cedr_b200_set_fast_path
+  bool fast_ok = false;       // plan + buffers allow the fast tier-0 kernels
   std::vector<DevBuf<BlockDev> > d_blocks;   // per tier
   DevBuf<dev::NodeConst> d_nc;
   std::vector<DevBuf<double> > d_rhom_tier;  // leaf rhom of tiers >= 1
@@ -276,6 +283,77 @@ SweepArgs base_args (cedr_b200_cdr& c, int cls, int tier) {
   return a;
 }
 
+// ---- fast tier-0 kernels (fast_kernels.cuh)
+
+bool fast_class (int cls, int mode) {
+  if (mode == MODE_UP) return cls == CLS_ST || cls == CLS_CST || cls == CLS_CAAS;
+  return cls == CLS_ST || cls == CLS_CST;
+}
+
+fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
+  fast::FastArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.blocks = c.d_blocks[0].p;
+  a.nblocks = static_cast<int>(c.plan.tiers[0].blocks.size());
+  a.dtab = c.d_dtab.p;
+  a.ptab = c.d_ptab.p;
+  a.wq = c.d_fwq.p;
+  a.rh = c.d_frh.p;
+  a.in = c.in;
+  a.in_ld = c.ld;
+  a.trcr_row = c.d_trcr_row.p;
+  a.trcr_prob = c.d_trcr_prob.p;
+  a.rec_out = c.d_rec[1].p;
+  a.rec_ld = c.tier_ld[1];
+  a.sol_in = c.d_sol[1].p;
+  a.sol_in_ld = c.tier_ld[1];
+  a.out = c.out;
+  a.out_ld = c.ld;
+  a.tracers = c.d_cls_tracers[cls].p;
+  a.ntr = static_cast<int>(c.cls_tracers[cls].size());
+  a.sbuf = (c.plan.tiers[0].max_nl + 2 + 1) & ~1;
+  a.prefer_mass_con = c.prefer_mass_con;
+  a.qglob = c.d_qglob.p;
+  // Tracers per CTA: enough CTAs for several waves, enough tracers per CTA to amortise
+  // the per-CTA setup and keep the TMA double buffer busy.
+  const long long work = static_cast<long long>(a.nblocks)*a.ntr;
+  a.group = static_cast<int>(std::max<long long>(1, std::min<long long>(16, work/(148*5*4))));
+  return a;
+}
+
+template <typename K>
+void launch_fast (cedr_b200_cdr& c, K kernel, const fast::FastArgs& a, size_t smem, int tag) {
+  if (a.ntr == 0) return;
+  CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(std::max<size_t>(smem, 48*1024))));
+  const long long grid = static_cast<long long>(a.nblocks)*((a.ntr + a.group - 1)/a.group);
+  cedr_b200_throw_if(grid > 0x7fffffffLL, "grid too large");
+  LaunchTimer lt(c, tag, 0);
+  kernel<<<static_cast<unsigned>(grid), fast::kThreads, smem, c.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++c.last_launches;
+}
+
+void launch_fast_up (cedr_b200_cdr& c, int cls) {
+  const fast::FastArgs a = fast_args(c, cls);
+  const int nrows = cls == CLS_ST ? 3 : 4;
+  const size_t smem = sizeof(double)*2*nrows*a.sbuf + 16 + sizeof(double)*32;
+  switch (cls) {
+  case CLS_ST: launch_fast(c, fast::up_kernel<CLS_ST>, a, smem, CEDR_B200_TAG_UP); break;
+  case CLS_CST: launch_fast(c, fast::up_kernel<CLS_CST>, a, smem, CEDR_B200_TAG_UP); break;
+  case CLS_CAAS: launch_fast(c, fast::up_kernel<CLS_CAAS>, a, smem, CEDR_B200_TAG_UP); break;
+  }
+}
+
+void launch_fast_down (cedr_b200_cdr& c, int cls) {
+  const fast::FastArgs a = fast_args(c, cls);
+  const size_t smem = sizeof(double)*(7*a.sbuf + 4*256 + fast::kD9) + 16;
+  if (cls == CLS_ST)
+    launch_fast(c, fast::down_kernel<CLS_ST>, a, smem, CEDR_B200_TAG_DOWN);
+  else
+    launch_fast(c, fast::down_kernel<CLS_CST>, a, smem, CEDR_B200_TAG_DOWN);
+}
+
 void run_rhom (cedr_b200_cdr& c) {
   const int ntiers = static_cast<int>(c.plan.tiers.size());
   for (int k = 0; k < ntiers; ++k) {
@@ -288,6 +366,9 @@ void run_rhom (cedr_b200_cdr& c) {
     a.in = k == 0 ? c.in : c.d_rhom_tier[k].p;
     a.root_out = k + 1 < ntiers ? c.d_rhom_tier[k+1].p : nullptr;
     a.nc = c.d_nc.p;
+    a.fpos = (k == 0 && c.fast_ok) ? c.d_fpos.p : nullptr;
+    a.fwq = c.d_fwq.p;
+    a.frh = c.d_frh.p;
     const size_t smem = sizeof(double)*2*static_cast<size_t>(c.plan.tiers[k].max_nl);
     LaunchTimer lt(c, CEDR_B200_TAG_RHOM, k);
     rhom_kernel<<<a.nblocks, kThreads, smem, c.stream>>>(a);
@@ -303,11 +384,15 @@ void run_qlt (cedr_b200_cdr& c) {
   run_rhom(c);
   for (int cls = 0; cls < CLS_CAAS; ++cls) {
     if (c.cls_tracers[cls].empty()) continue;
-    for (int k = 0; k < top; ++k)
-      launch_sweep_any(c, cls, k, MODE_UP, base_args(c, cls, k));
+    for (int k = 0; k < top; ++k) {
+      if (k == 0 && c.fast_ok && fast_class(cls, MODE_UP)) launch_fast_up(c, cls);
+      else launch_sweep_any(c, cls, k, MODE_UP, base_args(c, cls, k));
+    }
     launch_sweep_any(c, cls, top, MODE_TOP, base_args(c, cls, top));
-    for (int k = top - 1; k >= 0; --k)
-      launch_sweep_any(c, cls, k, MODE_DOWN, base_args(c, cls, k));
+    for (int k = top - 1; k >= 0; --k) {
+      if (k == 0 && c.fast_ok && fast_class(cls, MODE_DOWN)) launch_fast_down(c, cls);
+      else launch_sweep_any(c, cls, k, MODE_DOWN, base_args(c, cls, k));
+    }
   }
 }
 
@@ -317,8 +402,10 @@ void run_caas (cedr_b200_cdr& c) {
                      "CAAS sequential-order sums are not implemented yet");
   const int ntiers = static_cast<int>(c.plan.tiers.size());
   const int top = ntiers - 1;
-  for (int k = 0; k < top; ++k)
-    launch_sweep_any(c, CLS_CAAS, k, MODE_UP, base_args(c, CLS_CAAS, k));
+  for (int k = 0; k < top; ++k) {
+    if (k == 0 && c.fast_ok) launch_fast_up(c, CLS_CAAS);
+    else launch_sweep_any(c, CLS_CAAS, k, MODE_UP, base_args(c, CLS_CAAS, k));
+  }
   launch_sweep_any(c, CLS_CAAS, top, MODE_TOP, base_args(c, CLS_CAAS, top));
   const int nt = static_cast<int>(c.trcr_prob.size());
   const long long n = static_cast<long long>(c.nlcl)*nt;
@@ -390,7 +477,11 @@ void finish_setup (cedr_b200_cdr& c) {
       hb[b].lvlptr_off = sh.dev_lvlptr_off;
       hb[b].kid_off = sh.dev_kid_off;
       hb[b].ibase = blk.ibase;
-      hb[b].pad = 0;
+      hb[b].ftab_off = sh.fast ? sh.dev_dtab_off : -1;
+      hb[b].fpair_off = sh.dev_ptab_off;
+      hb[b].fpos_off = sh.dev_fpos_off;
+      hb[b].npairs = sh.fast ? static_cast<int>(sh.ptab.size()) : 0;
+      hb[b].fbase = blk.ibase;
     }
     c.d_blocks[k].upload(hb);
     c.tier_ld[k] = k == 0 ? c.ld : round_up(tier.nleaves, 16);
@@ -401,6 +492,15 @@ void finish_setup (cedr_b200_cdr& c) {
     }
   }
   c.d_nc.alloc(std::max(1, c.plan.ninternal));
+  c.d_dtab.upload(c.plan.dev_dtab);
+  c.d_ptab.upload(c.plan.dev_ptab);
+  c.d_fpos.upload(c.plan.dev_fpos);
+  c.fast_ok = c.fast_enabled && c.plan.tier0_fast &&
+    reinterpret_cast<uintptr_t>(c.in) % 16 == 0 && ! std::getenv("CEDR_B200_NO_FAST");
+  if (c.fast_ok) {
+    c.d_fwq.alloc(std::max(1, c.plan.ninternal));
+    c.d_frh.alloc(std::max(1, c.plan.ninternal));
+  }
   c.d_qglob.alloc(2*static_cast<size_t>(nt));
   c.d_caas_scal.alloc(2*static_cast<size_t>(nt));
   c.finished = true;
@@ -711,6 +811,17 @@ int cedr_b200_set_allgather (cedr_b200_cdr* c, cedr_b200_allgather_fn fn, void* 
 
 int cedr_b200_last_run_launches (const cedr_b200_cdr* c, int* n) {
   return guarded([&] { *n = c->last_launches; });
+}
+
+int cedr_b200_set_fast_path (cedr_b200_cdr* c, int on) {
+  return guarded([&] {
+    cedr_b200_throw_if(c->finished, "set_fast_path must precede finish_setup");
+    c->fast_enabled = on != 0;
+  });
+}
+
+int cedr_b200_uses_fast_path (const cedr_b200_cdr* c, int* on) {
+  return guarded([&] { *on = c->fast_ok; });
 }
 
 int cedr_b200_set_profiling (cedr_b200_cdr* c, int on) {

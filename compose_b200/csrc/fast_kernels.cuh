@@ -1,0 +1,435 @@
+// Fast path of the tier-0 sweeps for blocks whose shape is the recursive bisection
+// n -> (floor(n/2), n - floor(n/2)) of cedr_tree.cpp:391-413 with 512 < n <= 1024
+// leaves (what make_tree_over_1d_mesh yields below any node of that size; all the
+// BASELINE.json cubed-sphere configs cut into such blocks: 675 leaves at ne30/ne120,
+// 768 at ne256).
+//
+// Structure of such a block: a PERFECT binary tree down to depth 9 (512 nodes), where
+// each depth-9 node is either one leaf or a pair of leaves (n - 512 pairs). One CTA of
+// 128 threads sweeps one block for a group of tracers, one tracer at a time:
+//   - a tracer's leaf rows are staged into shared memory by TMA bulk copies
+//     (cp.async.bulk + mbarrier), double-buffered so tracer i+1 streams in while tracer
+//     i is being swept;
+//   - thread `tid` owns the depth-7 node `tid` (4 depth-9 nodes, 4..8 leaves): its
+//     micro-subtree is summed and solved in registers;
+//   - the 7 levels above the depth-7 nodes go through warp shuffles (sums) and shared
+//     memory (node problems);
+//   - solved leaf masses are staged in shared memory and written back coalesced.
+// The node arithmetic is the same device code as the generic path (node_solve.cuh), in
+// the same tree order, so results are bit-identical to it and to the reference.
+#ifndef CEDR_B200_FAST_KERNELS_CUH
+#define CEDR_B200_FAST_KERNELS_CUH
+
+#include <cstdint>
+
+#include "kernels.cuh"
+
+namespace cedr_b200 {
+namespace fast {
+
+constexpr int kThreads = 128;     // = number of depth-7 nodes of a block
+constexpr int kDepthLeafParents = 9;
+constexpr int kD9 = 512;          // depth-9 nodes per block
+constexpr int kMinLeaves = 513, kMaxLeaves = 1024;
+
+// Positions of a block's internal nodes in the fast const order:
+//   [0, 511): heap order (depth d, position p) -> 2^d - 1 + p, for d = 0..8
+//   [511, 511 + npairs): the depth-9 pairs, by increasing p
+constexpr int kHeapNodes = 511;
+
+// w and q of node_solve.cuh, 32 B, so two LDS.128 / LDG.128 fetch them.
+typedef FastWQ NodeWQ;
+typedef FastRh NodeRh;
+
+__device__ __forceinline__ unsigned smem_u32 (const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init (uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init () {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx (uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait (uint64_t* bar, unsigned parity) {
+  const unsigned a = smem_u32(bar);
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n"
+                 " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 " selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while ( ! ok);
+}
+// TMA bulk copy global -> shared (16-byte aligned addresses and size).
+__device__ __forceinline__ void tma_load (void* dst, const void* src, unsigned bytes,
+                                          uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+               "[%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct FastArgs {
+  const BlockDev* blocks;
+  int nblocks;
+  const unsigned short* dtab;   // per shape: 512 depth-9 entries, off | (pair << 15)
+  const unsigned short* ptab;   // per shape: pair list (depth-9 positions)
+  const NodeWQ* wq;             // per block: kHeapNodes + npairs entries, fast order
+  const NodeRh* rh;
+  const double* in;             // tier-0 rows
+  long long in_ld;
+  const int* trcr_row;
+  const int* trcr_prob;
+  double* rec_out;              // UP: [(4 t + f) rec_ld + block]
+  long long rec_ld;
+  const double* sol_in;         // DOWN: [t sol_in_ld + block]
+  long long sol_in_ld;
+  double* out;                  // DOWN: [t out_ld + leaf]
+  long long out_ld;
+  const int* tracers;
+  int ntr;
+  int group;                    // tracers per CTA
+  int sbuf;                     // doubles per staged row (even, >= max_nl + 2)
+  int prefer_mass_con;
+  const double* qglob;
+};
+
+template <int CLS> struct Rows {
+  // Rows of a tracer in the caller-facing buffer (cedr_qlt_inl.hpp:21-58) and where
+  // (min, Qm, max, prev) sit among them.
+  static constexpr bool caas = CLS == CLS_CAAS;
+  static constexpr bool nonneg = CLS == CLS_NN || CLS == CLS_CNN;
+  static constexpr bool consistent_only = CLS == CLS_T || CLS == CLS_CT;
+  static constexpr bool has_prev = CLS == CLS_CST || CLS == CLS_CT || CLS == CLS_CNN;
+  static constexpr int r_min = nonneg ? -1 : 0;
+  static constexpr int r_qm = nonneg ? 0 : 1;
+  static constexpr int r_max = nonneg ? -1 : 2;
+  static constexpr int r_prev = nonneg ? 1 : 3;
+};
+
+// ------------------------------------------------------------------------ UP
+//
+// Block-root record of QLT::l2r_combine_kid_data (cedr_qlt.cpp:339-430) for a
+// fast-path block; for CLS_CAAS the four tree-ordered sums of CAAS::reduce_locally
+// + BfbTreeAllReducer (cedr_caas.cpp:129-201, cedr_bfb_tree_allreduce.cpp:86-124).
+template <int CLS>
+__global__ void __launch_bounds__(kThreads)
+up_kernel (const FastArgs a) {
+  typedef Rows<CLS> R;
+  constexpr bool bounds = ! R::nonneg;
+  constexpr bool prev = R::has_prev || R::caas;
+  constexpr int nrows = (bounds ? 3 : 1) + (prev ? 1 : 0);
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* const stage = reinterpret_cast<double*>(smraw);          // [2][nrows][sbuf]
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(stage + 2*nrows*a.sbuf);
+  double* const wroot = reinterpret_cast<double*>(mbar + 2);       // [2][4 warps][4]
+
+  const int b = blockIdx.x % a.nblocks, grp = blockIdx.x / a.nblocks;
+  const BlockDev B = a.blocks[b];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int src0 = B.leaf0 & ~1, shift = B.leaf0 - src0;
+  const unsigned bytes = 8u*static_cast<unsigned>(((B.leaf0 + B.nl + 1) & ~1) - src0);
+  const int g0 = grp*a.group;
+  const int gn = min(a.group, a.ntr - g0);
+
+  // This thread's four depth-9 nodes: leaf offset and whether it is a pair.
+  const ushort4 e = reinterpret_cast<const ushort4*>(a.dtab + B.ftab_off)[tid];
+  const int o0 = (e.x & 0x7fff) + shift, o1 = (e.y & 0x7fff) + shift,
+    o2 = (e.z & 0x7fff) + shift, o3 = (e.w & 0x7fff) + shift;
+  const bool p0 = e.x >> 15, p1 = e.y >> 15, p2 = e.z >> 15, p3 = e.w >> 15;
+
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&] (const int i) {
+    const int t = a.tracers[g0 + i];
+    const double* src = a.in + static_cast<long long>(a.trcr_row[t])*a.in_ld + src0;
+    double* dst = stage + (i & 1)*nrows*a.sbuf;
+    mbar_expect_tx(&mbar[i & 1], nrows*bytes);
+#pragma unroll
+    for (int f = 0; f < nrows; ++f)
+      tma_load(dst + f*a.sbuf, src + f*a.in_ld, bytes, &mbar[i & 1]);
+  };
+  if (tid == 0) {
+    issue(0);
+    if (gn > 1) issue(1);
+  }
+
+  for (int i = 0; i < gn; ++i) {
+    const int t = a.tracers[g0 + i];
+    mbar_wait(&mbar[i & 1], (i >> 1) & 1);
+    const double* const s = stage + (i & 1)*nrows*a.sbuf;
+    // Leaf values of one depth-9 node -> its record (one leaf, or leaf + leaf).
+    double r[4];   // (min, Qm|clip, max, prev|term) of this thread's depth-7 node
+    {
+      double n[4][4];
+      const int off[4] = {o0, o1, o2, o3};
+      const bool pr[4] = {p0, p1, p2, p3};
+      bool conserve = true;
+      if (R::caas) conserve = a.trcr_prob[t] & 1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        double v[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int o = off[k] + j;
+          if (j == 1 && ! pr[k]) break;
+          if (R::caas) {
+            const double lo = s[o], q = s[a.sbuf + o], hi = s[2*a.sbuf + o];
+            const double term = conserve ? s[3*a.sbuf + o] : q;
+            const double clip = dev::rmin(hi, dev::rmax(lo, q));
+            v[j][0] = 0.0 + lo; v[j][1] = 0.0 + clip; v[j][2] = 0.0 + hi;
+            v[j][3] = 0.0 + term;
+          } else {
+            if (bounds) { v[j][0] = s[R::r_min*a.sbuf + o]; v[j][2] = s[R::r_max*a.sbuf + o]; }
+            v[j][1] = s[R::r_qm*a.sbuf + o];
+            if (prev) v[j][3] = s[R::r_prev*a.sbuf + o];
+          }
+        }
+        if (pr[k]) {
+          if (bounds) {
+            n[k][0] = R::consistent_only ? dev::rmin(v[0][0], v[1][0]) : v[0][0] + v[1][0];
+            n[k][2] = R::consistent_only ? dev::rmax(v[0][2], v[1][2]) : v[0][2] + v[1][2];
+          }
+          n[k][1] = v[0][1] + v[1][1];
+          if (prev) n[k][3] = v[0][3] + v[1][3];
+        } else {
+          if (bounds) { n[k][0] = v[0][0]; n[k][2] = v[0][2]; }
+          n[k][1] = v[0][1];
+          if (prev) n[k][3] = v[0][3];
+        }
+      }
+      // depth 8, then depth 7, in tree order (left + right).
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        if ((f == 0 || f == 2) && ! bounds) continue;
+        if (f == 3 && ! prev) continue;
+        if (R::consistent_only && f == 0)
+          r[f] = dev::rmin(dev::rmin(n[0][f], n[1][f]), dev::rmin(n[2][f], n[3][f]));
+        else if (R::consistent_only && f == 2)
+          r[f] = dev::rmax(dev::rmax(n[0][f], n[1][f]), dev::rmax(n[2][f], n[3][f]));
+        else
+          r[f] = (n[0][f] + n[1][f]) + (n[2][f] + n[3][f]);
+      }
+    }
+    // Depths 6..2 inside the warp: lane l (l % 2^(L+1) == 0) takes left + right.
+#pragma unroll
+    for (int L = 0; L < 5; ++L) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        if ((f == 0 || f == 2) && ! bounds) continue;
+        if (f == 3 && ! prev) continue;
+        const double o = __shfl_down_sync(0xffffffffu, r[f], 1 << L);
+        if (R::consistent_only && f == 0) r[f] = dev::rmin(r[f], o);
+        else if (R::consistent_only && f == 2) r[f] = dev::rmax(r[f], o);
+        else r[f] = r[f] + o;
+      }
+    }
+    double* const wr = wroot + (i & 1)*16;
+    if (lane == 0) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f) wr[warp*4 + f] = r[f];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // Depths 1 and 0, then the record for the next tier.
+      double* rec = a.rec_out + static_cast<long long>(t)*4*a.rec_ld + b;
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        if ((f == 0 || f == 2) && ! bounds) continue;
+        if (f == 3 && ! prev) continue;
+        double v;
+        if (R::consistent_only && f == 0)
+          v = dev::rmin(dev::rmin(wr[f], wr[4 + f]), dev::rmin(wr[8 + f], wr[12 + f]));
+        else if (R::consistent_only && f == 2)
+          v = dev::rmax(dev::rmax(wr[f], wr[4 + f]), dev::rmax(wr[8 + f], wr[12 + f]));
+        else
+          v = (wr[f] + wr[4 + f]) + (wr[8 + f] + wr[12 + f]);
+        rec[f*a.rec_ld] = v;
+      }
+      // All threads are past their reads of this stage (the barrier above).
+      if (i + 2 < gn) issue(i + 2);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------- DOWN
+//
+// QLT::r2l_solve_qp (cedr_qlt.cpp:490-604) over a fast-path block for the
+// shape-preserving classes (st, cst): recompute the block's sums (the up-sweep kept
+// nothing but the block-root record), then solve every node problem from the block
+// root's mass (solved by the tier above) down to the leaves.
+template <int CLS>
+__global__ void __launch_bounds__(kThreads)
+down_kernel (const FastArgs a) {
+  static_assert(CLS == CLS_ST || CLS == CLS_CST, "fast down-sweep: st / cst only");
+  constexpr int nrows = 3;   // Qm_min, Qm, Qm_max are the tracer's first three rows
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* const stage = reinterpret_cast<double*>(smraw);            // [2][3][sbuf]
+  double* const xout = stage + 2*nrows*a.sbuf;                       // [sbuf]
+  double* const un = xout + a.sbuf;                                  // [4][256]
+  double* const d9x = un + 4*256;                                    // [512]
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(d9x + kD9);     // [2]
+
+  const int b = blockIdx.x % a.nblocks, grp = blockIdx.x / a.nblocks;
+  const BlockDev B = a.blocks[b];
+  const int tid = threadIdx.x;
+  const int src0 = B.leaf0 & ~1, shift = B.leaf0 - src0;
+  const unsigned bytes = 8u*static_cast<unsigned>(((B.leaf0 + B.nl + 1) & ~1) - src0);
+  const int g0 = grp*a.group;
+  const int gn = min(a.group, a.ntr - g0);
+  const bool prefer = a.prefer_mass_con != 0;
+  const unsigned short* const dtab = a.dtab + B.ftab_off;
+  const unsigned short* const ptab = a.ptab + B.fpair_off;
+  const NodeWQ* const wq = a.wq + B.fbase;
+  const NodeRh* const rh = a.rh + B.fbase;
+
+  const ushort4 e = reinterpret_cast<const ushort4*>(dtab)[tid];
+  const int off[4] = {(e.x & 0x7fff) + shift, (e.y & 0x7fff) + shift,
+                      (e.z & 0x7fff) + shift, (e.w & 0x7fff) + shift};
+  const bool pr[4] = {(e.x >> 15) != 0, (e.y >> 15) != 0, (e.z >> 15) != 0,
+                      (e.w >> 15) != 0};
+  // Node constants of this thread's micro-subtree (depth 7: heap 127 + tid; depth 8:
+  // heap 255 + 2 tid, + 1) are the same for every tracer: keep them in registers.
+  const NodeWQ c7 = wq[127 + tid], c8a = wq[255 + 2*tid], c8b = wq[256 + 2*tid];
+
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&] (const int i) {
+    const int t = a.tracers[g0 + i];
+    const double* src = a.in + static_cast<long long>(a.trcr_row[t])*a.in_ld + src0;
+    double* dst = stage + (i & 1)*nrows*a.sbuf;
+    mbar_expect_tx(&mbar[i & 1], nrows*bytes);
+#pragma unroll
+    for (int f = 0; f < nrows; ++f)
+      tma_load(dst + f*a.sbuf, src + f*a.in_ld, bytes, &mbar[i & 1]);
+  };
+  if (tid == 0) {
+    issue(0);
+    if (gn > 1) issue(1);
+  }
+
+  // Solve one node through node_solve.cuh; the rare bound-adjustment branch reads
+  // the kids' rhom from global memory.
+  auto solve = [&] (const NodeWQ& c, const int cpos, const double* nd, const double bm,
+                    const double* k0, const double* k1, double& x0, double& x1) {
+    dev::NodeConst nc;
+    nc.w0 = c.w0; nc.w1 = c.w1; nc.q0 = c.q0; nc.q1 = c.q1;
+    const bool lo = bm < nd[0], hi = bm > nd[2];
+    if (lo || hi) {
+      // cedr_qlt_inl.hpp:131-143 needs rhom of the kids; fetch only here.
+      const NodeRh r = rh[cpos];
+      nc.rh0 = r.rh0; nc.rh1 = r.rh1;
+    } else {
+      nc.rh0 = nc.rh1 = 1;
+    }
+    dev::solve_node_bounded(nc, prefer, nd[0], nd[1], nd[2], bm, k0[0], k0[1], k0[2],
+                            k1[0], k1[1], k1[2], x0, x1);
+  };
+
+  for (int i = 0; i < gn; ++i) {
+    const int t = a.tracers[g0 + i];
+    mbar_wait(&mbar[i & 1], (i >> 1) & 1);
+    const double* const s = stage + (i & 1)*nrows*a.sbuf;
+    // ---- micro-subtree sums in registers: 4 depth-9 nodes, 2 depth-8, 1 depth-7.
+    double n9[4][3], n8[2][3], n7[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        const double v0 = s[f*a.sbuf + off[k]];
+        n9[k][f] = pr[k] ? v0 + s[f*a.sbuf + off[k] + 1] : v0;
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      n8[0][f] = n9[0][f] + n9[1][f];
+      n8[1][f] = n9[2][f] + n9[3][f];
+      n7[f] = n8[0][f] + n8[1][f];
+      un[f*256 + 127 + tid] = n7[f];
+    }
+    __syncthreads();
+    // ---- sums of depths 6..0 (heap node h has kids 2h+1, 2h+2).
+    for (int d = 6; d >= 0; --d) {
+      if (tid < (1 << d)) {
+        const int h = (1 << d) - 1 + tid;
+#pragma unroll
+        for (int f = 0; f < 3; ++f)
+          un[f*256 + h] = un[f*256 + 2*h + 1] + un[f*256 + 2*h + 2];
+      }
+      if (d > 5) __syncthreads(); else __syncwarp();
+    }
+    // ---- node problems of depths 0..6. Depths 0..5 fit in warp 0.
+    if (tid == 0) un[3*256] = a.sol_in[static_cast<long long>(t)*a.sol_in_ld + b];
+    __syncwarp();
+    for (int d = 0; d <= 6; ++d) {
+      if (d == 6) __syncthreads();
+      if (tid < (1 << d)) {
+        const int h = (1 << d) - 1 + tid;
+        const double nd[3] = {un[h], un[256 + h], un[512 + h]};
+        const double k0[3] = {un[2*h + 1], un[256 + 2*h + 1], un[512 + 2*h + 1]};
+        const double k1[3] = {un[2*h + 2], un[256 + 2*h + 2], un[512 + 2*h + 2]};
+        double x0, x1;
+        solve(wq[h], h, nd, un[768 + h], k0, k1, x0, x1);
+        un[768 + 2*h + 1] = x0;
+        un[768 + 2*h + 2] = x1;
+      }
+      if (d < 5) __syncwarp();
+    }
+    __syncthreads();
+    // ---- micro-subtree node problems in registers.
+    {
+      const double x7 = un[768 + 127 + tid];
+      double x8[2], x9[4];
+      solve(c7, 127 + tid, n7, x7, n8[0], n8[1], x8[0], x8[1]);
+      solve(c8a, 255 + 2*tid, n8[0], x8[0], n9[0], n9[1], x9[0], x9[1]);
+      solve(c8b, 256 + 2*tid, n8[1], x8[1], n9[2], n9[3], x9[2], x9[3]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (pr[k]) d9x[4*tid + k] = x9[k];
+        else xout[off[k]] = x9[k];
+      }
+    }
+    __syncthreads();
+    // ---- the depth-9 pairs, densely over the threads.
+    for (int j = tid; j < B.npairs; j += kThreads) {
+      const int p = ptab[j];
+      const int o = (dtab[p] & 0x7fff) + shift;
+      double k0[3], k1[3], nd[3];
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        k0[f] = s[f*a.sbuf + o];
+        k1[f] = s[f*a.sbuf + o + 1];
+        nd[f] = k0[f] + k1[f];
+      }
+      double x0, x1;
+      solve(wq[kHeapNodes + j], kHeapNodes + j, nd, d9x[p], k0, k1, x0, x1);
+      xout[o] = x0;
+      xout[o + 1] = x1;
+    }
+    __syncthreads();
+    // ---- coalesced write-back of the block's solved leaf masses.
+    {
+      double* const o = a.out + static_cast<long long>(t)*a.out_ld + B.leaf0;
+      for (int k = tid; k < B.nl; k += kThreads) o[k] = xout[shift + k];
+    }
+    __syncthreads();
+    if (tid == 0 && i + 2 < gn) issue(i + 2);
+  }
+}
+
+} // namespace fast
+} // namespace cedr_b200
+
+#endif

@@ -23,8 +23,14 @@ namespace cedr_b200 {
 
 struct BlockDev {
   int leaf0, nl, ni, nlev;
-  int lvlptr_off, kid_off, ibase, pad;
+  int lvlptr_off, kid_off, ibase;
+  // Fast-path tables (fast_kernels.cuh); ftab_off < 0 if the shape is not fast.
+  int ftab_off, fpair_off, fpos_off, npairs, fbase;
 };
+
+// The same node constants, split and in the fast path's node order.
+struct alignas(16) FastWQ { double w0, w1, q0, q1; };
+struct alignas(16) FastRh { double rh0, rh1; };
 
 // Tracer classes: the six canonical QLT problem classes in the reference's
 // order (cedr_qlt_inl.hpp:101-108), plus CAAS.
@@ -248,6 +254,9 @@ struct RhomArgs {
   const double* in;    // this tier's leaf rhom
   double* root_out;    // next tier's leaf rhom, [block] (may be null at the top)
   dev::NodeConst* nc;
+  const unsigned short* fpos;  // fast-path const positions (may be null)
+  FastWQ* fwq;
+  FastRh* frh;
 };
 
 __global__ void __launch_bounds__(256)
@@ -274,6 +283,15 @@ rhom_kernel (const RhomArgs a) {
       c.rh0 = rh0;
       c.rh1 = rh1;
       a.nc[B.ibase + j] = c;
+      if (a.fpos && B.ftab_off >= 0) {
+        const int pos = B.fbase + a.fpos[B.fpos_off + j];
+        FastWQ wq;
+        wq.w0 = c.w0; wq.w1 = c.w1; wq.q0 = c.q0; wq.q1 = c.q1;
+        a.fwq[pos] = wq;
+        FastRh r;
+        r.rh0 = rh0; r.rh1 = rh1;
+        a.frh[pos] = r;
+      }
     }
     __syncthreads();
   }

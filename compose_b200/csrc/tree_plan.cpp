@@ -42,6 +42,68 @@ void bisect (int cs, int ce, bool imbalanced, std::vector<int>& kids,
 
 } // namespace
 
+// Try to describe `sh` as "perfect to depth 9, leaves or pairs below" (see
+// fast_kernels.cuh). Leaves sh.fast false if it is not of that form.
+static void build_fast_tables (Shape& sh) {
+  sh.fast = false;
+  if (sh.nl < 513 || sh.nl > 1024 || sh.ni != sh.nl - 1) return;
+  const int nl = sh.nl, ni = sh.ni;
+  std::vector<int> depth(ni, -1), pos(ni, -1);
+  std::vector<unsigned short> dtab(512, 0xffff), fpos(ni, 0xffff);
+  std::vector<char> is_pair(512, 0);
+  depth[ni-1] = 0;
+  pos[ni-1] = 0;
+  // Internal nodes are ordered kids-before-parents, so walk from the back.
+  for (int j = ni - 1; j >= 0; --j) {
+    if (depth[j] < 0) return;
+    const int d = depth[j], p = pos[j];
+    if (d > 9) return;
+    const int kid[2] = {sh.kid0[j], sh.kid1[j]};
+    if (d == 9) {
+      // Must be a pair of adjacent leaves.
+      if (kid[0] >= nl || kid[1] != kid[0] + 1) return;
+      dtab[p] = static_cast<unsigned short>(kid[0] | 0x8000);
+      is_pair[p] = 1;
+      continue;
+    }
+    fpos[j] = static_cast<unsigned short>((1 << d) - 1 + p);
+    for (int k = 0; k < 2; ++k) {
+      const int cp = 2*p + k;
+      if (kid[k] >= nl) {
+        depth[kid[k] - nl] = d + 1;
+        pos[kid[k] - nl] = cp;
+      } else {
+        if (d + 1 != 9) return;  // a leaf shallower than depth 9
+        dtab[cp] = static_cast<unsigned short>(kid[k]);
+      }
+    }
+  }
+  std::vector<unsigned short> ptab;
+  for (int p = 0; p < 512; ++p) {
+    if (dtab[p] == 0xffff) return;
+    if (is_pair[p]) ptab.push_back(static_cast<unsigned short>(p));
+  }
+  if (static_cast<int>(ptab.size()) != nl - 512) return;
+  // Pairs take the const positions after the 511 heap nodes, by increasing p.
+  for (int j = 0; j < ni; ++j)
+    if (depth[j] == 9) {
+      const int p = pos[j];
+      const int r = static_cast<int>(std::lower_bound(ptab.begin(), ptab.end(), p) -
+                                     ptab.begin());
+      fpos[j] = static_cast<unsigned short>(511 + r);
+    }
+  // Leaf offsets must increase with p by 1 or 2 (DFS order), starting at 0.
+  int expect = 0;
+  for (int p = 0; p < 512; ++p) {
+    if ((dtab[p] & 0x7fff) != expect) return;
+    expect += is_pair[p] ? 2 : 1;
+  }
+  sh.dtab.swap(dtab);
+  sh.ptab.swap(ptab);
+  sh.fpos.swap(fpos);
+  sh.fast = true;
+}
+
 void make_bisection_tree (int ncells, bool imbalanced, std::vector<int>& kids,
                           std::vector<int64_t>& cellidx) {
   if (ncells < 1) fail("ncells must be >= 1");
@@ -65,6 +127,10 @@ void Plan::build (int ncells_, int nnodes, int root, const int* kids,
   dev_lvlptr.clear();
   dev_kid0.clear();
   dev_kid1.clear();
+  dev_dtab.clear();
+  dev_ptab.clear();
+  dev_fpos.clear();
+  tier0_fast = false;
 
   // ---- DFS: leaf order (= the reference's lci), post-order, heights.
   std::vector<int> post;
@@ -217,6 +283,17 @@ void Plan::build (int ncells_, int nnodes, int root, const int* kids,
       key.insert(key.end(), sh.kid1.begin(), sh.kid1.end());
       std::map<std::vector<int>, int>::iterator it = shape_index.find(key);
       if (it == shape_index.end()) {
+        build_fast_tables(sh);
+        if (sh.fast) {
+          sh.dev_dtab_off = static_cast<int>(dev_dtab.size());
+          sh.dev_ptab_off = static_cast<int>(dev_ptab.size());
+          sh.dev_fpos_off = static_cast<int>(dev_fpos.size());
+          dev_dtab.insert(dev_dtab.end(), sh.dtab.begin(), sh.dtab.end());
+          dev_ptab.insert(dev_ptab.end(), sh.ptab.begin(), sh.ptab.end());
+          // keep ptab/dtab offsets even so ushort4 loads stay aligned
+          while (dev_ptab.size() % 4) dev_ptab.push_back(0);
+          dev_fpos.insert(dev_fpos.end(), sh.fpos.begin(), sh.fpos.end());
+        }
         sh.dev_lvlptr_off = static_cast<int>(dev_lvlptr.size());
         sh.dev_kid_off = static_cast<int>(dev_kid0.size());
         dev_lvlptr.insert(dev_lvlptr.end(), sh.lvlptr.begin(), sh.lvlptr.end());
@@ -258,6 +335,9 @@ void Plan::build (int ncells_, int nnodes, int root, const int* kids,
     tiers.push_back(tier);
     if (last) break;
   }
+  tier0_fast = tiers.size() > 1;
+  for (size_t b = 0; b < tiers[0].blocks.size(); ++b)
+    if ( ! shapes[tiers[0].blocks[b].shape].fast) tier0_fast = false;
   if (ninternal != ncells - 1) {
     std::stringstream ss;
     ss << "internal error: counted " << ninternal << " internal nodes, expected "

@@ -38,6 +38,15 @@ struct Shape {
   bool bisection = false;
   // Offsets into the packed device arrays (filled by pack()).
   int dev_lvlptr_off = 0, dev_kid_off = 0;
+
+  // Fast-path tables (fast_kernels.cuh), present iff `fast`: the shape is a perfect
+  // binary tree down to depth 9 whose 512 depth-9 nodes are single leaves or pairs
+  // of leaves (true for bisection shapes with 512 < nl <= 1024).
+  bool fast = false;
+  std::vector<unsigned short> dtab;  // [512] leaf offset | (is pair << 15)
+  std::vector<unsigned short> ptab;  // depth-9 positions of the pairs, increasing
+  std::vector<unsigned short> fpos;  // [ni] internal node j -> fast const position
+  int dev_dtab_off = 0, dev_ptab_off = 0, dev_fpos_off = 0;
 };
 
 struct Block {
@@ -67,6 +76,9 @@ struct Plan {
 
   // Packed topology for the device.
   std::vector<int> dev_lvlptr, dev_kid0, dev_kid1;
+  std::vector<unsigned short> dev_dtab, dev_ptab, dev_fpos;
+  // True if every tier-0 block has a fast shape (then the fast kernels can run it).
+  bool tier0_fast = false;
 
   // Build from a flat tree: kids[2*i], kids[2*i+1] (-1,-1 for a leaf),
   // cellidx[i] for leaves, rank[i] for leaves (may be null: all rank 0).

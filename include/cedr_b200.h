@@ -173,6 +173,15 @@ int cedr_b200_set_allgather(cedr_b200_cdr* cdr, cedr_b200_allgather_fn fn, void*
 
 /* Number of kernels launched by the last run() on this CDR. */
 int cedr_b200_last_run_launches(const cedr_b200_cdr* cdr, int* n);
+/* Tier-0 kernel selection. Blocks shaped like a recursive bisection with 513..1024
+ * leaves (every block of the cubed-sphere configs) run the fast kernels
+ * (TMA-staged, register micro-subtrees); any other tree runs the generic
+ * shared-memory kernels. Both produce identical bits. set_fast_path(0) before
+ * finish_setup forces the generic kernels (A/B testing); uses_fast_path reports
+ * the choice after finish_setup. */
+int cedr_b200_set_fast_path(cedr_b200_cdr* cdr, int on);
+int cedr_b200_uses_fast_path(const cedr_b200_cdr* cdr, int* on);
+
 /* Per-launch device times of run(): with profiling on, every kernel launch of
  * run() is bracketed by CUDA events on the CDR's stream (measurement aid for
  * bench.py's roofline line; off by default). After a synchronize,

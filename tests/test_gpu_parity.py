@@ -177,3 +177,46 @@ def test_errors_mirror_reference():
         c.declare_tracer(cb.CONSERVE | cb.CONSISTENT)
     with pytest.raises(cb.CedrError, match="0 cells"):
         cb.CAAS(0)
+
+
+@pytest.mark.parametrize("ncells", [5400, 8*513, 8*768, 8192, 2*1023, 3*700 + 1])
+@pytest.mark.parametrize("prefer", [False, True])
+def test_fast_path_blocks_bitwise(oracle, ncells, prefer):
+    """Tier-0 blocks of 513..1024 leaves run the fast kernels (TMA + register
+    micro-subtrees) for the st/cst classes; same bits as the oracle and as the generic
+    kernels, for every block size class (few pairs .. all pairs)."""
+    import compose_b200 as cb
+    from gpu_util import run_qlt_gpu
+    ts, v = R.generate(ncells, seed=3*ncells + prefer)
+    pts = [t.problem_type for t in ts]
+    tree = oracle.bisection_tree(ncells)
+    ref = oracle.qlt(tree, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev, prefer)
+    got, q = run_qlt_gpu(ncells, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev,
+                         prefer=prefer, nrun=2)
+    assert q.uses_fast_path()
+    assert np.array_equal(got, ref)
+    assert R.check(ts, v, got, prefer) == []
+
+
+def test_fast_and_generic_paths_agree_on_headline_inputs(oracle):
+    import torch
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    ncells, nt = 5400, 40
+    rhom, lo, q, hi, prev = (torch.from_numpy(x).cuda() for x in W.headline(ncells, nt, 1))
+    outs = []
+    for fast in (True, False):
+        for kind in ("qlt", "caas"):
+            c = cb.QLT(ncells) if kind == "qlt" else cb.CAAS(ncells)
+            c.set_fast_path(fast)
+            for _ in range(nt):
+                c.declare_tracer(7)
+            c.end_tracer_declarations()
+            c.finish_setup()
+            assert c.uses_fast_path() == fast
+            c.set_rhom(rhom)
+            c.set_Qm(q, lo, hi, prev)
+            c.run()
+            outs.append(c.get_Qm().cpu().numpy())
+    assert np.array_equal(outs[0], outs[2])
+    assert np.array_equal(outs[1], outs[3])
