@@ -73,6 +73,8 @@ SYMBOLS = [
     ("cedr_b200_last_run_launches", C.c_int, [_H, _ip]),
     ("cedr_b200_set_fast_path", C.c_int, [_H, C.c_int]),
     ("cedr_b200_uses_fast_path", C.c_int, [_H, _ip]),
+    ("cedr_b200_set_fused", C.c_int, [_H, C.c_int, C.c_int]),
+    ("cedr_b200_uses_fused", C.c_int, [_H, _ip]),
     ("cedr_b200_set_profiling", C.c_int, [_H, C.c_int]),
     ("cedr_b200_get_launch_times", C.c_int, [_H, C.c_int, C.POINTER(C.c_float), _ip, _ip,
                                              _ip]),
@@ -267,6 +269,14 @@ class CDR:
         _check(self._lib.cedr_b200_uses_fast_path(self._h, C.byref(v)))
         return bool(v.value)
 
+    def set_fused(self, on=True, depth=0):
+        _check(self._lib.cedr_b200_set_fused(self._h, int(bool(on)), int(depth)))
+
+    def uses_fused(self):
+        v = C.c_int(0)
+        _check(self._lib.cedr_b200_uses_fused(self._h, C.byref(v)))
+        return bool(v.value)
+
     def set_profiling(self, on=True):
         _check(self._lib.cedr_b200_set_profiling(self._h, int(bool(on))))
 
@@ -277,7 +287,7 @@ class CDR:
         tags, tiers, n = (C.c_int*cap)(), (C.c_int*cap)(), C.c_int(0)
         _check(self._lib.cedr_b200_get_launch_times(self._h, cap, ms, tags, tiers,
                                                     C.byref(n)))
-        names = ["rhom", "up", "top", "down", "caas_adjust", "exchange"]
+        names = ["rhom", "up", "top", "down", "caas_adjust", "exchange", "fused"]
         return [(names[tags[i]], tiers[i], ms[i]) for i in range(n.value)]
 
     def last_run_launches(self):

@@ -21,6 +21,7 @@
 
 #include "kernels.cuh"
 #include "fast_kernels.cuh"
+#include "fused_kernels.cuh"
 #include "tree_plan.h"
 
 namespace {
@@ -151,6 +152,12 @@ struct cedr_b200_cdr {
   DevBuf<FastRh> d_frh;
   bool fast_enabled = true;   // cedr_b200_set_fast_path
   bool fast_ok = false;       // plan + buffers allow the fast tier-0 kernels
+  bool fused_enabled = true;  // cedr_b200_set_fused
+  bool fused_ok = false;      // plan + device allow the fused persistent kernel
+  int fused_depth = 2;        // tracers between UP(k) and DOWN(k)
+  int fused_capacity = 0;     // co-resident CTAs of the fused kernel on this device
+  DevBuf<unsigned> d_sync;    // [2 nt]: arrival counters, flags
+  DevBuf<int> d_status;
   std::vector<DevBuf<BlockDev> > d_blocks;   // per tier
   DevBuf<dev::NodeConst> d_nc;
   std::vector<DevBuf<double> > d_rhom_tier;  // leaf rhom of tiers >= 1
@@ -354,6 +361,96 @@ void launch_fast_down (cedr_b200_cdr& c, int cls) {
     launch_fast(c, fast::down_kernel<CLS_CST>, a, smem, CEDR_B200_TAG_DOWN);
 }
 
+// ---- fused persistent kernel (fused_kernels.cuh)
+
+bool fused_class (int cls) { return cls == CLS_ST || cls == CLS_CST || cls == CLS_CAAS; }
+
+template <int CLS> int fused_capacity_of (const size_t smem) {
+  CUDA_CHECK(cudaFuncSetAttribute(fused::run_kernel<CLS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+  int per_sm = 0, dev = 0, nsm = 0;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused::run_kernel<CLS>,
+                                                           fused::kThreads, smem));
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  return per_sm*nsm;
+}
+
+int fused_sbuf (const cedr_b200_cdr& c) { return (c.plan.tiers[0].max_nl + 2 + 1) & ~1; }
+
+// Decide whether run() can be the fused kernel; called from finish_setup.
+void fused_setup (cedr_b200_cdr& c) {
+  c.fused_ok = false;
+  if ( ! c.fused_enabled || ! c.fast_ok || std::getenv("CEDR_B200_NO_FUSED")) return;
+  if (c.nranks > 1) return;
+  if (c.plan.tiers.size() != 2 || c.plan.tiers[1].blocks.size() != 1) return;
+  const int sbuf = fused_sbuf(c);
+  const size_t nl1 = c.plan.tiers[1].nleaves;
+  if (4*(2*nl1 - 1) > fused::top_scratch_doubles(sbuf)) return;
+  int dev = 0, coop = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if ( ! coop) return;
+  const size_t smem = fused::smem_bytes(sbuf);
+  int cap = c.is_caas ? fused_capacity_of<CLS_CAAS>(smem) :
+    std::min(fused_capacity_of<CLS_ST>(smem), fused_capacity_of<CLS_CST>(smem));
+  if (cap < static_cast<int>(c.plan.tiers[0].blocks.size())) return;
+  c.fused_capacity = cap;
+  if (const char* e = std::getenv("CEDR_B200_FUSED_DEPTH"))
+    c.fused_depth = std::max(1, std::atoi(e));
+  c.d_sync.alloc(2*std::max<size_t>(1, c.trcr_prob.size()));
+  c.d_status.alloc(1);
+  CUDA_CHECK(cudaMemsetAsync(c.d_status.p, 0, sizeof(int), c.stream));
+  c.fused_ok = true;
+}
+
+
+void launch_fused (cedr_b200_cdr& c, int cls) {
+  const int ntr = static_cast<int>(c.cls_tracers[cls].size());
+  if (ntr == 0) return;
+  fused::Args a;
+  std::memset(&a, 0, sizeof(a));
+  a.blocks = c.d_blocks[0].p;
+  a.nblocks = static_cast<int>(c.plan.tiers[0].blocks.size());
+  a.dtab = c.d_dtab.p;
+  a.ptab = c.d_ptab.p;
+  a.wq = c.d_fwq.p;
+  a.rh = c.d_frh.p;
+  a.in = c.in;
+  a.in_ld = c.ld;
+  a.trcr_row = c.d_trcr_row.p;
+  a.trcr_prob = c.d_trcr_prob.p;
+  a.rec = c.d_rec[1].p;
+  a.rec_ld = c.tier_ld[1];
+  a.sol = c.d_sol[1].p;
+  a.sol_ld = c.tier_ld[1];
+  a.out = c.out;
+  a.out_ld = c.ld;
+  a.tracers = c.d_cls_tracers[cls].p;
+  a.ntr = ntr;
+  a.sbuf = fused_sbuf(c);
+  a.prefer_mass_con = c.prefer_mass_con;
+  a.depth = c.fused_depth;
+  a.cnt = c.d_sync.p;
+  a.flag = c.d_sync.p + ntr;
+  a.status = c.d_status.p;
+  a.caas_scal = c.d_caas_scal.p;
+  a.top = base_args(c, cls, 1);
+  const int nlanes = std::max(1, std::min(c.fused_capacity/a.nblocks, ntr));
+  const dim3 grid(static_cast<unsigned>(a.nblocks)*nlanes), block(fused::kThreads);
+  const size_t smem = fused::smem_bytes(a.sbuf);
+  CUDA_CHECK(cudaMemsetAsync(c.d_sync.p, 0, 2*static_cast<size_t>(ntr)*sizeof(unsigned),
+                             c.stream));
+  void* params[] = {&a};
+  const void* fn = cls == CLS_ST ? reinterpret_cast<const void*>(fused::run_kernel<CLS_ST>) :
+    cls == CLS_CST ? reinterpret_cast<const void*>(fused::run_kernel<CLS_CST>) :
+    reinterpret_cast<const void*>(fused::run_kernel<CLS_CAAS>);
+  LaunchTimer lt(c, CEDR_B200_TAG_FUSED, 0);
+  CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, block, params, smem, c.stream));
+  ++c.last_launches;
+}
+
 void run_rhom (cedr_b200_cdr& c) {
   const int ntiers = static_cast<int>(c.plan.tiers.size());
   for (int k = 0; k < ntiers; ++k) {
@@ -384,6 +481,7 @@ void run_qlt (cedr_b200_cdr& c) {
   run_rhom(c);
   for (int cls = 0; cls < CLS_CAAS; ++cls) {
     if (c.cls_tracers[cls].empty()) continue;
+    if (c.fused_ok && fused_class(cls)) { launch_fused(c, cls); continue; }
     for (int k = 0; k < top; ++k) {
       if (k == 0 && c.fast_ok && fast_class(cls, MODE_UP)) launch_fast_up(c, cls);
       else launch_sweep_any(c, cls, k, MODE_UP, base_args(c, cls, k));
@@ -400,6 +498,7 @@ void run_caas (cedr_b200_cdr& c) {
   cedr_b200_throw_if(c.nranks > 1, "multi-rank CAAS::run is not wired up yet");
   cedr_b200_throw_if(c.caas_sum_mode != CEDR_B200_CAAS_SUM_TREE,
                      "CAAS sequential-order sums are not implemented yet");
+  if (c.fused_ok) { launch_fused(c, CLS_CAAS); return; }
   const int ntiers = static_cast<int>(c.plan.tiers.size());
   const int top = ntiers - 1;
   for (int k = 0; k < top; ++k) {
@@ -503,6 +602,7 @@ void finish_setup (cedr_b200_cdr& c) {
   }
   c.d_qglob.alloc(2*static_cast<size_t>(nt));
   c.d_caas_scal.alloc(2*static_cast<size_t>(nt));
+  fused_setup(c);
   c.finished = true;
 }
 
@@ -802,7 +902,27 @@ int cedr_b200_set_stream (cedr_b200_cdr* c, void* s) {
 }
 
 int cedr_b200_synchronize (cedr_b200_cdr* c) {
-  return guarded([&] { CUDA_CHECK(cudaStreamSynchronize(c->stream)); });
+  return guarded([&] {
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->d_status.p) {
+      int st = 0;
+      CUDA_CHECK(cudaMemcpy(&st, c->d_status.p, sizeof(int), cudaMemcpyDeviceToHost));
+      if (st) throw std::runtime_error("cedr_b200: the fused run() kernel gave up waiting "
+                                       "for a tracer's root (results are invalid)");
+    }
+  });
+}
+
+int cedr_b200_set_fused (cedr_b200_cdr* c, int on, int depth) {
+  return guarded([&] {
+    cedr_b200_throw_if(c->finished, "set_fused must precede finish_setup");
+    c->fused_enabled = on != 0;
+    if (depth > 0) c->fused_depth = depth;
+  });
+}
+
+int cedr_b200_uses_fused (const cedr_b200_cdr* c, int* on) {
+  return guarded([&] { *on = c->fused_ok; });
 }
 
 int cedr_b200_set_allgather (cedr_b200_cdr* c, cedr_b200_allgather_fn fn, void* ctx) {

@@ -29,8 +29,8 @@ struct BlockDev {
 };
 
 // The same node constants, split and in the fast path's node order.
-struct alignas(16) FastWQ { double w0, w1, q0, q1; };
-struct alignas(16) FastRh { double rh0, rh1; };
+typedef dev::NodeWQ FastWQ;
+typedef dev::NodeRh FastRh;
 
 // Tracer classes: the six canonical QLT problem classes in the reference's
 // order (cedr_qlt_inl.hpp:101-108), plus CAAS.
@@ -70,10 +70,11 @@ struct SweepArgs {
   double* caas_scal;    // [2*t]: mode (-1, 0, +1), [2*t+1]: fac
 };
 
+// Sweep of one block for one tracer by the whole CTA (any blockDim); `sm` holds
+// 4*(nl + ni) doubles. Contains __syncthreads: every thread of the CTA must call it.
 template <int CLS, int MODE>
-__global__ void __launch_bounds__(256)
-sweep_kernel (const SweepArgs a) {
-  extern __shared__ double sm[];
+__device__ __forceinline__ void
+sweep_block (const SweepArgs& a, const int b, const int t, double* const sm) {
   constexpr bool caas = CLS == CLS_CAAS;
   constexpr bool nonneg = CLS == CLS_NN || CLS == CLS_CNN;
   constexpr bool consistent_only = CLS == CLS_T || CLS == CLS_CT;
@@ -84,8 +85,6 @@ sweep_kernel (const SweepArgs a) {
   constexpr bool need_bounds = ! nonneg && (MODE != MODE_DOWN || ! consistent_only);
   constexpr bool need_prev = has_prev && MODE != MODE_DOWN;
 
-  const int b = blockIdx.x % a.nblocks;
-  const int t = a.tracers[blockIdx.x / a.nblocks];
   const BlockDev B = a.blocks[b];
   const int nn = B.nl + B.ni;
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -113,8 +112,8 @@ sweep_kernel (const SweepArgs a) {
       // reduction as 0 + value (accumulator start, cedr_caas.cpp:145-151).
       const bool conserve = a.trcr_prob[t] & 1;
       for (int i = tid; i < B.nl; i += nth) {
-        const double lo = p0[i], q = p1[i], hi = p2[i];
-        const double term = conserve ? p3[i] : q;
+        const double lo = __ldcg(p0 + i), q = __ldcg(p1 + i), hi = __ldcg(p2 + i);
+        const double term = conserve ? __ldcg(p3 + i) : q;
         const double clip = dev::rmin(hi, dev::rmax(lo, q));
         f0[i] = 0.0 + lo;
         f1[i] = 0.0 + clip;
@@ -122,10 +121,12 @@ sweep_kernel (const SweepArgs a) {
         f3[i] = 0.0 + term;
       }
     } else {
+      // Read-once data; for tiers >= 1 it may have been written by other SMs of the
+      // same (fused) launch, so bypass L1.
       for (int i = tid; i < B.nl; i += nth) {
-        if (need_bounds) { f0[i] = p0[i]; f2[i] = p2[i]; }
-        f1[i] = p1[i];
-        if (need_prev) f3[i] = p3[i];
+        if (need_bounds) { f0[i] = __ldcg(p0 + i); f2[i] = __ldcg(p2 + i); }
+        f1[i] = __ldcg(p1 + i);
+        if (need_prev) f3[i] = __ldcg(p3 + i);
       }
     }
   }
@@ -240,6 +241,13 @@ sweep_kernel (const SweepArgs a) {
   }
   double* const o = a.out + (long long) t*a.out_ld + B.leaf0;
   for (int i = tid; i < B.nl; i += nth) o[i] = f3[i];
+}
+
+template <int CLS, int MODE>
+__global__ void __launch_bounds__(256)
+sweep_kernel (const SweepArgs a) {
+  extern __shared__ double sm[];
+  sweep_block<CLS, MODE>(a, blockIdx.x % a.nblocks, a.tracers[blockIdx.x / a.nblocks], sm);
 }
 
 // rhom sweep: word 0 of every slot in the reference (cedr_qlt.cpp:356-360),

@@ -168,6 +168,156 @@ solve_node_bounded (const NodeConst& c, const bool prefer_mass_con,
        ! prefer_mass_con, x0, x1);
 }
 
+// ---------------------------------------------------------------------------
+// Lean form of the shape-preserving node problem for the fused kernels: the same
+// operations on the same operands as solve_node_bounded / qp2d above (hence the same
+// bits), arranged so that the common flow is short straight-line code:
+//   - the node-level bound adjustment (b outside [pmin, pmax]) is a cold call;
+//   - fabs is folded into compare / multiply operand modifiers;
+//   - check_lu's two corner residuals are evaluated without nested early returns;
+//   - in the boundary branch, the "drop the first minimum and the first maximum of the
+//     four alphas, keep the other two in index order" scan of cedr_local_inl.hpp:112-131
+//     is replaced by two compares whenever a0 < a2 and a1 < a3 (a box with nonzero
+//     width on both sides): then the first minimum has index 0 or 1 (a2, a3 are
+//     strictly above a0, a1) and the first maximum has index 2 or 3, so the scan keeps
+//     {the larger of a0, a1; ties -> 1} and {the smaller of a2, a3; ties -> 3} whatever
+//     their mutual order. Anything else takes the literal scan.
+struct alignas(16) NodeWQ { double w0, w1, q0, q1; };
+struct alignas(16) NodeRh { double rh0, rh1; };
+
+__device__ __noinline__ void
+solve_bounded_cold (const NodeWQ c, const NodeRh* rh, const bool prefer, const double pmin,
+                    const double pqm, const double pmax, const double b, const double lo0,
+                    const double y0, const double hi0, const double lo1, const double y1,
+                    const double hi1, double* x) {
+  NodeConst nc;
+  nc.w0 = c.w0; nc.w1 = c.w1; nc.q0 = c.q0; nc.q1 = c.q1;
+  const NodeRh r = *rh;
+  nc.rh0 = r.rh0; nc.rh1 = r.rh1;
+  double x0, x1;
+  solve_node_bounded(nc, prefer, pmin, pqm, pmax, b, lo0, y0, hi0, lo1, y1, hi1, x0, x1);
+  x[0] = x0; x[1] = x1;
+}
+
+// The literal boundary scan (any alpha order), out of line.
+__device__ __noinline__ void
+qp2d_boundary_cold (const double w0, const double w1, const double b, const double lo0,
+                    const double lo1, const double hi0, const double hi1, const double y0,
+                    const double y1, const bool clip, double* x) {
+  const double xb = 0.5*b;
+  double al[4];
+  al[0] = lo1 - xb; al[1] = -(hi0 - xb); al[2] = hi1 - xb; al[3] = -(lo0 - xb);
+  double mn = al[0], mx = al[0];
+  int imin = 0, imax = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i) {
+    if (al[i] < mn) { mn = al[i]; imin = i; }
+    if (al[i] > mx) { mx = al[i]; imax = i; }
+  }
+  int ai0 = -1, ai1 = -1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i != imin && i != imax) {
+      if (ai0 < 0) ai0 = i;
+      else if (ai1 < 0) ai1 = i;
+    }
+  const double alpha0 = ai0 == 0 ? al[0] : ai0 == 1 ? al[1] : ai0 == 2 ? al[2] : al[3];
+  const double alpha1 = ai1 == 1 ? al[1] : ai1 == 2 ? al[2] : al[3];
+  double obj0, obj1;
+  {
+    const double d0 = y0 - (xb - alpha0), d1 = y1 - (xb + alpha0);
+    obj0 = w0*(d0*d0) + w1*(d1*d1);
+  }
+  {
+    const double d0 = y0 - (xb - alpha1), d1 = y1 - (xb + alpha1);
+    obj1 = w0*(d0*d0) + w1*(d1*d1);
+  }
+  const int ai = obj0 <= obj1 ? ai0 : ai1;
+  double x0, x1;
+  if (ai == 0 || ai == 2) {
+    x1 = ai == 0 ? lo1 : hi1;
+    x0 = b - x1;
+    if (clip) x0 = rmin(hi0, rmax(lo0, x0));
+  } else {
+    x0 = ai == 1 ? hi0 : lo0;
+    x1 = b - x0;
+    if (clip) x1 = rmin(hi1, rmax(lo1, x1));
+  }
+  x[0] = x0; x[1] = x1;
+}
+
+template <bool PREFER>
+__device__ __forceinline__ void
+solve_bounded_lean (const NodeWQ& c, const NodeRh* rh, const double pmin, const double pqm,
+                    const double pmax, const double b, const double lo0, const double y0,
+                    const double hi0, const double lo1, const double y1, const double hi1,
+                    double& x0, double& x1) {
+  if (b < pmin || b > pmax) {
+    double x[2];
+    solve_bounded_cold(c, rh, PREFER, pmin, pqm, pmax, b, lo0, y0, hi0, lo1, y1, hi1, x);
+    x0 = x[0]; x1 = x[1];
+    return;
+  }
+  if (b == pqm) {
+    if (y0 >= lo0 && y0 <= hi0 && y1 >= lo1 && y1 <= hi1) { x0 = y0; x1 = y1; return; }
+  }
+  if ( ! PREFER) {
+    // calc_r_tol + check_lu (cedr_local_inl.hpp:13-41); only infeasibility returns.
+    double ab = fabs(b) > fabs(y0) ? b : y0;
+    ab = fabs(ab) > fabs(y1) ? ab : y1;
+    const double r_tol = CEDR_B200_TEN_EPS*fabs(ab);
+    const double r1 = (lo0 - b) + lo1;
+    const double r2 = (hi0 - b) + hi1;
+    const bool c1 = ! (fabs(r1) <= r_tol);
+    const bool inf_lo = c1 && r1 > 0;
+    const bool inf_hi = c1 && ! (fabs(r2) <= r_tol) && r2 < 0;
+    if (inf_lo || inf_hi) {
+      x0 = inf_lo ? lo0 : hi0;
+      x1 = inf_lo ? lo1 : hi1;
+      return;
+    }
+  }
+  { // Unconstrained optimum, cedr_local_inl.hpp:80-97.
+    const double qmass = c.q0 + c.q1;
+    const double dm = (b - y0) - y1;
+    const double lambda = dm/qmass;
+    x0 = y0 + lambda*c.q0;
+    x1 = y1 + lambda*c.q1;
+    if ( ! (x0 < lo0 || x0 > hi0) && ! (x1 < lo1 || x1 > hi1)) return;
+  }
+  // Boundary branch. a0 bottom, a1 right, a2 top, a3 left.
+  const double xb = 0.5*b;
+  const double a0 = lo1 - xb, a1 = -(hi0 - xb), a2 = hi1 - xb, a3 = -(lo0 - xb);
+  const bool L = a1 >= a0, H = a3 <= a2;       // kept pair = (max(a0,a1), min(a2,a3))
+  const double aL = L ? a1 : a0, aH = H ? a3 : a2;
+  if ( ! (a0 < a2 && a1 < a3)) {
+    double x[2];
+    qp2d_boundary_cold(c.w0, c.w1, b, lo0, lo1, hi0, hi1, y0, y1, ! PREFER, x);
+    x0 = x[0]; x1 = x[1];
+    return;
+  }
+  double obj0, obj1;
+  {
+    const double d0 = y0 - (xb - aL), d1 = y1 - (xb + aL);
+    obj0 = c.w0*(d0*d0) + c.w1*(d1*d1);
+  }
+  {
+    const double d0 = y0 - (xb - aH), d1 = y1 - (xb + aH);
+    obj1 = c.w0*(d0*d0) + c.w1*(d1*d1);
+  }
+  const bool first = obj0 <= obj1;
+  // ai = first ? (L ? 1 : 0) : (H ? 3 : 2); odd ai pins x0, even pins x1.
+  const bool pin0 = first ? L : H;
+  const double v = first ? (L ? hi0 : lo1) : (H ? lo0 : hi1);
+  double o = b - v;
+  if ( ! PREFER) {
+    const double olo = pin0 ? lo1 : lo0, ohi = pin0 ? hi1 : hi0;
+    o = rmin(ohi, rmax(olo, o));
+  }
+  x0 = pin0 ? v : o;
+  x1 = pin0 ? o : v;
+}
+
 // The nonnegative node problem, cedr_qlt_inl.hpp:188-197 -> solve_1eq_nonneg
 // (cedr_local_inl.hpp:307-330) with n = 2, least squares: bounds [0, b/a_i],
 // default clip / early-exit flags (independent of the CDR option).

@@ -181,6 +181,14 @@ int cedr_b200_last_run_launches(const cedr_b200_cdr* cdr, int* n);
  * the choice after finish_setup. */
 int cedr_b200_set_fast_path(cedr_b200_cdr* cdr, int on);
 int cedr_b200_uses_fast_path(const cedr_b200_cdr* cdr, int* on);
+/* When the fast shapes apply and the block roots form a single tier-1 block, run() is
+ * ONE persistent cooperative kernel per problem class (fused_kernels.cuh): up-sweep,
+ * tier-1 sweep and down-sweep pipelined over tracers, the down-sweep re-reading the
+ * leaves from L2. set_fused(0, 0) before finish_setup forces the multi-launch path;
+ * depth > 0 sets the number of tracers between a block's up- and down-sweep
+ * (default 2). Results are bit-identical either way. */
+int cedr_b200_set_fused(cedr_b200_cdr* cdr, int on, int depth);
+int cedr_b200_uses_fused(const cedr_b200_cdr* cdr, int* on);
 
 /* Per-launch device times of run(): with profiling on, every kernel launch of
  * run() is bracketed by CUDA events on the CDR's stream (measurement aid for
@@ -189,7 +197,8 @@ int cedr_b200_uses_fast_path(const cedr_b200_cdr* cdr, int* on);
  * kernel tag names_host[i] (see CEDR_B200_TAG_*). */
 enum {
   CEDR_B200_TAG_RHOM = 0, CEDR_B200_TAG_UP = 1, CEDR_B200_TAG_TOP = 2,
-  CEDR_B200_TAG_DOWN = 3, CEDR_B200_TAG_CAAS_ADJUST = 4, CEDR_B200_TAG_EXCHANGE = 5
+  CEDR_B200_TAG_DOWN = 3, CEDR_B200_TAG_CAAS_ADJUST = 4, CEDR_B200_TAG_EXCHANGE = 5,
+  CEDR_B200_TAG_FUSED = 6
 };
 int cedr_b200_set_profiling(cedr_b200_cdr* cdr, int on);
 int cedr_b200_get_launch_times(cedr_b200_cdr* cdr, int cap, float* ms_host,

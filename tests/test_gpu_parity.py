@@ -181,7 +181,8 @@ def test_errors_mirror_reference():
 
 @pytest.mark.parametrize("ncells", [5400, 8*513, 8*768, 8192, 2*1023, 3*700 + 1])
 @pytest.mark.parametrize("prefer", [False, True])
-def test_fast_path_blocks_bitwise(oracle, ncells, prefer):
+@pytest.mark.parametrize("fused,depth", [(False, 0), (True, 1), (True, 2), (True, 3)])
+def test_fast_path_blocks_bitwise(oracle, ncells, prefer, fused, depth):
     """Tier-0 blocks of 513..1024 leaves run the fast kernels (TMA + register
     micro-subtrees) for the st/cst classes; same bits as the oracle and as the generic
     kernels, for every block size class (few pairs .. all pairs)."""
@@ -192,10 +193,56 @@ def test_fast_path_blocks_bitwise(oracle, ncells, prefer):
     tree = oracle.bisection_tree(ncells)
     ref = oracle.qlt(tree, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev, prefer)
     got, q = run_qlt_gpu(ncells, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev,
-                         prefer=prefer, nrun=2)
+                         prefer=prefer, nrun=2, fused=fused, depth=depth)
     assert q.uses_fast_path()
+    assert q.uses_fused() == fused
     assert np.array_equal(got, ref)
     assert R.check(ts, v, got, prefer) == []
+
+
+@pytest.mark.parametrize("ncells,nt,depth", [(86400, 24, 2), (86400, 9, 1), (5400, 700, 2),
+                                             (5400, 333, 4), (8*768, 150, 3)])
+def test_fused_pipeline_many_tracers_bitwise(oracle, ncells, nt, depth):
+    """The fused persistent kernel with several tracers per CTA lane (the up/down
+    pipeline, the per-tracer arrival counters and the in-kernel tier-1 sweep all in play)
+    for QLT `cst` and CAAS, against the oracle and against the multi-launch path."""
+    from compose_b200 import workloads as W
+    from gpu_util import run_qlt_gpu, run_caas_gpu
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, 3)
+    pts = [7]*nt
+    tree = oracle.bisection_tree(ncells)
+    ref = oracle.qlt(tree, pts, rhom, lo, q, hi, prev)
+    got, c = run_qlt_gpu(ncells, pts, rhom, lo, q, hi, prev, nrun=2, fused=True, depth=depth)
+    assert c.uses_fused()
+    assert c.last_run_launches() <= 4
+    assert np.array_equal(got, ref)
+    ref = oracle.caas(ncells, pts, lo, q, hi, prev, tree=tree)
+    got, c = run_caas_gpu(ncells, pts, rhom, lo, q, hi, prev, fused=True, depth=depth)
+    assert c.uses_fused() and c.last_run_launches() == 1
+    assert np.array_equal(got, ref)
+    got2, c2 = run_caas_gpu(ncells, pts, rhom, lo, q, hi, prev, fused=False)
+    assert not c2.uses_fused()
+    assert np.array_equal(got, got2)
+
+
+def test_fused_mixed_classes_and_noop_inputs(oracle):
+    """st and cst tracers go through the fused kernel, the other four classes through
+    the multi-launch kernels, in one run(); and inputs already in bounds with
+    Qm == Qm_prev must come back bit-for-bit (the quick exit, cedr_qlt_inl.hpp:145-160)."""
+    from compose_b200 import workloads as W
+    from gpu_util import run_qlt_gpu
+    ncells = 5400
+    ts, v = R.generate(ncells, seed=99)
+    pts = [t.problem_type for t in ts]
+    tree = oracle.bisection_tree(ncells)
+    ref = oracle.qlt(tree, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev)
+    got, c = run_qlt_gpu(ncells, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev, fused=True)
+    assert c.uses_fused()
+    assert np.array_equal(got, ref)
+    nt = 40
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, 5)
+    got, c = run_qlt_gpu(ncells, [7]*nt, rhom, lo, prev, hi, prev, fused=True)
+    assert np.array_equal(got, prev)
 
 
 def test_fast_and_generic_paths_agree_on_headline_inputs(oracle):
