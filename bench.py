@@ -158,8 +158,10 @@ def config_dict(args, ncells, nt):
             "step": "QLT::run + CAAS::run (tree-ordered sums), 2*ncells*nt updates",
             "l2": "inputs (>= 0.6 GB per reconstructor) exceed the 126 MB L2; no flush",
             "parallelism": ("single GPU" if args.gpus == 1 else
-                            "%d GPUs, tracers partitioned (interim; subtree partition next)"
-                            % args.gpus)}
+                            "%d GPUs, cells partitioned by subtree (each rank owns "
+                            "ncells/%d contiguous cells = whole tier-0 blocks); one NCCL "
+                            "all-gather of the block roots per run(), tiers above "
+                            "replicated in fixed tree order" % (args.gpus, args.gpus))}
 
 
 def main():
@@ -193,6 +195,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"    # keep NCCL's version banner off stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -201,20 +204,25 @@ def main():
         torch.cuda.synchronize()
 
     ncells, nt, cid = workload_dims(args.workload)
-    # Interim multi-GPU decomposition: each rank takes a contiguous slice of tracers.
-    nt_lcl = nt//world + (1 if rank < nt % world else 0)
-    t_first = rank*(nt//world) + min(rank, nt % world)
+    # Subtree partition: rank r owns cells [r*nl, (r+1)*nl) of every tracer.
+    if ncells % world:
+        raise SystemExit("bench.py: ncells must be divisible by the number of GPUs")
+    nl = ncells//world
+    nt_lcl = nt
 
     # ---- inputs, resident in HBM before any timed region
-    rhom, lo, q, hi, prev = cb.fill_headline(ncells, nt, cid)
-    if world > 1:
-        lo, q, hi, prev = (x[t_first:t_first + nt_lcl].contiguous() for x in (lo, q, hi, prev))
+    rhom, lo, q, hi, prev = cb.fill_headline(ncells, nt, cid, cell0=rank*nl, nlclcells=nl)
 
     def make(kind):
-        c = cb.QLT(ncells) if kind == "qlt" else cb.CAAS(ncells)
+        if kind == "qlt":
+            c = cb.QLT(ncells, rank=rank, nranks=world)
+        else:
+            c = cb.CAAS(nl, cell0=rank*nl, ncells_global=ncells, rank=rank, nranks=world)
         for _ in range(nt_lcl):
             c.declare_tracer(CST)
         c.end_tracer_declarations()
+        if world > 1:
+            c.enable_distributed(world)
         c.finish_setup()
         c.set_rhom(rhom)
         c.set_Qm(q, lo, hi, prev)
@@ -282,10 +290,10 @@ def main():
     if not args.no_e2e:
         del qlt, caas
         torch.cuda.empty_cache()
-        pipe = HostStepPipeline(ncells, nt_lcl)
+        pipe = HostStepPipeline(ncells, nt_lcl, rank=rank, nranks=world)
         pin = lambda x: x.cpu().pin_memory()
         rhom_h, lo_h, q_h, hi_h, prev_h = (pin(x) for x in (rhom, lo, q, hi, prev))
-        out_h = {k: torch.empty((nt_lcl, ncells), dtype=torch.float64).pin_memory()
+        out_h = {k: torch.empty((nt_lcl, nl), dtype=torch.float64).pin_memory()
                  for k in pipe.kinds}
         pipe.step(rhom_h, lo_h, q_h, hi_h, prev_h, out_h)       # warm-up
         barrier()

@@ -70,6 +70,12 @@ SYMBOLS = [
     ("cedr_b200_set_stream", C.c_int, [_H, _vp]),
     ("cedr_b200_synchronize", C.c_int, [_H]),
     ("cedr_b200_set_allgather", C.c_int, [_H, ALLGATHER_FN, _vp]),
+    ("cedr_b200_get_exchange_count", C.c_int, [_H, C.POINTER(C.c_size_t)]),
+    ("cedr_b200_set_exchange_buffers", C.c_int, [_H, _vp, _vp]),
+    ("cedr_b200_get_exchange_buffers", C.c_int, [_H, C.POINTER(_vp), C.POINTER(_vp)]),
+    ("cedr_b200_run_phase", C.c_int, [_H, C.c_int]),
+    ("cedr_b200_partition_probe", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, _ip, _ip, _ip, _ip, _ip, _ip, _ip]),
     ("cedr_b200_last_run_launches", C.c_int, [_H, _ip]),
     ("cedr_b200_set_fast_path", C.c_int, [_H, C.c_int]),
     ("cedr_b200_uses_fast_path", C.c_int, [_H, _ip]),
@@ -85,6 +91,9 @@ SYMBOLS = [
     ("cedr_b200_make_1d_tree", C.c_int, [C.c_int, C.c_int, _ip, _lp]),
     ("cedr_b200_fill_headline", C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int, _vp, _vp,
                                           _vp, _vp, _vp, _vp]),
+    ("cedr_b200_fill_headline_range", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_int64, C.c_int, _vp, _vp, _vp, _vp, _vp,
+                                                _vp]),
 ]
 
 _lib = None
@@ -251,6 +260,51 @@ class CDR:
     def run(self):
         _check(self._lib.cedr_b200_run(self._h))
 
+    # -- multi-rank (subtree partition; one process per GPU)
+    def exchange_count(self):
+        v = C.c_size_t(0)
+        _check(self._lib.cedr_b200_get_exchange_count(self._h, C.byref(v)))
+        return v.value
+
+    def enable_distributed(self, nranks, group=None):
+        """Call between end_tracer_declarations and finish_setup on every rank: allocates
+        the exchange message buffers as torch tensors and wires run()'s one all-gather to
+        torch.distributed (NCCL over NVLink on a GPU box)."""
+        import torch
+        import torch.distributed as dist
+        n = self.exchange_count()
+        self._xsend = torch.zeros(max(n, 1), dtype=torch.float64, device="cuda")
+        self._xrecv = torch.zeros(max(n, 1)*nranks, dtype=torch.float64, device="cuda")
+        _check(self._lib.cedr_b200_set_exchange_buffers(self._h, _ptr(self._xsend),
+                                                        _ptr(self._xrecv)))
+
+        def gather(ctx, send, recv, count, stream):
+            try:
+                dist.all_gather_into_tensor(self._xrecv, self._xsend, group=group)
+                return 0
+            except Exception:   # surfaced as a CedrError by run()
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._cb = ALLGATHER_FN(gather)
+        _check(self._lib.cedr_b200_set_allgather(self._h, self._cb, None))
+
+    def run_phase(self, phase):
+        _check(self._lib.cedr_b200_run_phase(self._h, int(phase)))
+
+    def exchange_buffers(self, nranks):
+        """(send, recv) as cuda float64 tensors viewing the CDR's message buffers; only
+        for emulating several ranks in one process (tests)."""
+        return self._xsend, self._xrecv
+
+    def use_tensor_exchange_buffers(self, nranks):
+        import torch
+        n = self.exchange_count()
+        self._xsend = torch.zeros(max(n, 1), dtype=torch.float64, device="cuda")
+        self._xrecv = torch.zeros(max(n, 1)*nranks, dtype=torch.float64, device="cuda")
+        _check(self._lib.cedr_b200_set_exchange_buffers(self._h, _ptr(self._xsend),
+                                                        _ptr(self._xrecv)))
+
     def get_Qm(self, out=None, t0=0, nt=None):
         import torch
         nt = self.get_num_tracers() - t0 if nt is None else nt
@@ -338,17 +392,20 @@ class CAAS(CDR):
                                                int(rank), int(nranks)))
 
 
-def fill_headline(ncells, nt, config_id, lda=None):
-    """Synthetic SURVEY 8(d) workload generated on the device. Returns cuda tensors
-    (rhom[ncells], qm_min, qm, qm_max, qm_prev: [nt, lda])."""
+def fill_headline(ncells, nt, config_id, lda=None, cell0=0, nlclcells=None):
+    """Synthetic SURVEY 8(d) workload generated on the device, optionally only cells
+    [cell0, cell0 + nlclcells). Returns cuda tensors (rhom[nlcl], qm_min, qm, qm_max,
+    qm_prev: [nt, lda])."""
     import torch
     lib = load_library()
-    lda = ncells if lda is None else lda
-    rhom = torch.empty(ncells, dtype=torch.float64, device="cuda")
+    nl = ncells - cell0 if nlclcells is None else nlclcells
+    lda = nl if lda is None else lda
+    rhom = torch.empty(nl, dtype=torch.float64, device="cuda")
     arrs = [torch.empty((nt, lda), dtype=torch.float64, device="cuda") for _ in range(4)]
-    _check(lib.cedr_b200_fill_headline(int(ncells), int(nt), int(lda), int(config_id),
-                                       _ptr(rhom), _ptr(arrs[0]), _ptr(arrs[1]),
-                                       _ptr(arrs[2]), _ptr(arrs[3]), _stream_ptr()))
+    _check(lib.cedr_b200_fill_headline_range(int(ncells), int(cell0), int(nl), int(nt),
+                                             int(lda), int(config_id), _ptr(rhom),
+                                             _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
+                                             _ptr(arrs[3]), _stream_ptr()))
     return (rhom,) + tuple(arrs)
 
 
@@ -362,6 +419,23 @@ def make_1d_tree(ncells, imbalanced=False):
     _check(lib.cedr_b200_make_1d_tree(int(ncells), int(bool(imbalanced)),
                                       kids.ctypes.data_as(_ip), cellidx.ctypes.data_as(_lp)))
     return kids, cellidx, 0
+
+
+def partition_probe(ncells, rank, nranks, max_block_leaves=1024, imbalanced=False):
+    """Host-only: which tier-0 blocks of the 1-D mesh tree `rank` of `nranks` owns."""
+    import numpy as np
+    lib = load_library()
+    cap = ncells
+    g, l0, nl = (np.zeros(cap, np.int32) for _ in range(3))
+    a, b, c, d = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    _check(lib.cedr_b200_partition_probe(int(ncells), int(bool(imbalanced)),
+                                         int(max_block_leaves), int(rank), int(nranks), cap,
+                                         C.byref(a), C.byref(b), C.byref(c), C.byref(d),
+                                         g.ctypes.data_as(_ip), l0.ctypes.data_as(_ip),
+                                         nl.ctypes.data_as(_ip)))
+    n = b.value
+    return {"nlclcells": a.value, "nown": n, "nown_max": c.value, "nblocks": d.value,
+            "gidx": g[:n].copy(), "leaf0": l0[:n].copy(), "nl": nl[:n].copy()}
 
 
 def plan_probe(ncells, tree, max_block_leaves=1024):

@@ -129,6 +129,11 @@ struct cedr_b200_cdr {
   int max_block_leaves = 1024;
   Plan plan;
   std::unordered_map<int64_t,int> gci2lci;
+  std::vector<int> leaf_lci;   // DFS leaf index -> local cell index (-1: not owned)
+  std::vector<int> own_blocks; // tier-0 blocks this rank owns (all of them on one rank)
+  int nown_max = 0;            // blocks per rank in the exchange message (padded)
+  std::string partition_error; // why this rank's cells are not a subtree partition
+  int64_t caas_cell0 = 0;
 
   // Tracers.
   bool declaring = true;
@@ -152,7 +157,7 @@ struct cedr_b200_cdr {
   DevBuf<FastRh> d_frh;
   bool fast_enabled = true;   // cedr_b200_set_fast_path
   bool fast_ok = false;       // plan + buffers allow the fast tier-0 kernels
-  bool fused_enabled = true;  // cedr_b200_set_fused
+  bool fused_enabled = false; // cedr_b200_set_fused (opt-in until it beats the multi-launch path)
   bool fused_ok = false;      // plan + device allow the fused persistent kernel
   int fused_depth = 2;        // tracers between UP(k) and DOWN(k)
   int fused_capacity = 0;     // co-resident CTAs of the fused kernel on this device
@@ -168,6 +173,9 @@ struct cedr_b200_cdr {
   cudaStream_t stream = 0;
   cedr_b200_allgather_fn allgather = nullptr;
   void* allgather_ctx = nullptr;
+  DevBuf<double> xsend_own, xrecv_own;   // exchange message / gathered messages
+  double* xsend = nullptr;
+  double* xrecv = nullptr;
   int last_launches = 0;
 
   // Optional per-launch timing (cedr_b200_set_profiling).
@@ -252,11 +260,17 @@ void launch_sweep_any (cedr_b200_cdr& c, int cls, int tier, int mode, const Swee
   }
 }
 
+// Blocks in the device list of a tier: tier 0 holds only this rank's blocks.
+int nblocks_dev (const cedr_b200_cdr& c, int tier) {
+  return tier == 0 ? static_cast<int>(c.own_blocks.size()) :
+    static_cast<int>(c.plan.tiers[tier].blocks.size());
+}
+
 SweepArgs base_args (cedr_b200_cdr& c, int cls, int tier) {
   SweepArgs a;
   std::memset(&a, 0, sizeof(a));
   a.blocks = c.d_blocks[tier].p;
-  a.nblocks = static_cast<int>(c.plan.tiers[tier].blocks.size());
+  a.nblocks = nblocks_dev(c, tier);
   a.lvlptr = c.d_lvlptr.p;
   a.kid0 = c.d_kid0.p;
   a.kid1 = c.d_kid1.p;
@@ -301,7 +315,7 @@ fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
   fast::FastArgs a;
   std::memset(&a, 0, sizeof(a));
   a.blocks = c.d_blocks[0].p;
-  a.nblocks = static_cast<int>(c.plan.tiers[0].blocks.size());
+  a.nblocks = nblocks_dev(c, 0);
   a.dtab = c.d_dtab.p;
   a.ptab = c.d_ptab.p;
   a.wq = c.d_fwq.p;
@@ -329,14 +343,15 @@ fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
 }
 
 template <typename K>
-void launch_fast (cedr_b200_cdr& c, K kernel, const fast::FastArgs& a, size_t smem, int tag) {
+void launch_fast (cedr_b200_cdr& c, K kernel, const fast::FastArgs& a, size_t smem, int tag,
+                  int threads = fast::kThreads) {
   if (a.ntr == 0) return;
   CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(std::max<size_t>(smem, 48*1024))));
   const long long grid = static_cast<long long>(a.nblocks)*((a.ntr + a.group - 1)/a.group);
   cedr_b200_throw_if(grid > 0x7fffffffLL, "grid too large");
   LaunchTimer lt(c, tag, 0);
-  kernel<<<static_cast<unsigned>(grid), fast::kThreads, smem, c.stream>>>(a);
+  kernel<<<static_cast<unsigned>(grid), threads, smem, c.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++c.last_launches;
 }
@@ -354,11 +369,21 @@ void launch_fast_up (cedr_b200_cdr& c, int cls) {
 
 void launch_fast_down (cedr_b200_cdr& c, int cls) {
   const fast::FastArgs a = fast_args(c, cls);
-  const size_t smem = sizeof(double)*(7*a.sbuf + 4*256 + fast::kD9) + 16;
+  if (std::getenv("CEDR_B200_DOWN1")) {   // the unspecialised kernel, for A/B timing
+    const size_t smem = sizeof(double)*(7*a.sbuf + 4*256 + fast::kD9) + 16;
+    if (cls == CLS_ST)
+      launch_fast(c, fast::down_kernel<CLS_ST>, a, smem, CEDR_B200_TAG_DOWN);
+    else
+      launch_fast(c, fast::down_kernel<CLS_CST>, a, smem, CEDR_B200_TAG_DOWN);
+    return;
+  }
+  const size_t smem = fast::down2_smem_bytes(a.sbuf);
   if (cls == CLS_ST)
-    launch_fast(c, fast::down_kernel<CLS_ST>, a, smem, CEDR_B200_TAG_DOWN);
+    launch_fast(c, fast::down2_kernel<CLS_ST>, a, smem, CEDR_B200_TAG_DOWN,
+                fast::kDown2Threads);
   else
-    launch_fast(c, fast::down_kernel<CLS_CST>, a, smem, CEDR_B200_TAG_DOWN);
+    launch_fast(c, fast::down2_kernel<CLS_CST>, a, smem, CEDR_B200_TAG_DOWN,
+                fast::kDown2Threads);
 }
 
 // ---- fused persistent kernel (fused_kernels.cuh)
@@ -451,12 +476,13 @@ void launch_fused (cedr_b200_cdr& c, int cls) {
   ++c.last_launches;
 }
 
-void run_rhom (cedr_b200_cdr& c) {
+// rhom sweep of tiers [k0, k1).
+void run_rhom (cedr_b200_cdr& c, int k0, int k1) {
   const int ntiers = static_cast<int>(c.plan.tiers.size());
-  for (int k = 0; k < ntiers; ++k) {
+  for (int k = k0; k < k1; ++k) {
     RhomArgs a;
     a.blocks = c.d_blocks[k].p;
-    a.nblocks = static_cast<int>(c.plan.tiers[k].blocks.size());
+    a.nblocks = nblocks_dev(c, k);
     a.lvlptr = c.d_lvlptr.p;
     a.kid0 = c.d_kid0.p;
     a.kid1 = c.d_kid1.p;
@@ -474,37 +500,98 @@ void run_rhom (cedr_b200_cdr& c) {
   }
 }
 
-void run_qlt (cedr_b200_cdr& c) {
-  cedr_b200_throw_if(c.nranks > 1, "multi-rank QLT::run is not wired up yet");
+void launch_up (cedr_b200_cdr& c, int cls, int k) {
+  if (k == 0 && c.fast_ok && fast_class(cls, MODE_UP)) launch_fast_up(c, cls);
+  else launch_sweep_any(c, cls, k, MODE_UP, base_args(c, cls, k));
+}
+
+void launch_down (cedr_b200_cdr& c, int cls, int k) {
+  if (k == 0 && c.fast_ok && fast_class(cls, MODE_DOWN)) launch_fast_down(c, cls);
+  else launch_sweep_any(c, cls, k, MODE_DOWN, base_args(c, cls, k));
+}
+
+size_t exchange_count (const cedr_b200_cdr& c) {
+  return static_cast<size_t>(c.nown_max)*(4*c.trcr_prob.size() + 2);
+}
+
+int grid_for (long long n) {
+  return static_cast<int>(std::max<long long>(1, std::min<long long>((n + kThreads - 1)/kThreads,
+                                                                   148*32)));
+}
+
+// This rank's tier-0 block roots -> the exchange message.
+void exchange_pack (cedr_b200_cdr& c, bool with_rhom) {
+  LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 0);
+  pack_kernel<<<grid_for(exchange_count(c)), kThreads, 0, c.stream>>>(
+    c.d_blocks[0].p, nblocks_dev(c, 0), c.nown_max, static_cast<int>(c.trcr_prob.size()),
+    with_rhom ? c.d_rhom_tier[1].p : nullptr, c.d_rec[1].p, c.tier_ld[1], c.xsend);
+  CUDA_CHECK(cudaGetLastError());
+  ++c.last_launches;
+}
+
+// Every rank's message -> the (replicated) tier-1 leaves.
+void exchange_unpack (cedr_b200_cdr& c, bool with_rhom) {
+  LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 1);
+  unpack_kernel<<<grid_for(exchange_count(c)*c.nranks), kThreads, 0, c.stream>>>(
+    c.xrecv, c.nranks, c.nown_max, static_cast<int>(c.trcr_prob.size()),
+    with_rhom ? c.d_rhom_tier[1].p : nullptr, c.d_rec[1].p, c.tier_ld[1]);
+  CUDA_CHECK(cudaGetLastError());
+  ++c.last_launches;
+}
+
+void exchange_allgather (cedr_b200_cdr& c) {
+  cedr_b200_throw_if( ! c.allgather, "nranks > 1 but no all-gather was set "
+                     "(cedr_b200_set_allgather)");
+  const int e = c.allgather(c.allgather_ctx, c.xsend, c.xrecv, exchange_count(c), c.stream);
+  cedr_b200_throw_if(e != 0, "the all-gather callback failed with code " << e);
+}
+
+// QLT::run, cedr_qlt.cpp:618-640. phase < 0: everything (one rank: no exchange);
+// phase 0: up to the exchange message; phase 1: from the gathered messages on.
+void run_qlt (cedr_b200_cdr& c, int phase) {
   const int ntiers = static_cast<int>(c.plan.tiers.size());
   const int top = ntiers - 1;
-  run_rhom(c);
-  for (int cls = 0; cls < CLS_CAAS; ++cls) {
-    if (c.cls_tracers[cls].empty()) continue;
-    if (c.fused_ok && fused_class(cls)) { launch_fused(c, cls); continue; }
-    for (int k = 0; k < top; ++k) {
-      if (k == 0 && c.fast_ok && fast_class(cls, MODE_UP)) launch_fast_up(c, cls);
-      else launch_sweep_any(c, cls, k, MODE_UP, base_args(c, cls, k));
+  const bool multi = c.nranks > 1;
+  if (phase <= 0) {
+    run_rhom(c, 0, multi ? 1 : ntiers);
+    if (multi) {
+      for (int cls = 0; cls < CLS_CAAS; ++cls)
+        if ( ! c.cls_tracers[cls].empty()) launch_up(c, cls, 0);
+      exchange_pack(c, true);
     }
-    launch_sweep_any(c, cls, top, MODE_TOP, base_args(c, cls, top));
-    for (int k = top - 1; k >= 0; --k) {
-      if (k == 0 && c.fast_ok && fast_class(cls, MODE_DOWN)) launch_fast_down(c, cls);
-      else launch_sweep_any(c, cls, k, MODE_DOWN, base_args(c, cls, k));
+  }
+  if (multi && phase < 0) exchange_allgather(c);
+  if (phase != 0) {
+    if (multi) {
+      exchange_unpack(c, true);
+      run_rhom(c, 1, ntiers);
+    }
+    for (int cls = 0; cls < CLS_CAAS; ++cls) {
+      if (c.cls_tracers[cls].empty()) continue;
+      if (c.fused_ok && fused_class(cls)) { launch_fused(c, cls); continue; }
+      for (int k = multi ? 1 : 0; k < top; ++k) launch_up(c, cls, k);
+      launch_sweep_any(c, cls, top, MODE_TOP, base_args(c, cls, top));
+      for (int k = top - 1; k >= 0; --k) launch_down(c, cls, k);
     }
   }
 }
 
-void run_caas (cedr_b200_cdr& c) {
-  cedr_b200_throw_if(c.nranks > 1, "multi-rank CAAS::run is not wired up yet");
+// CAAS::run, cedr_caas.cpp:258-270; phases as for run_qlt.
+void run_caas (cedr_b200_cdr& c, int phase) {
   cedr_b200_throw_if(c.caas_sum_mode != CEDR_B200_CAAS_SUM_TREE,
                      "CAAS sequential-order sums are not implemented yet");
+  const bool multi = c.nranks > 1;
   if (c.fused_ok) { launch_fused(c, CLS_CAAS); return; }
   const int ntiers = static_cast<int>(c.plan.tiers.size());
   const int top = ntiers - 1;
-  for (int k = 0; k < top; ++k) {
-    if (k == 0 && c.fast_ok) launch_fast_up(c, CLS_CAAS);
-    else launch_sweep_any(c, CLS_CAAS, k, MODE_UP, base_args(c, CLS_CAAS, k));
+  if (phase <= 0 && multi) {
+    launch_up(c, CLS_CAAS, 0);
+    exchange_pack(c, false);
   }
+  if (multi && phase < 0) exchange_allgather(c);
+  if (phase == 0) return;
+  if (multi) exchange_unpack(c, false);
+  for (int k = multi ? 1 : 0; k < top; ++k) launch_up(c, CLS_CAAS, k);
   launch_sweep_any(c, CLS_CAAS, top, MODE_TOP, base_args(c, CLS_CAAS, top));
   const int nt = static_cast<int>(c.trcr_prob.size());
   const long long n = static_cast<long long>(c.nlcl)*nt;
@@ -520,13 +607,52 @@ void build_plan (cedr_b200_cdr& c) {
   c.plan.build(c.ncells, static_cast<int>(c.tree_cellidx.size()), c.tree_root,
                c.tree_kids.data(), c.tree_cellidx.data(),
                c.tree_rank.empty() ? nullptr : c.tree_rank.data(), c.max_block_leaves);
+  // Local cell indices: this rank's leaves in DFS order (QLT::init_ordinals,
+  // cedr_qlt.cpp:220-227; the reference numbers a rank's leaf slots the same way).
   c.gci2lci.clear();
+  c.leaf_lci.assign(c.ncells, -1);
   c.nlcl = 0;
   for (int i = 0; i < c.ncells; ++i)
     if (c.plan.leaf_rank[i] == c.rank) {
-      c.gci2lci[c.plan.lci2gci[i]] = i;
+      c.leaf_lci[i] = c.nlcl;
+      c.gci2lci[c.plan.lci2gci[i]] = c.nlcl;
       ++c.nlcl;
     }
+  // Subtree partition: a rank owns whole tier-0 blocks; everything above
+  // tier 0 is replicated on every rank.
+  c.own_blocks.clear();
+  c.partition_error.clear();
+  const std::vector<Block>& blocks = c.plan.tiers[0].blocks;
+  for (size_t b = 0; b < blocks.size(); ++b) {
+    if (c.nranks == 1 || blocks[b].owner == c.rank) {
+      c.own_blocks.push_back(static_cast<int>(b));
+      continue;
+    }
+    if (blocks[b].owner == -1 && c.partition_error.empty())
+      for (int i = blocks[b].leaf0; i < blocks[b].leaf0 + blocks[b].nl; ++i)
+        if (c.plan.leaf_rank[i] == c.rank) {
+          // Reported by end_tracer_declarations: max_block_leaves may still change.
+          std::stringstream ss;
+          ss << "with nranks > 1 the cells of a rank must form whole blocks of the tree "
+            "plan (subtree partition); block " << b << " of " << blocks[b].nl
+             << " leaves mixes ranks. General cell->rank maps are not supported yet.";
+          c.partition_error = ss.str();
+          break;
+        }
+  }
+  if (c.nranks > 1) {
+    c.nown_max = static_cast<int>((blocks.size() + c.nranks - 1)/c.nranks);
+    if (static_cast<int>(c.own_blocks.size()) > c.nown_max && c.partition_error.empty()) {
+      std::stringstream ss;
+      ss << "this rank owns " << c.own_blocks.size() << " blocks, more than "
+        "ceil(#blocks/#ranks) = " << c.nown_max << ": uneven partitions are not supported yet";
+      c.partition_error = ss.str();
+    }
+  }
+}
+
+void run_any (cedr_b200_cdr& c, int phase) {
+  if (c.is_caas) run_caas(c, phase); else run_qlt(c, phase);
 }
 
 void get_buffers_sizes (cedr_b200_cdr& c, size_t& b1, size_t& b2) {
@@ -565,11 +691,16 @@ void finish_setup (cedr_b200_cdr& c) {
   c.tier_ld.assign(ntiers, 0);
   for (int k = 0; k < ntiers; ++k) {
     const Tier& tier = c.plan.tiers[k];
-    std::vector<BlockDev> hb(tier.blocks.size());
+    // Tier 0: only this rank's blocks, their leaves as local cell indices.
+    std::vector<int> list;
+    if (k == 0) list = c.own_blocks;
+    else for (size_t b = 0; b < tier.blocks.size(); ++b) list.push_back(static_cast<int>(b));
+    std::vector<BlockDev> hb(list.size());
     for (size_t b = 0; b < hb.size(); ++b) {
-      const Block& blk = tier.blocks[b];
+      const Block& blk = tier.blocks[list[b]];
       const Shape& sh = c.plan.shapes[blk.shape];
-      hb[b].leaf0 = blk.leaf0;
+      hb[b].gidx = list[b];
+      hb[b].leaf0 = k == 0 ? c.leaf_lci[blk.leaf0] : blk.leaf0;
       hb[b].nl = blk.nl;
       hb[b].ni = sh.ni;
       hb[b].nlev = sh.nlev;
@@ -582,6 +713,7 @@ void finish_setup (cedr_b200_cdr& c) {
       hb[b].npairs = sh.fast ? static_cast<int>(sh.ptab.size()) : 0;
       hb[b].fbase = blk.ibase;
     }
+    if (hb.empty()) hb.resize(1);
     c.d_blocks[k].upload(hb);
     c.tier_ld[k] = k == 0 ? c.ld : round_up(tier.nleaves, 16);
     if (k > 0) {
@@ -602,6 +734,12 @@ void finish_setup (cedr_b200_cdr& c) {
   }
   c.d_qglob.alloc(2*static_cast<size_t>(nt));
   c.d_caas_scal.alloc(2*static_cast<size_t>(nt));
+  if (c.nranks > 1 && ! c.xsend) {
+    c.xsend_own.alloc(exchange_count(c));
+    c.xrecv_own.alloc(exchange_count(c)*c.nranks);
+    c.xsend = c.xsend_own.p;
+    c.xrecv = c.xrecv_own.p;
+  }
   fused_setup(c);
   c.finished = true;
 }
@@ -685,17 +823,29 @@ int cedr_b200_caas_create (cedr_b200_cdr** out, int nlclcells, int sum_mode,
     cedr_b200_throw_if(! out, "null output pointer");
     require_device();
     cedr_b200_throw_if(nlclcells == 0, "CAAS does not support 0 cells on a rank.");
-    cedr_b200_throw_if(nranks > 1, "multi-rank CAAS is not wired up yet");
-    cedr_b200_throw_if(cell0 != 0 || ncells_global != nlclcells,
+    cedr_b200_throw_if(nranks == 1 && (cell0 != 0 || ncells_global != nlclcells),
                        "one rank: cell0 must be 0 and ncells_global == nlclcells");
+    cedr_b200_throw_if(cell0 < 0 || cell0 + nlclcells > ncells_global ||
+                       ncells_global > 0x7fffffffLL, "bad cell range");
     std::unique_ptr<cedr_b200_cdr> c(new cedr_b200_cdr);
     c->is_caas = true;
     c->rank = rank;
     c->nranks = nranks;
     c->caas_sum_mode = sum_mode;
-    c->ncells = nlclcells;
-    fill_1d_tree(*c, nlclcells, false);
+    c->ncells = static_cast<int>(ncells_global);
+    c->caas_cell0 = cell0;
+    // The tree-ordered sums run over a bisection tree of ALL cells; this rank's cells
+    // [cell0, cell0 + nlclcells) must be whole blocks of it. Other ranks' cells only
+    // need to be "not mine" (-2).
+    make_bisection_tree(c->ncells, false, c->tree_kids, c->tree_cellidx);
+    c->tree_root = 0;
+    c->tree_rank.assign(c->tree_cellidx.size(), 0);
+    for (size_t i = 0; i < c->tree_cellidx.size(); ++i) {
+      const int64_t ci = c->tree_cellidx[i];
+      if (ci >= 0) c->tree_rank[i] = (ci >= cell0 && ci < cell0 + nlclcells) ? rank : -2;
+    }
     build_plan(*c);
+    cedr_b200_throw_if(c->nlcl != nlclcells, "internal: owned cell count mismatch");
     *out = c.release();
   });
 }
@@ -749,7 +899,11 @@ int cedr_b200_end_tracer_declarations (cedr_b200_cdr* c) {
       c->cls_tracers[cls].push_back(t);
     }
     c->nrows = row;
-    c->ld = round_up(c->is_caas ? c->nlcl : c->ncells, 16);
+    c->ld = round_up(std::max(1, c->nlcl), 16);
+    cedr_b200_throw_if( ! c->partition_error.empty(), c->partition_error);
+    cedr_b200_throw_if(c->nranks > 1 && c->plan.tiers.size() < 2,
+                       "with nranks > 1 the tree plan needs >= 2 tiers "
+                       "(lower max_block_leaves for tiny trees)");
     c->declaring = false;
   });
 }
@@ -790,7 +944,40 @@ int cedr_b200_run (cedr_b200_cdr* c) {
     cedr_b200_throw_if(! c->finished, "finish_setup must be called before run.");
     c->last_launches = 0;
     c->ntimed = 0;
-    if (c->is_caas) run_caas(*c); else run_qlt(*c);
+    run_any(*c, -1);
+  });
+}
+
+int cedr_b200_run_phase (cedr_b200_cdr* c, int phase) {
+  return guarded([&] {
+    cedr_b200_throw_if( ! c->finished, "finish_setup must be called before run.");
+    cedr_b200_throw_if(phase != 0 && phase != 1, "phase must be 0 or 1");
+    if (phase == 0) { c->last_launches = 0; c->ntimed = 0; }
+    if (c->nranks == 1) { if (phase == 0) run_any(*c, -1); }
+    else run_any(*c, phase);
+  });
+}
+
+int cedr_b200_get_exchange_count (const cedr_b200_cdr* c, size_t* count) {
+  return guarded([&] {
+    cedr_b200_throw_if(c->declaring, "end_tracer_declarations must be called first.");
+    *count = c->nranks > 1 ? exchange_count(*c) : 0;
+  });
+}
+
+int cedr_b200_set_exchange_buffers (cedr_b200_cdr* c, double* send, double* recv) {
+  return guarded([&] {
+    cedr_b200_throw_if(c->finished, "set_exchange_buffers must precede finish_setup");
+    c->xsend = send;
+    c->xrecv = recv;
+  });
+}
+
+int cedr_b200_get_exchange_buffers (const cedr_b200_cdr* c, double** send, double** recv) {
+  return guarded([&] {
+    cedr_b200_throw_if( ! c->finished, "finish_setup must be called first.");
+    *send = c->xsend;
+    *recv = c->xrecv;
   });
 }
 
@@ -1041,17 +1228,52 @@ int cedr_b200_plan_probe (int ncells, int nnodes, int root, const int* kids,
   });
 }
 
+int cedr_b200_partition_probe (int ncells, int imbalanced, int max_block_leaves, int rank,
+                               int nranks, int cap, int* nlclcells, int* nown, int* nown_max,
+                               int* nblocks_global, int* gidx_host, int* leaf0_host,
+                               int* nl_host) {
+  return guarded([&] {
+    cedr_b200_cdr c;
+    c.rank = rank;
+    c.nranks = nranks;
+    c.ncells = ncells;
+    c.max_block_leaves = max_block_leaves;
+    cedr_b200_throw_if(nranks > ncells, "#GIDs < #ranks is not supported.");
+    fill_1d_tree(c, ncells, imbalanced != 0);
+    build_plan(c);
+    cedr_b200_throw_if( ! c.partition_error.empty(), c.partition_error);
+    if (nlclcells) *nlclcells = c.nlcl;
+    if (nown) *nown = static_cast<int>(c.own_blocks.size());
+    if (nown_max) *nown_max = c.nown_max;
+    if (nblocks_global) *nblocks_global = static_cast<int>(c.plan.tiers[0].blocks.size());
+    for (size_t j = 0; j < c.own_blocks.size() && static_cast<int>(j) < cap; ++j) {
+      const Block& blk = c.plan.tiers[0].blocks[c.own_blocks[j]];
+      if (gidx_host) gidx_host[j] = c.own_blocks[j];
+      if (leaf0_host) leaf0_host[j] = blk.leaf0;
+      if (nl_host) nl_host[j] = blk.nl;
+    }
+  });
+}
+
 int cedr_b200_fill_headline (int ncells, int nt, int64_t lda, int config_id,
                              double* rhom, double* qm_min, double* qm, double* qm_max,
                              double* qm_prev, void* stream) {
+  return cedr_b200_fill_headline_range(ncells, 0, ncells, nt, lda, config_id, rhom, qm_min,
+                                       qm, qm_max, qm_prev, stream);
+}
+
+int cedr_b200_fill_headline_range (int ncells, int cell0, int nlcl, int nt, int64_t lda,
+                                   int config_id, double* rhom, double* qm_min, double* qm,
+                                   double* qm_max, double* qm_prev, void* stream) {
   return guarded([&] {
     require_device();
-    const long long n = static_cast<long long>(ncells)*nt;
+    cedr_b200_throw_if(cell0 < 0 || nlcl < 0 || cell0 + nlcl > ncells, "bad cell range");
+    const long long n = static_cast<long long>(nlcl)*nt;
     const int grid = static_cast<int>(std::min<long long>((n + kThreads - 1)/kThreads,
                                                           148*32));
     fill_headline_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       ncells, nt, lda, 0xCED20000ull + static_cast<unsigned long long>(config_id),
-      rhom, qm_min, qm, qm_max, qm_prev);
+      rhom, qm_min, qm, qm_max, qm_prev, cell0, nlcl);
     CUDA_CHECK(cudaGetLastError());
   });
 }

@@ -240,7 +240,7 @@ up_kernel (const FastArgs a) {
     __syncthreads();
     if (tid == 0) {
       // Depths 1 and 0, then the record for the next tier.
-      double* rec = a.rec_out + static_cast<long long>(t)*4*a.rec_ld + b;
+      double* rec = a.rec_out + static_cast<long long>(t)*4*a.rec_ld + B.gidx;
 #pragma unroll
       for (int f = 0; f < 4; ++f) {
         if ((f == 0 || f == 2) && ! bounds) continue;
@@ -371,7 +371,7 @@ down_kernel (const FastArgs a) {
       if (d > 5) __syncthreads(); else __syncwarp();
     }
     // ---- node problems of depths 0..6. Depths 0..5 fit in warp 0.
-    if (tid == 0) un[3*256] = a.sol_in[static_cast<long long>(t)*a.sol_in_ld + b];
+    if (tid == 0) un[3*256] = a.sol_in[static_cast<long long>(t)*a.sol_in_ld + B.gidx];
     __syncwarp();
     for (int d = 0; d <= 6; ++d) {
       if (d == 6) __syncthreads();
@@ -426,6 +426,279 @@ down_kernel (const FastArgs a) {
     }
     __syncthreads();
     if (tid == 0 && i + 2 < gn) issue(i + 2);
+  }
+}
+
+// ---------------------------------------------------------------- DOWN, specialised
+//
+// Same work as down_kernel, organised so that no warp ever waits for the serial part of
+// the block. The block's node problems split into
+//   - the block top, depths 0..6 (127 nodes): a chain of 7 dependent levels, at most 64
+//     problems wide -- one TOP warp walks it;
+//   - the micro-subtrees, depths 7..9 (~80% of the nodes): 128 independent columns, one
+//     per thread of the four LEAF warps, dense and barrier-free.
+// The CTA walks its group of tracers as a two-stage pipeline: while the leaf warps sum
+// tracer i's micro-subtrees (A(i)) and then solve tracer i-1's (C(i-1)), the top warp
+// solves the block top of tracer i (T(i)). Stages hand over through named barriers;
+// leaf rows are TMA-staged two tracers deep.
+constexpr int kLeafThreads = 128;
+constexpr int kDown2Threads = 160;
+
+// Named barriers with immediate ids (a register id makes ptxas reserve all 16).
+template <int ID, int COUNT> __device__ __forceinline__ void bar_sync_i () {
+  asm volatile("bar.sync %0, %1;" :: "n"(ID), "n"(COUNT) : "memory");
+}
+template <int ID, int COUNT> __device__ __forceinline__ void bar_arrive_i () {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" :: "n"(ID), "n"(COUNT) : "memory");
+}
+// id = BASE + parity
+template <int BASE, int COUNT> __device__ __forceinline__ void bar_sync (const int parity) {
+  if (parity) bar_sync_i<BASE + 1, COUNT>(); else bar_sync_i<BASE, COUNT>();
+}
+template <int BASE, int COUNT> __device__ __forceinline__ void bar_arrive (const int parity) {
+  if (parity) bar_arrive_i<BASE + 1, COUNT>(); else bar_arrive_i<BASE, COUNT>();
+}
+
+// Shared memory of down2_kernel, in doubles: stage[2][3][sbuf], un[2][3][256],
+// xs[2][256], then topc[128] (NodeWQ) and 2 mbarriers.
+inline size_t down2_smem_bytes (const int sbuf) {
+  return sizeof(double)*(6*static_cast<size_t>(sbuf) + 2*3*256 + 2*256) +
+    128*sizeof(dev::NodeWQ) + 16;
+}
+
+template <int CLS>
+__global__ void __launch_bounds__(kDown2Threads, 3)
+down2_kernel (const FastArgs a) {
+  static_assert(CLS == CLS_ST || CLS == CLS_CST, "fast down-sweep: st / cst only");
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int sbuf = a.sbuf;
+  double* const stage = reinterpret_cast<double*>(smraw);            // [2][3][sbuf]
+  double* const un = stage + 6*sbuf;                                 // [2][3][256]
+  double* const xs = un + 2*3*256;                                   // [2][256]
+  dev::NodeWQ* const topc = reinterpret_cast<dev::NodeWQ*>(xs + 2*256);   // [128]
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(topc + 128);    // [2]
+  constexpr int BAR_A = 1, BAR_T = 3, BAR_LEAF = 5;   // + parity for A and T
+
+  const int b = blockIdx.x % a.nblocks, grp = blockIdx.x / a.nblocks;
+  const BlockDev B = a.blocks[b];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int src0 = B.leaf0 & ~1, shift = B.leaf0 - src0;
+  const unsigned bytes = 8u*static_cast<unsigned>(((B.leaf0 + B.nl + 1) & ~1) - src0);
+  const int g0 = grp*a.group;
+  const int gn = min(a.group, a.ntr - g0);
+  const unsigned short* const dtab = a.dtab + B.ftab_off;
+  const unsigned short* const ptab = a.ptab + B.fpair_off;
+  const dev::NodeWQ* const wq = a.wq + B.fbase;
+  const dev::NodeRh* const rh = a.rh + B.fbase;
+  const bool prefer = a.prefer_mass_con != 0;
+
+  auto solve = [&] (const dev::NodeWQ& c, const int cpos, const double* nd, const double bm,
+                    const double* k0, const double* k1, double& x0, double& x1) {
+    if (prefer)
+      dev::solve_bounded_lean<true>(c, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
+                                    k0[2], k1[0], k1[1], k1[2], x0, x1);
+    else
+      dev::solve_bounded_lean<false>(c, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
+                                     k0[2], k1[0], k1[1], k1[2], x0, x1);
+  };
+
+  if (tid < kHeapNodes/4) topc[tid] = wq[tid];
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == 4) {
+    // ------------------------------------------------------------- TOP warp
+    for (int i = 0; i < gn; ++i) {
+      const int t = a.tracers[g0 + i];
+      double* const u = un + (i & 1)*3*256;
+      double* const x = xs + (i & 1)*256;
+      // The block root's mass, from the tier above (issued before the wait).
+      double xroot = 0;
+      if (lane == 0) xroot = __ldcg(a.sol_in + static_cast<long long>(t)*a.sol_in_ld + B.gidx);
+      bar_sync<BAR_A, kDown2Threads>(i & 1);     // A(i): depth-7 sums are in u
+      // Sums of depths 6..0 (heap node h has kids 2h+1, 2h+2).
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int h = 63 + lane + 32*q;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) u[f*256 + h] = u[f*256 + 2*h + 1] + u[f*256 + 2*h + 2];
+      }
+      __syncwarp();
+      for (int dd = 5; dd >= 0; --dd) {
+        if (lane < (1 << dd)) {
+          const int h = (1 << dd) - 1 + lane;
+#pragma unroll
+          for (int f = 0; f < 3; ++f) u[f*256 + h] = u[f*256 + 2*h + 1] + u[f*256 + 2*h + 2];
+        }
+        __syncwarp();
+      }
+      if (lane == 0) x[0] = xroot;
+      __syncwarp();
+      // Node problems of depths 0..6.
+      for (int dd = 0; dd <= 6; ++dd) {
+        for (int p = lane; p < (1 << dd); p += 32) {
+          const int h = (1 << dd) - 1 + p;
+          const double nd[3] = {u[h], u[256 + h], u[512 + h]};
+          const double k0[3] = {u[2*h + 1], u[256 + 2*h + 1], u[512 + 2*h + 1]};
+          const double k1[3] = {u[2*h + 2], u[256 + 2*h + 2], u[512 + 2*h + 2]};
+          double x0, x1;
+          solve(topc[h], h, nd, x[h], k0, k1, x0, x1);
+          x[2*h + 1] = x0;
+          x[2*h + 2] = x1;
+        }
+        __syncwarp();
+      }
+      bar_arrive<BAR_T, kDown2Threads>(i & 1);   // T(i): x[127..254] are solved
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------- LEAF warps
+  const ushort4 e = reinterpret_cast<const ushort4*>(dtab)[tid];
+  const int off[4] = {(e.x & 0x7fff) + shift, (e.y & 0x7fff) + shift,
+                      (e.z & 0x7fff) + shift, (e.w & 0x7fff) + shift};
+  const bool pr[4] = {(e.x >> 15) != 0, (e.y >> 15) != 0, (e.z >> 15) != 0,
+                      (e.w >> 15) != 0};
+  // This warp's pairs are ptab[ps .. pe): depth-9 positions in [128 warp, 128 warp + 128).
+  int ps = 0, pe = 0;
+  for (int j = lane; j < B.npairs; j += 32) {
+    const int p = ptab[j];
+    ps += p < 128*warp;
+    pe += p < 128*warp + 128;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    pe += __shfl_xor_sync(0xffffffffu, pe, o);
+  }
+  // Leaf offset | depth-9 position << 16 of this lane's (up to two) pairs.
+  unsigned pair_slot[2] = {0xffffffffu, 0xffffffffu};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int j = ps + lane + 32*q;
+    if (j < pe) {
+      const unsigned p = ptab[j];
+      pair_slot[q] = ((dtab[p] & 0x7fffu) + shift) | (p << 16);
+    }
+  }
+  const dev::NodeWQ c7 = wq[127 + tid], c8a = wq[255 + 2*tid], c8b = wq[256 + 2*tid];
+
+  auto issue = [&] (const int i) {
+    const int t = a.tracers[g0 + i];
+    const double* src = a.in + static_cast<long long>(a.trcr_row[t])*a.in_ld + src0;
+    double* dst = stage + (i & 1)*3*sbuf;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&mbar[i & 1], 3*bytes);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) tma_load(dst + f*sbuf, src + f*a.in_ld, bytes, &mbar[i & 1]);
+  };
+  if (tid == 0) {
+    issue(0);
+    if (gn > 1) issue(1);
+  }
+
+  for (int i = 0; i <= gn; ++i) {
+    if (i < gn) {
+      // ---- A(i): depth-7 sums of tracer i into un[i & 1].
+      mbar_wait(&mbar[i & 1], (i >> 1) & 1);
+      const double* const s = stage + (i & 1)*3*sbuf;
+      double* const u = un + (i & 1)*3*256;
+      double n7[3] = {0, 0, 0};
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        double n8[3];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+          const int ka = 2*hf, kb = 2*hf + 1;
+          const double a0 = s[f*sbuf + off[ka]], a1 = s[f*sbuf + off[ka] + 1];
+          const double b0 = s[f*sbuf + off[kb]], b1 = s[f*sbuf + off[kb] + 1];
+          n8[f] = (pr[ka] ? a0 + a1 : a0) + (pr[kb] ? b0 + b1 : b0);
+        }
+#pragma unroll
+        for (int f = 0; f < 3; ++f) n7[f] = hf ? n7[f] + n8[f] : n8[f];
+      }
+#pragma unroll
+      for (int f = 0; f < 3; ++f) u[f*256 + 127 + tid] = n7[f];
+      bar_arrive<BAR_A, kDown2Threads>(i & 1);
+    }
+    if (i >= 1) {
+      // ---- C(i-1): the micro-subtrees of tracer i-1, from the top warp's x.
+      const int k = i - 1;
+      const int t = a.tracers[g0 + k];
+      double* const s = stage + (k & 1)*3*sbuf;
+      double* const xout = s + sbuf;                 // solved leaves replace the Qm row
+      double* const d9x = un + (k & 1)*3*256;        // the sums are dead once T(k) is done
+      const double* const x = xs + (k & 1)*256;
+      auto node9 = [&] (const int q, double* n9) {
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+          const double v0 = s[f*sbuf + off[q]], v1 = s[f*sbuf + off[q] + 1];
+          n9[f] = pr[q] ? v0 + v1 : v0;
+        }
+      };
+      dev::NodeWQ cp[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        if (pair_slot[q] != 0xffffffffu) cp[q] = wq[kHeapNodes + ps + lane + 32*q];
+      double n9[4][3], n8[2][3], n7[3];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) node9(q, n9[q]);
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        n8[0][f] = n9[0][f] + n9[1][f];
+        n8[1][f] = n9[2][f] + n9[3][f];
+        n7[f] = n8[0][f] + n8[1][f];
+      }
+      bar_sync<BAR_T, kDown2Threads>(k & 1);     // T(k) done
+      double x8[2];
+      solve(c7, 127 + tid, n7, x[127 + tid], n8[0], n8[1], x8[0], x8[1]);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        double x9[2];
+        solve(hf ? c8b : c8a, 255 + 2*tid + hf, n8[hf], x8[hf], n9[2*hf], n9[2*hf + 1],
+              x9[0], x9[1]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int q = 2*hf + j;
+          if (pr[q]) d9x[4*tid + q] = x9[j];
+          else xout[off[q]] = x9[j];
+        }
+      }
+      __syncwarp();
+      auto solve_pair = [&] (const dev::NodeWQ& c, const int j, const int o, const int p) {
+        double k0[3], k1[3], nd[3];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+          k0[f] = s[f*sbuf + o];
+          k1[f] = s[f*sbuf + o + 1];
+          nd[f] = k0[f] + k1[f];
+        }
+        double x0, x1;
+        solve(c, kHeapNodes + j, nd, d9x[p], k0, k1, x0, x1);
+        xout[o] = x0;
+        xout[o + 1] = x1;
+      };
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        if (pair_slot[q] != 0xffffffffu)
+          solve_pair(cp[q], ps + lane + 32*q, pair_slot[q] & 0xffff, pair_slot[q] >> 16);
+      for (int j = ps + lane + 64; j < pe; j += 32) {   // blocks with > 64 pairs per warp
+        const int p = ptab[j];
+        solve_pair(wq[kHeapNodes + j], j, (dtab[p] & 0x7fff) + shift, p);
+      }
+      bar_sync_i<BAR_LEAF, kLeafThreads>();
+      {
+        double* const o = a.out + static_cast<long long>(t)*a.out_ld + B.leaf0;
+        for (int q = tid; q < B.nl; q += kLeafThreads) o[q] = xout[shift + q];
+      }
+      bar_sync_i<BAR_LEAF, kLeafThreads>();
+      if (tid == 0 && k + 2 < gn) issue(k + 2);
+    }
   }
 }
 

@@ -273,7 +273,7 @@ run_kernel (const Args a) {
       __syncthreads();   // bufU consumed by everyone; warp roots visible
       if (tid == 0) {
         // Depths 1 and 0, then the record for tier 1.
-        double* rec = a.rec + static_cast<long long>(t)*4*a.rec_ld + b;
+        double* rec = a.rec + static_cast<long long>(t)*4*a.rec_ld + B.gidx;
 #pragma unroll
         for (int f = 0; f < nrowsU; ++f)
           rec[f*a.rec_ld] = (sm.wroot[f] + sm.wroot[4 + f]) + (sm.wroot[8 + f] + sm.wroot[12 + f]);
@@ -380,7 +380,7 @@ run_kernel (const Args a) {
       // The block root's mass comes from tier 1.
       if (tid == 0) {
         wait_flag(i);
-        un[3*256] = __ldcg(a.sol + static_cast<long long>(t)*a.sol_ld + b);
+        un[3*256] = __ldcg(a.sol + static_cast<long long>(t)*a.sol_ld + B.gidx);
       }
       __syncwarp();
       // Node problems of depths 0..6; depths 0..5 fit in warp 0.

@@ -26,6 +26,10 @@ struct BlockDev {
   int lvlptr_off, kid_off, ibase;
   // Fast-path tables (fast_kernels.cuh); ftab_off < 0 if the shape is not fast.
   int ftab_off, fpair_off, fpos_off, npairs, fbase;
+  // Index of this block among ALL blocks of its tier (= its leaf number in the next
+  // tier). Equals its position in the device block list except in tier 0 of a
+  // multi-rank run, where the list holds only the blocks this rank owns.
+  int gidx;
 };
 
 // The same node constants, split and in the fast path's node order.
@@ -167,7 +171,7 @@ sweep_block (const SweepArgs& a, const int b, const int t, double* const sm) {
 
   if (MODE == MODE_UP) {
     if (tid == 0) {
-      double* r = a.rec_out + (long long) t*4*a.rec_ld + b;
+      double* r = a.rec_out + (long long) t*4*a.rec_ld + B.gidx;
       if (need_bounds) { r[0] = f0[root]; r[2*a.rec_ld] = f2[root]; }
       r[a.rec_ld] = f1[root];
       if (need_prev) r[3*a.rec_ld] = f3[root];
@@ -207,7 +211,7 @@ sweep_block (const SweepArgs& a, const int b, const int t, double* const sm) {
     if (tid == 0 && ! has_prev) f3[root] = f1[root];
   } else {
     if (consistent_only) { qmin = a.qglob[2*t]; qmax = a.qglob[2*t+1]; }
-    if (tid == 0) f3[root] = a.sol_in[(long long) t*a.sol_in_ld + b];
+    if (tid == 0) f3[root] = a.sol_in[(long long) t*a.sol_in_ld + B.gidx];
   }
   __syncthreads();
 
@@ -303,7 +307,43 @@ rhom_kernel (const RhomArgs a) {
     }
     __syncthreads();
   }
-  if (tid == 0 && a.root_out) a.root_out[blockIdx.x] = sm[B.ni ? nn - 1 : 0];
+  if (tid == 0 && a.root_out) a.root_out[B.gidx] = sm[B.ni ? nn - 1 : 0];
+}
+
+// Multi-rank exchange (replaces the per-level messages of cedr_qlt.cpp:327-337, 432-439
+// and CAAS's MPI_Allreduce, cedr_caas.cpp:203-209): a rank's message is one entry per
+// owned tier-0 block, [global block index, rhom of the block root, the 4 nt words of its
+// record], padded with index -1 to the same length on every rank. After the all-gather
+// every rank scatters all entries into its (replicated) tier-1 leaf arrays.
+__global__ void __launch_bounds__(256)
+pack_kernel (const BlockDev* blocks, const int nown, const int nown_max, const int nt,
+             const double* rhom1, const double* rec, const long long rec_ld, double* send) {
+  const long long stride = 4LL*nt + 2, n = stride*nown_max;
+  for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
+       k += (long long) gridDim.x*blockDim.x) {
+    const int j = (int) (k / stride);
+    const long long w = k % stride;
+    double v = w == 0 ? -1.0 : 0.0;
+    if (j < nown) {
+      const int g = blocks[j].gidx;
+      v = w == 0 ? (double) g : w == 1 ? (rhom1 ? rhom1[g] : 0.0) : rec[(w - 2)*rec_ld + g];
+    }
+    send[k] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_kernel (const double* recv, const int nranks, const int nown_max, const int nt,
+               double* rhom1, double* rec, const long long rec_ld) {
+  const long long stride = 4LL*nt + 2, n = stride*nown_max*nranks;
+  for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
+       k += (long long) gridDim.x*blockDim.x) {
+    const long long e = k / stride, w = k % stride;
+    const int g = (int) recv[e*stride];
+    if (g < 0 || w == 0) continue;
+    if (w == 1) { if (rhom1) rhom1[g] = recv[k]; }
+    else rec[(w - 2)*rec_ld + g] = recv[k];
+  }
 }
 
 // CAAS::finish_locally, cedr_caas.cpp:211-253, per-cell part; also writes the
@@ -386,19 +426,22 @@ __device__ __forceinline__ double splitmix_u (const unsigned long long seed,
 __global__ void __launch_bounds__(256)
 fill_headline_kernel (const int ncells, const int nt, const long long lda,
                       const unsigned long long seed, double* rhom, double* qm_min,
-                      double* qm, double* qm_max, double* qm_prev) {
-  const long long n = (long long) ncells*nt;
-  for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
-       k += (long long) gridDim.x*blockDim.x) {
-    const int t = (int) (k / ncells), i = (int) (k % ncells);
+                      double* qm, double* qm_max, double* qm_prev, const int cell0,
+                      const int nlcl) {
+  // Cells [cell0, cell0 + nlcl) of the ncells-cell workload.
+  const long long n = (long long) nlcl*nt;
+  for (long long kk = blockIdx.x*(long long) blockDim.x + threadIdx.x; kk < n;
+       kk += (long long) gridDim.x*blockDim.x) {
+    const int t = (int) (kk / nlcl), il = (int) (kk % nlcl), i = cell0 + il;
+    const long long k = (long long) t*ncells + i;
     const double rh = 0.5*(1 + splitmix_u(seed, i));
-    if (t == 0) rhom[i] = rh;
+    if (t == 0) rhom[il] = rh;
     const unsigned long long p = (unsigned long long) ncells + 4ull*k;
     const double q_min = 0.1*splitmix_u(seed, p);
     const double q_max = q_min + splitmix_u(seed, p + 1);
     const double q = q_min + (q_max - q_min)*(1.4*splitmix_u(seed, p + 2) - 0.2);
     const double q_prev = q_min + (q_max - q_min)*splitmix_u(seed, p + 3);
-    const long long s = (long long) t*lda + i;
+    const long long s = (long long) t*lda + il;
     qm_min[s] = q_min*rh;
     qm_max[s] = q_max*rh;
     qm[s] = q*rh;

@@ -16,7 +16,12 @@ import compose_b200 as cb
 
 class HostStepPipeline:
     def __init__(self, ncells, nt, problem_type=7, chunk_nt=640, nslots=3,
-                 reconstructors=("qlt", "caas")):
+                 reconstructors=("qlt", "caas"), rank=0, nranks=1):
+        """With nranks > 1 (one process per GPU, torch.distributed initialised) this rank
+        holds cells [rank*ncells/nranks, (rank+1)*ncells/nranks) of every tracer and each
+        chunk's run() all-gathers the block roots (subtree partition)."""
+        ncells_global = ncells
+        ncells = ncells//nranks
         self.ncells, self.nt = ncells, nt
         self.chunk_nt = min(chunk_nt, nt)
         self.nchunks = (nt + self.chunk_nt - 1)//self.chunk_nt
@@ -32,10 +37,16 @@ class HostStepPipeline:
                                            device="cuda") for k in self.kinds}
                 s["cdr"] = {}
                 for k in self.kinds:
-                    c = cb.QLT(ncells) if k == "qlt" else cb.CAAS(ncells)
+                    if k == "qlt":
+                        c = cb.QLT(ncells_global, rank=rank, nranks=nranks)
+                    else:
+                        c = cb.CAAS(ncells, cell0=rank*ncells, ncells_global=ncells_global,
+                                    rank=rank, nranks=nranks)
                     for _t in range(self.chunk_nt):
                         c.declare_tracer(problem_type)
                     c.end_tracer_declarations()
+                    if nranks > 1:
+                        c.enable_distributed(nranks)
                     c.finish_setup()   # binds the slot's stream
                     s["cdr"][k] = c
             self.slots.append(s)

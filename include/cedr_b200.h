@@ -169,6 +169,34 @@ typedef int (*cedr_b200_allgather_fn)(void* ctx, const double* send, double* rec
                                       size_t count, void* cuda_stream);
 int cedr_b200_set_allgather(cedr_b200_cdr* cdr, cedr_b200_allgather_fn fn, void* ctx);
 
+/* Multi-rank partition: rank r owns the cells the tree assigns to it
+ * (tree::Node::rank, cedr_tree_caller.hpp:14); they must form whole tier-0 blocks of the
+ * plan (a subtree partition, e.g. the contiguous map of cedr_tree.cpp:368-369 on a
+ * bisection tree). Each rank up-sweeps its own blocks, the block roots (record + rhom)
+ * are all-gathered -- `count` doubles per rank, the same on every rank -- and every rank
+ * then sweeps the replicated tiers above in the fixed tree order, so results are
+ * bit-identical to a one-rank run (the reference gets the same property from
+ * cedr_bfb_tree_allreduce.cpp:115-124). get_exchange_count is valid after
+ * end_tracer_declarations. set_exchange_buffers (before finish_setup) hands in caller
+ * device buffers of `count` and `nranks*count` doubles, e.g. registered NCCL or
+ * torch tensors; otherwise they are allocated internally. */
+int cedr_b200_get_exchange_count(const cedr_b200_cdr* cdr, size_t* count);
+int cedr_b200_set_exchange_buffers(cedr_b200_cdr* cdr, double* send, double* recv);
+int cedr_b200_get_exchange_buffers(const cedr_b200_cdr* cdr, double** send, double** recv);
+/* run() split at the exchange, for callers that drive the collective themselves and for
+ * emulating P ranks on one device: phase 0 enqueues everything up to the packed message
+ * in `send`; the caller fills `recv` with every rank's message (rank-major); phase 1
+ * enqueues the rest. On one rank phase 0 is the whole run() and phase 1 does nothing. */
+int cedr_b200_run_phase(cedr_b200_cdr* cdr, int phase);
+/* Host-only view of the partition of make_tree_over_1d_mesh(ncells, imbalanced) with the
+ * contiguous cell->rank map, for `rank` of `nranks`: number of owned cells and blocks,
+ * the padded block count of the exchange, and for each owned block (up to `cap`) its
+ * global block index, first leaf (global DFS index) and leaf count. */
+int cedr_b200_partition_probe(int ncells, int imbalanced, int max_block_leaves, int rank,
+                              int nranks, int cap, int* nlclcells, int* nown, int* nown_max,
+                              int* nblocks_global, int* gidx_host, int* leaf0_host,
+                              int* nl_host);
+
 /* ---- introspection for tests / benches --------------------------------- */
 
 /* Number of kernels launched by the last run() on this CDR. */
@@ -234,6 +262,11 @@ int cedr_b200_make_1d_tree(int ncells, int imbalanced, int* kids_host,
 int cedr_b200_fill_headline(int ncells, int nt, int64_t lda, int config_id,
                             double* rhom, double* qm_min, double* qm, double* qm_max,
                             double* qm_prev, void* cuda_stream);
+/* The same workload restricted to cells [cell0, cell0 + nlclcells) (one rank's share):
+ * rhom[nlclcells] and [nt][lda] arrays indexed by the local cell. */
+int cedr_b200_fill_headline_range(int ncells, int cell0, int nlclcells, int nt, int64_t lda,
+                                  int config_id, double* rhom, double* qm_min, double* qm,
+                                  double* qm_max, double* qm_prev, void* cuda_stream);
 
 #ifdef __cplusplus
 }

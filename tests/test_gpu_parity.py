@@ -267,3 +267,110 @@ def test_fast_and_generic_paths_agree_on_headline_inputs(oracle):
             outs.append(c.get_Qm().cpu().numpy())
     assert np.array_equal(outs[0], outs[2])
     assert np.array_equal(outs[1], outs[3])
+
+
+# ---------------------------------------------------------------- multi-rank
+#
+# P ranks emulated on one device: P CDR objects (rank r of P), each fed only its own
+# cells; run() is split at the exchange (run_phase) and the test plays the all-gather.
+# The single-rank oracle on the whole problem is the reference (SURVEY 8c "multi-rank
+# reference"): the partition must not change a single bit.
+
+def _emulate_exchange(cdrs):
+    import torch
+    for c in cdrs:
+        c.run_phase(0)
+    torch.cuda.synchronize()
+    msg = torch.cat([c._xsend for c in cdrs])
+    for c in cdrs:
+        assert c._xrecv.numel() == msg.numel()
+        c._xrecv.copy_(msg)
+    for c in cdrs:
+        c.run_phase(1)
+    for c in cdrs:
+        c.synchronize()
+
+
+def run_qlt_multirank(ncells, P, pts, rhom, qm_min, qm, qm_max, qm_prev, mbl=None,
+                      prefer=False):
+    import torch
+    import compose_b200 as cb
+    cdrs, gcis = [], []
+    for r in range(P):
+        q = cb.QLT(ncells, rank=r, nranks=P,
+                   prefer_numerical_mass_conservation_to_numerical_bounds=prefer)
+        if mbl:
+            q.set_max_block_leaves(mbl)
+        for p in pts:
+            q.declare_tracer(int(p))
+        q.end_tracer_declarations()
+        q.use_tensor_exchange_buffers(P)
+        q.finish_setup()
+        g = q.get_owned_glblcells()
+        assert len(g) == q.nlclcells()
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a)[..., g])).cuda()
+        q.set_rhom(dev(rhom))
+        q.set_Qm(dev(qm), dev(qm_min), dev(qm_max), dev(qm_prev))
+        cdrs.append(q)
+        gcis.append(g)
+    assert sorted(np.concatenate(gcis).tolist()) == list(range(ncells))
+    _emulate_exchange(cdrs)
+    res = np.empty((len(pts), ncells))
+    for q, g in zip(cdrs, gcis):
+        res[:, g] = q.get_Qm().cpu().numpy()
+    return res
+
+
+@pytest.mark.parametrize("ncells,P,mbl", [(5400, 2, None), (5400, 8, None), (8*768, 4, None),
+                                          (64, 2, 4), (64, 8, 8), (1024, 4, 32),
+                                          (86400, 8, None)])
+def test_qlt_subtree_partition_bitwise(oracle, ncells, P, mbl):
+    ts, v = R.generate(ncells, seed=7*ncells + P)
+    if ncells > 10000:
+        ts = ts[:12]
+    pts = [t.problem_type for t in ts]
+    n = len(pts)
+    tree = oracle.bisection_tree(ncells)
+    ref = oracle.qlt(tree, pts, v.rhom, v.Qm_min[:n], v.Qm[:n], v.Qm_max[:n], v.Qm_prev[:n])
+    got = run_qlt_multirank(ncells, P, pts, v.rhom, v.Qm_min[:n], v.Qm[:n], v.Qm_max[:n],
+                            v.Qm_prev[:n], mbl=mbl)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("ncells,P,mbl", [(5400, 2, None), (5400, 8, None), (64, 4, 4),
+                                          (86400, 8, None)])
+def test_caas_subtree_partition_bitwise(oracle, ncells, P, mbl):
+    import torch
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    nt = 10
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, 11)
+    pts = [7]*nt
+    ref = oracle.caas(ncells, pts, lo, q, hi, prev, tree=oracle.bisection_tree(ncells))
+    nl = ncells//P
+    cdrs = []
+    for r in range(P):
+        c = cb.CAAS(nl, cell0=r*nl, ncells_global=ncells, rank=r, nranks=P)
+        if mbl:
+            c.set_max_block_leaves(mbl)
+        for p in pts:
+            c.declare_tracer(p)
+        c.end_tracer_declarations()
+        c.use_tensor_exchange_buffers(P)
+        c.finish_setup()
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a[..., r*nl:(r + 1)*nl])).cuda()
+        c.set_rhom(dev(rhom))
+        c.set_Qm(dev(q), dev(lo), dev(hi), dev(prev))
+        cdrs.append(c)
+    _emulate_exchange(cdrs)
+    got = np.concatenate([c.get_Qm().cpu().numpy() for c in cdrs], axis=1)
+    assert np.array_equal(got, ref)
+
+
+def test_partition_must_be_whole_blocks():
+    import compose_b200 as cb
+    # 3 ranks over 5400 cells: 1800-cell ranges cut the 675-leaf blocks.
+    q = cb.QLT(5400, rank=1, nranks=3)
+    q.declare_tracer(7)
+    with pytest.raises(cb.CedrError, match="whole blocks"):
+        q.end_tracer_declarations()
