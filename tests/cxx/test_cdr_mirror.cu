@@ -1,0 +1,216 @@
+// C++ caller-side test of include/cedr_b200.hpp, written the way the reference's own
+// callers use cedr::CDR:
+//   (A) device path: the concrete DeviceOp copied by value into kernels that call
+//       set_rhom / set_Qm / get_Qm per (cell, tracer), as TestRandomized::run does with
+//       Kokkos lambdas (cedr_test_randomized_inl.hpp:12-65);
+//   (B) host path: plain host loops over op.set_Qm / cdr.run() / op.get_Qm, as the 1-D
+//       transport test does (cedr_test_1d_transport.cpp:170-189), on a CDR built with
+//       Memory::managed;
+// and checks the results bit-for-bit against the CPU oracle (oracle/cedr_oracle.h --
+// test infrastructure, linked only into this test), plus the reference's error behaviour.
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+#include <vector>
+
+#include "cedr_b200.hpp"
+#include "cedr_oracle.h"
+
+using namespace cedr;
+
+template <typename Op>
+__global__ void set_all (const Op op, const int n, const int nt, const double* rhom,
+                         const double* lo, const double* q, const double* hi,
+                         const double* prev, const long long* gcis) {
+  // One thread per (cell, tracer); rhom first, as the contract requires -- here by a
+  // separate launch (see main).
+  const long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x;
+  if (k >= (long long) n*nt) return;
+  const int t = (int) (k / n), i = (int) (k % n);
+  const long long g = gcis[i];
+  op.set_Qm(i, t, q[(long long) t*n + g], lo[(long long) t*n + g], hi[(long long) t*n + g],
+            prev[(long long) t*n + g]);
+}
+template <typename Op>
+__global__ void set_rhom_all (const Op op, const int n, const double* rhom,
+                              const long long* gcis) {
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) op.set_rhom(i, 0, rhom[gcis[i]]);
+}
+template <typename Op>
+__global__ void get_all (const Op op, const int n, const int nt, double* out,
+                         const long long* gcis) {
+  const long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x;
+  if (k >= (long long) n*nt) return;
+  const int t = (int) (k / n), i = (int) (k % n);
+  out[(long long) t*n + gcis[i]] = op.get_Qm(i, t);
+}
+
+template <typename T> T* to_dev (const std::vector<T>& h) {
+  T* d = nullptr;
+  cudaMalloc(&d, h.size()*sizeof(T));
+  cudaMemcpy(d, h.data(), h.size()*sizeof(T), cudaMemcpyHostToDevice);
+  return d;
+}
+
+struct Problem {
+  int n, nt;
+  std::vector<int> pts;
+  std::vector<double> rhom, lo, q, hi, prev;
+  Problem (int n_, const std::vector<int>& pts_) : n(n_), nt((int) pts_.size()), pts(pts_) {
+    rhom.resize(n);
+    for (auto* v : {&lo, &q, &hi, &prev}) v->resize((size_t) n*nt);
+    oracle_fill_headline(n, 9, 0, nt, rhom.data(), lo.data(), q.data(), hi.data(), prev.data());
+  }
+};
+
+static int nerr = 0;
+#define REQUIRE(c) do { if ( ! (c)) { ++nerr; std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #c); } } while (0)
+
+static bool same_bits (const std::vector<double>& a, const std::vector<double>& b) {
+  return a.size() == b.size() && std::memcmp(a.data(), b.data(), a.size()*sizeof(double)) == 0;
+}
+
+static std::vector<double> oracle_qlt (const Problem& p, bool imbalanced, bool prefer) {
+  const int nn = 2*p.n - 1;
+  std::vector<int> kids(2*nn);
+  std::vector<int64_t> cellidx(nn);
+  oracle_make_bisection_tree(p.n, imbalanced, kids.data(), cellidx.data());
+  std::vector<double> out((size_t) p.n*p.nt);
+  REQUIRE(oracle_qlt_run(p.n, nn, 0, kids.data(), cellidx.data(), p.nt, p.pts.data(), prefer,
+                         p.rhom.data(), p.lo.data(), p.q.data(), p.hi.data(), p.prev.data(),
+                         out.data()) == 0);
+  return out;
+}
+
+static std::vector<double> oracle_caas (const Problem& p) {
+  const int nn = 2*p.n - 1;
+  std::vector<int> kids(2*nn);
+  std::vector<int64_t> cellidx(nn);
+  oracle_make_bisection_tree(p.n, 0, kids.data(), cellidx.data());
+  std::vector<double> out((size_t) p.n*p.nt);
+  REQUIRE(oracle_caas_run(p.n, 1, nn, 0, kids.data(), cellidx.data(), p.nt, p.pts.data(),
+                          p.lo.data(), p.q.data(), p.hi.data(), p.prev.data(), out.data()) == 0);
+  return out;
+}
+
+// (A) through kernels that copy the DeviceOp by value.
+template <typename CDRT>
+static std::vector<double> run_device (CDRT& cdr, const Problem& p,
+                                       const std::vector<long long>& gcis) {
+  for (int t = 0; t < p.nt; ++t) cdr.declare_tracer(p.pts[t], 0);
+  cdr.end_tracer_declarations();
+  cdr.finish_setup();
+  const typename CDRT::DeviceOp op = cdr.get_device_op();
+  double* rhom = to_dev(p.rhom), * lo = to_dev(p.lo), * q = to_dev(p.q), * hi = to_dev(p.hi),
+    * prev = to_dev(p.prev);
+  long long* g = to_dev(gcis);
+  double* out = nullptr;
+  cudaMalloc(&out, (size_t) p.n*p.nt*sizeof(double));
+  const int nb = (int) (((long long) p.n*p.nt + 255)/256);
+  set_rhom_all<<<(p.n + 255)/256, 256>>>(op, p.n, rhom, g);
+  set_all<<<nb, 256>>>(op, p.n, p.nt, rhom, lo, q, hi, prev, g);
+  cdr.run();
+  get_all<<<nb, 256>>>(op, p.n, p.nt, out, g);
+  std::vector<double> h((size_t) p.n*p.nt);
+  cudaMemcpy(h.data(), out, h.size()*sizeof(double), cudaMemcpyDeviceToHost);
+  for (void* d : {(void*) rhom, (void*) lo, (void*) q, (void*) hi, (void*) prev, (void*) g,
+        (void*) out})
+    cudaFree(d);
+  return h;
+}
+
+// (B) through host calls on a managed-memory CDR.
+template <typename CDRT>
+static std::vector<double> run_host (CDRT& cdr, const Problem& p,
+                                     const std::vector<long long>& gcis) {
+  for (int t = 0; t < p.nt; ++t) cdr.declare_tracer(p.pts[t], 0);
+  cdr.end_tracer_declarations();
+  cdr.finish_setup();
+  const CDR::DeviceOp& op = cdr.get_device_op();
+  std::vector<double> out((size_t) p.n*p.nt);
+  for (int rep = 0; rep < 2; ++rep) {   // CDR::run is repeatable (a time-step loop)
+    for (int i = 0; i < p.n; ++i) op.set_rhom(i, 0, p.rhom[gcis[i]]);
+    for (int t = 0; t < p.nt; ++t)
+      for (int i = 0; i < p.n; ++i) {
+        const size_t k = (size_t) t*p.n + gcis[i];
+        op.set_Qm(i, t, p.q[k], p.lo[k], p.hi[k], p.prev[k]);
+      }
+    cdr.run();
+    for (int t = 0; t < p.nt; ++t)
+      for (int i = 0; i < p.n; ++i) out[(size_t) t*p.n + gcis[i]] = op.get_Qm(i, t);
+  }
+  return out;
+}
+
+int main () {
+  typedef qlt::QLT<> QLTT;
+  typedef caas::CAAS<> CAAST;
+  const int cst = ProblemType::conserve | ProblemType::shapepreserve | ProblemType::consistent,
+    st = ProblemType::shapepreserve | ProblemType::consistent,
+    ct = ProblemType::conserve | ProblemType::consistent, t_ = ProblemType::consistent;
+  mpi::Parallel::Ptr par = mpi::make_parallel();
+
+  for (const int n : {1, 2, 21, 111, 1350, 5400})
+    for (const bool imbalanced : {false, true})
+      for (const bool prefer : {false, true}) {
+        if (n == 5400 && (imbalanced || prefer)) continue;
+        const Problem p(n, {cst, st, ct, t_, ProblemType::shapepreserve, cst});
+        CDR::Options o;
+        o.prefer_numerical_mass_conservation_to_numerical_bounds = prefer;
+        const std::vector<double> ref = oracle_qlt(p, imbalanced, prefer);
+        tree::Node::Ptr tree = tree::make_tree_over_1d_mesh(par, n, imbalanced);
+        std::vector<Long> g;
+        {
+          QLTT q(par, n, tree, o);
+          tree = nullptr;   // the CDR keeps nothing of the caller's tree (cedr_tree.cpp:477)
+          q.get_owned_glblcells(g);
+          REQUIRE(q.nlclcells() == n && (int) g.size() == n);
+          for (int i = 0; i < n; i += 1 + n/7) REQUIRE(q.gci2lci((Int) g[i]) == i);
+          const std::vector<long long> gl(g.begin(), g.end());
+          REQUIRE(same_bits(run_device(q, p, gl), ref));
+          REQUIRE(q.get_num_tracers() == p.nt);
+          REQUIRE(q.get_problem_type(4) == st);   // `s` is reported canonically as `st`
+        }
+        if (n <= 1350) {
+          QLTT q(par, n, tree::make_tree_over_1d_mesh(par, n, imbalanced), o, Memory::managed);
+          const std::vector<long long> gl(g.begin(), g.end());
+          REQUIRE(same_bits(run_host(q, p, gl), ref));
+        }
+      }
+
+  for (const int n : {1, 4, 11, 1350, 5400}) {
+    const Problem p(n, {cst, ProblemType::shapepreserve, cst, st});
+    const std::vector<double> ref = oracle_caas(p);
+    std::vector<long long> id(n);
+    for (int i = 0; i < n; ++i) id[i] = i;
+    { CAAST c(par, n); REQUIRE(same_bits(run_device(c, p, id), ref)); }
+    if (n <= 1350) {
+      CAAST c(par, n, nullptr, Memory::managed);
+      REQUIRE(same_bits(run_host(c, p, id), ref));
+    }
+  }
+
+  { // Error behaviour: std::logic_error, message shaped like cedr_throw_if's.
+    QLTT q(par, 8, tree::make_tree_over_1d_mesh(par, 8));
+    q.declare_tracer(cst, 0);
+    q.end_tracer_declarations();
+    bool threw = false;
+    try { q.declare_tracer(cst, 0); }
+    catch (const std::logic_error& e) {
+      threw = std::strstr(e.what(), "The condition:") && std::strstr(e.what(), "led to the exception");
+    }
+    REQUIRE(threw);
+    threw = false;
+    try { CAAST c(par, 4); c.declare_tracer(ct, 0); }
+    catch (const std::logic_error&) { threw = true; }
+    REQUIRE(threw);
+    std::stringstream ss;
+    q.finish_setup();
+    q.print(ss);
+    REQUIRE(ss.str().find("QLT") != std::string::npos);
+  }
+
+  std::printf(nerr ? "FAIL (%d)\n" : "PASS\n", nerr);
+  return nerr ? 1 : 0;
+}
