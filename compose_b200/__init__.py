@@ -79,6 +79,7 @@ SYMBOLS = [
     ("cedr_b200_last_run_launches", C.c_int, [_H, _ip]),
     ("cedr_b200_set_fast_path", C.c_int, [_H, C.c_int]),
     ("cedr_b200_uses_fast_path", C.c_int, [_H, _ip]),
+    ("cedr_b200_debug_phase_clocks", C.c_int, [_H, C.POINTER(C.c_ulonglong)]),
     ("cedr_b200_set_fused", C.c_int, [_H, C.c_int, C.c_int]),
     ("cedr_b200_uses_fused", C.c_int, [_H, _ip]),
     ("cedr_b200_set_profiling", C.c_int, [_H, C.c_int]),
@@ -330,6 +331,11 @@ class CDR:
         v = C.c_int(0)
         _check(self._lib.cedr_b200_uses_fused(self._h, C.byref(v)))
         return bool(v.value)
+
+    def debug_phase_clocks(self):
+        out = (C.c_ulonglong*16)()
+        _check(self._lib.cedr_b200_debug_phase_clocks(self._h, out))
+        return list(out)
 
     def set_profiling(self, on=True):
         _check(self._lib.cedr_b200_set_profiling(self._h, int(bool(on))))

@@ -155,12 +155,15 @@ struct cedr_b200_cdr {
   DevBuf<unsigned short> d_dtab, d_ptab, d_fpos;
   DevBuf<FastWQ> d_fwq;
   DevBuf<FastRh> d_frh;
+  DevBuf<double> d_frq;
   bool fast_enabled = true;   // cedr_b200_set_fast_path
   bool fast_ok = false;       // plan + buffers allow the fast tier-0 kernels
   bool fused_enabled = false; // cedr_b200_set_fused (opt-in until it beats the multi-launch path)
   bool fused_ok = false;      // plan + device allow the fused persistent kernel
   int fused_depth = 2;        // tracers between UP(k) and DOWN(k)
   int fused_capacity = 0;     // co-resident CTAs of the fused kernel on this device
+  DevBuf<unsigned long long> d_phase_clk;   // debug (CEDR_B200_PHASE_CLOCKS builds)
+  DevBuf<double> d_n7;        // depth-7 sums per own block x tracer (fast path)
   DevBuf<unsigned> d_sync;    // [2 nt]: arrival counters, flags
   DevBuf<int> d_status;
   std::vector<DevBuf<BlockDev> > d_blocks;   // per tier
@@ -338,7 +341,17 @@ fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
   // Tracers per CTA: enough CTAs for several waves, enough tracers per CTA to amortise
   // the per-CTA setup and keep the TMA double buffer busy.
   const long long work = static_cast<long long>(a.nblocks)*a.ntr;
-  a.group = static_cast<int>(std::max<long long>(1, std::min<long long>(16, work/(148*5*4))));
+  a.group = static_cast<int>(std::max<long long>(1, std::min<long long>(32, work/(148*5*4))));
+  if (const char* e = std::getenv("CEDR_B200_GROUP")) a.group = std::max(1, std::atoi(e));
+  a.n7buf = std::getenv("CEDR_B200_DOWN1") ? nullptr : c.d_n7.p;
+  a.rq = c.d_frq.p;
+#ifdef CEDR_B200_PHASE_CLOCKS
+  if ( ! c.d_phase_clk.p) {
+    c.d_phase_clk.alloc(16);
+    CUDA_CHECK(cudaMemset(c.d_phase_clk.p, 0, 16*sizeof(unsigned long long)));
+  }
+  a.phase_clk = c.d_phase_clk.p;
+#endif
   return a;
 }
 
@@ -492,6 +505,7 @@ void run_rhom (cedr_b200_cdr& c, int k0, int k1) {
     a.fpos = (k == 0 && c.fast_ok) ? c.d_fpos.p : nullptr;
     a.fwq = c.d_fwq.p;
     a.frh = c.d_frh.p;
+    a.frq = c.d_frq.p;
     const size_t smem = sizeof(double)*2*static_cast<size_t>(c.plan.tiers[k].max_nl);
     LaunchTimer lt(c, CEDR_B200_TAG_RHOM, k);
     rhom_kernel<<<a.nblocks, kThreads, smem, c.stream>>>(a);
@@ -727,10 +741,16 @@ void finish_setup (cedr_b200_cdr& c) {
   c.d_ptab.upload(c.plan.dev_ptab);
   c.d_fpos.upload(c.plan.dev_fpos);
   c.fast_ok = c.fast_enabled && c.plan.tier0_fast &&
-    reinterpret_cast<uintptr_t>(c.in) % 16 == 0 && ! std::getenv("CEDR_B200_NO_FAST");
+    reinterpret_cast<uintptr_t>(c.in) % 16 == 0 &&
+    (c.is_caas || reinterpret_cast<uintptr_t>(c.out) % 16 == 0) &&
+    ! std::getenv("CEDR_B200_NO_FAST");
   if (c.fast_ok) {
     c.d_fwq.alloc(std::max(1, c.plan.ninternal));
     c.d_frh.alloc(std::max(1, c.plan.ninternal));
+    c.d_frq.alloc(std::max(1, c.plan.ninternal));
+    if ( ! c.is_caas)
+      c.d_n7.alloc(static_cast<size_t>(384)*std::max<size_t>(1, c.own_blocks.size())*
+                   std::max(1, nt));
   }
   c.d_qglob.alloc(2*static_cast<size_t>(nt));
   c.d_caas_scal.alloc(2*static_cast<size_t>(nt));
@@ -1096,6 +1116,18 @@ int cedr_b200_synchronize (cedr_b200_cdr* c) {
       CUDA_CHECK(cudaMemcpy(&st, c->d_status.p, sizeof(int), cudaMemcpyDeviceToHost));
       if (st) throw std::runtime_error("cedr_b200: the fused run() kernel gave up waiting "
                                        "for a tracer's root (results are invalid)");
+    }
+  });
+}
+
+int cedr_b200_debug_phase_clocks (cedr_b200_cdr* c, unsigned long long* out16) {
+  return guarded([&] {
+    for (int i = 0; i < 16; ++i) out16[i] = 0;
+    if (c->d_phase_clk.p) {
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      CUDA_CHECK(cudaMemcpy(out16, c->d_phase_clk.p, 16*sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemset(c->d_phase_clk.p, 0, 16*sizeof(unsigned long long)));
     }
   });
 }

@@ -65,6 +65,18 @@ __device__ __forceinline__ void mbar_wait (uint64_t* bar, unsigned parity) {
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
   } while ( ! ok);
 }
+// TMA bulk copy shared -> global (16-byte aligned addresses and size), bulk-group tracked.
+__device__ __forceinline__ void tma_store (void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit () {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// Wait until the committed bulk stores have finished READING shared memory.
+__device__ __forceinline__ void tma_store_wait_read () {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 // TMA bulk copy global -> shared (16-byte aligned addresses and size).
 __device__ __forceinline__ void tma_load (void* dst, const void* src, unsigned bytes,
                                           uint64_t* bar) {
@@ -96,7 +108,22 @@ struct FastArgs {
   int sbuf;                     // doubles per staged row (even, >= max_nl + 2)
   int prefer_mass_con;
   const double* qglob;
+  unsigned long long* phase_clk;  // debug: per-phase clock sums (CEDR_B200_PHASE_CLOCKS)
+  // Depth-7 sums (min, Qm, max) of every block x tracer, written by up_kernel for
+  // down2_kernel's top warp: [(t nblocks + block)*384 + f*128 + depth-7 node].
+  double* n7buf;
+  const double* rq;             // per block, fast order: RN(1/(q0 + q1)) or 0 (node_solve.cuh)
 };
+
+#ifdef CEDR_B200_PHASE_CLOCKS
+# define CEDR_PHASE_DECL long long pc_t0 = clock64(); unsigned long long pc_acc[8] = {0}
+# define CEDR_PHASE(k) do { const long long pc_t1 = clock64(); pc_acc[k] += pc_t1 - pc_t0; pc_t0 = pc_t1; } while (0)
+# define CEDR_PHASE_FLUSH(base) do { if (a.phase_clk) for (int pc_i = 0; pc_i < 8; ++pc_i) atomicAdd(a.phase_clk + (base) + pc_i, pc_acc[pc_i]); } while (0)
+#else
+# define CEDR_PHASE_DECL do {} while (0)
+# define CEDR_PHASE(k) do {} while (0)
+# define CEDR_PHASE_FLUSH(base) do {} while (0)
+#endif
 
 template <int CLS> struct Rows {
   // Rows of a tracer in the caller-facing buffer (cedr_qlt_inl.hpp:21-58) and where
@@ -218,6 +245,11 @@ up_kernel (const FastArgs a) {
         else
           r[f] = (n[0][f] + n[1][f]) + (n[2][f] + n[3][f]);
       }
+    }
+    if ((CLS == CLS_ST || CLS == CLS_CST) && a.n7buf) {
+      double* const n7 = a.n7buf + (static_cast<long long>(t)*a.nblocks + b)*384;
+#pragma unroll
+      for (int f = 0; f < 3; ++f) n7[f*128 + tid] = r[f];
     }
     // Depths 6..2 inside the warp: lane l (l % 2^(L+1) == 0) takes left + right.
 #pragma unroll
@@ -437,10 +469,14 @@ down_kernel (const FastArgs a) {
 //     problems wide -- one TOP warp walks it;
 //   - the micro-subtrees, depths 7..9 (~80% of the nodes): 128 independent columns, one
 //     per thread of the four LEAF warps, dense and barrier-free.
-// The CTA walks its group of tracers as a two-stage pipeline: while the leaf warps sum
-// tracer i's micro-subtrees (A(i)) and then solve tracer i-1's (C(i-1)), the top warp
-// solves the block top of tracer i (T(i)). Stages hand over through named barriers;
-// leaf rows are TMA-staged two tracers deep.
+// The two run as a pipeline over the CTA's group of tracers. The top warp needs only the
+// 128 depth-7 sums of a tracer, which the up-sweep kernel left in `n7buf` (3 KB per
+// block x tracer): it TMA-loads them, sums depths 6..0 with vector loads and warp
+// shuffles, solves depths 0..6 and publishes the 128 depth-7 masses (T(i)). The leaf
+// warps TMA-stage the tracer's (min, Qm, max) rows two tracers deep, re-sum their
+// micro-subtrees, wait for T(i) and solve depths 7..9 (C(i)). Hand-over is by named
+// barriers: BAR_T "T(i) published", BAR_C "C(i) has read its masses" (the top warp may
+// reuse the buffers of tracer i for tracer i+2).
 constexpr int kLeafThreads = 128;
 constexpr int kDown2Threads = 160;
 
@@ -460,11 +496,13 @@ template <int BASE, int COUNT> __device__ __forceinline__ void bar_arrive (const
   if (parity) bar_arrive_i<BASE + 1, COUNT>(); else bar_arrive_i<BASE, COUNT>();
 }
 
-// Shared memory of down2_kernel, in doubles: stage[2][3][sbuf], un[2][3][256],
-// xs[2][256], then topc[128] (NodeWQ) and 2 mbarriers.
+// Shared memory of down2_kernel, in doubles: stage[2][3][sbuf] leaf rows, n7s[2][3][128]
+// depth-7 sums, un[2][3][128] sums of heap nodes 0..126, xs[2][256] solved masses of heap
+// nodes 0..254, d9x[512] solved masses of the depth-9 pairs; then topc[128] (NodeWQ) and
+// 4 mbarriers.
 inline size_t down2_smem_bytes (const int sbuf) {
-  return sizeof(double)*(6*static_cast<size_t>(sbuf) + 2*3*256 + 2*256) +
-    128*sizeof(dev::NodeWQ) + 16;
+  return sizeof(double)*(6*static_cast<size_t>(sbuf) + 2*3*128 + 2*3*128 + 2*256 + kD9 + 128) +
+    128*sizeof(dev::NodeWQ) + 32;
 }
 
 template <int CLS>
@@ -474,11 +512,14 @@ down2_kernel (const FastArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int sbuf = a.sbuf;
   double* const stage = reinterpret_cast<double*>(smraw);            // [2][3][sbuf]
-  double* const un = stage + 6*sbuf;                                 // [2][3][256]
-  double* const xs = un + 2*3*256;                                   // [2][256]
-  dev::NodeWQ* const topc = reinterpret_cast<dev::NodeWQ*>(xs + 2*256);   // [128]
-  uint64_t* const mbar = reinterpret_cast<uint64_t*>(topc + 128);    // [2]
-  constexpr int BAR_A = 1, BAR_T = 3, BAR_LEAF = 5;   // + parity for A and T
+  double* const n7s = stage + 6*sbuf;                                // [2][3][128]
+  double* const un = n7s + 2*3*128;                                  // [2][3][128]
+  double* const xs = un + 2*3*128;                                   // [2][256]
+  double* const d9x = xs + 2*256;                                    // [4][128]
+  double* const toprq = d9x + kD9;                                   // [128]
+  dev::NodeWQ* const topc = reinterpret_cast<dev::NodeWQ*>(toprq + 128);  // [128]
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(topc + 128);    // [2] rows, [2] n7
+  constexpr int BAR_T = 1, BAR_C = 3, BAR_LEAF = 5;   // + parity for T and C
 
   const int b = blockIdx.x % a.nblocks, grp = blockIdx.x / a.nblocks;
   const BlockDev B = a.blocks[b];
@@ -491,70 +532,101 @@ down2_kernel (const FastArgs a) {
   const unsigned short* const ptab = a.ptab + B.fpair_off;
   const dev::NodeWQ* const wq = a.wq + B.fbase;
   const dev::NodeRh* const rh = a.rh + B.fbase;
+  const double* const rqv = a.rq + B.fbase;
   const bool prefer = a.prefer_mass_con != 0;
 
-  auto solve = [&] (const dev::NodeWQ& c, const int cpos, const double* nd, const double bm,
-                    const double* k0, const double* k1, double& x0, double& x1) {
+  auto solve = [&] (const dev::NodeWQ& c, const double rq, const int cpos, const double* nd,
+                    const double bm, const double* k0, const double* k1, double& x0,
+                    double& x1) {
     if (prefer)
-      dev::solve_bounded_lean<true>(c, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
+      dev::solve_bounded_lean<true>(c, rq, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
                                     k0[2], k1[0], k1[1], k1[2], x0, x1);
     else
-      dev::solve_bounded_lean<false>(c, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
+      dev::solve_bounded_lean<false>(c, rq, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
                                      k0[2], k1[0], k1[1], k1[2], x0, x1);
   };
 
-  if (tid < kHeapNodes/4) topc[tid] = wq[tid];
+  if (tid < kHeapNodes/4) { topc[tid] = wq[tid]; toprq[tid] = rqv[tid]; }
   if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+    for (int q = 0; q < 4; ++q) mbar_init(&mbar[q], 1);
     mbar_fence_init();
   }
   __syncthreads();
 
   if (warp == 4) {
     // ------------------------------------------------------------- TOP warp
+    CEDR_PHASE_DECL;
+    auto issue_n7 = [&] (const int i) {
+      const int t = a.tracers[g0 + i];
+      const double* src = a.n7buf + (static_cast<long long>(t)*a.nblocks + b)*384;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&mbar[2 + (i & 1)], 384*8);
+      tma_load(n7s + (i & 1)*384, src, 384*8, &mbar[2 + (i & 1)]);
+    };
+    if (lane == 0) {
+      issue_n7(0);
+      if (gn > 1) issue_n7(1);
+    }
     for (int i = 0; i < gn; ++i) {
       const int t = a.tracers[g0 + i];
-      double* const u = un + (i & 1)*3*256;
+      const double* const s7 = n7s + (i & 1)*384;
+      double* const u = un + (i & 1)*384;
       double* const x = xs + (i & 1)*256;
-      // The block root's mass, from the tier above (issued before the wait).
+      // The block root's mass, from the tier above (issued before the waits).
       double xroot = 0;
       if (lane == 0) xroot = __ldcg(a.sol_in + static_cast<long long>(t)*a.sol_in_ld + B.gidx);
-      bar_sync<BAR_A, kDown2Threads>(i & 1);     // A(i): depth-7 sums are in u
-      // Sums of depths 6..0 (heap node h has kids 2h+1, 2h+2).
+      CEDR_PHASE(0);
+      mbar_wait(&mbar[2 + (i & 1)], (i >> 1) & 1);
+      if (i >= 2) bar_sync<BAR_C, kDown2Threads>(i & 1);   // C(i-2) is done with x, u
+      CEDR_PHASE(1);
+      // Sums of depths 6..0. Lane l holds depth-7 nodes 4l..4l+3: depth 6 and 5 locally,
+      // depths 4..0 by shuffles (heap node h has kids 2h+1, 2h+2; left + right).
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int h = 63 + lane + 32*q;
+      for (int f = 0; f < 3; ++f) {
+        const double2 v01 = reinterpret_cast<const double2*>(s7 + f*128)[2*lane];
+        const double2 v23 = reinterpret_cast<const double2*>(s7 + f*128)[2*lane + 1];
+        const double d6a = v01.x + v01.y, d6b = v23.x + v23.y;
+        u[f*128 + 63 + 2*lane] = d6a;
+        u[f*128 + 64 + 2*lane] = d6b;
+        double r = d6a + d6b;
+        u[f*128 + 31 + lane] = r;
 #pragma unroll
-        for (int f = 0; f < 3; ++f) u[f*256 + h] = u[f*256 + 2*h + 1] + u[f*256 + 2*h + 2];
-      }
-      __syncwarp();
-      for (int dd = 5; dd >= 0; --dd) {
-        if (lane < (1 << dd)) {
-          const int h = (1 << dd) - 1 + lane;
-#pragma unroll
-          for (int f = 0; f < 3; ++f) u[f*256 + h] = u[f*256 + 2*h + 1] + u[f*256 + 2*h + 2];
+        for (int Lv = 0; Lv < 5; ++Lv) {
+          r = r + __shfl_down_sync(0xffffffffu, r, 1 << Lv);
+          if ((lane & ((2 << Lv) - 1)) == 0) u[f*128 + (16 >> Lv) - 1 + (lane >> (Lv + 1))] = r;
         }
-        __syncwarp();
       }
       if (lane == 0) x[0] = xroot;
       __syncwarp();
-      // Node problems of depths 0..6.
+      CEDR_PHASE(2);
+      // Node problems of depths 0..6 (the kids of depth 6 are the depth-7 sums).
       for (int dd = 0; dd <= 6; ++dd) {
         for (int p = lane; p < (1 << dd); p += 32) {
           const int h = (1 << dd) - 1 + p;
-          const double nd[3] = {u[h], u[256 + h], u[512 + h]};
-          const double k0[3] = {u[2*h + 1], u[256 + 2*h + 1], u[512 + 2*h + 1]};
-          const double k1[3] = {u[2*h + 2], u[256 + 2*h + 2], u[512 + 2*h + 2]};
+          const double nd[3] = {u[h], u[128 + h], u[256 + h]};
+          double k0[3], k1[3];
+          if (dd < 6) {
+#pragma unroll
+            for (int f = 0; f < 3; ++f) { k0[f] = u[f*128 + 2*h + 1]; k1[f] = u[f*128 + 2*h + 2]; }
+          } else {
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+              const double2 v = reinterpret_cast<const double2*>(s7 + f*128)[p];
+              k0[f] = v.x; k1[f] = v.y;
+            }
+          }
           double x0, x1;
-          solve(topc[h], h, nd, x[h], k0, k1, x0, x1);
+          solve(topc[h], toprq[h], h, nd, x[h], k0, k1, x0, x1);
           x[2*h + 1] = x0;
           x[2*h + 2] = x1;
         }
         __syncwarp();
       }
+      CEDR_PHASE(3);
+      if (lane == 0 && i + 2 < gn) issue_n7(i + 2);
       bar_arrive<BAR_T, kDown2Threads>(i & 1);   // T(i): x[127..254] are solved
     }
+    if (lane == 0) CEDR_PHASE_FLUSH(8);
     return;
   }
 
@@ -576,17 +648,23 @@ down2_kernel (const FastArgs a) {
     ps += __shfl_xor_sync(0xffffffffu, ps, o);
     pe += __shfl_xor_sync(0xffffffffu, pe, o);
   }
-  // Leaf offset | depth-9 position << 16 of this lane's (up to two) pairs.
+  // Leaf offset | d9x slot << 16 of this lane's (up to two) pairs; d9x slot of depth-9
+  // position p = 4 tid' + q is q*128 + tid' (conflict-free for the owners' stores).
   unsigned pair_slot[2] = {0xffffffffu, 0xffffffffu};
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const int j = ps + lane + 32*q;
     if (j < pe) {
       const unsigned p = ptab[j];
-      pair_slot[q] = ((dtab[p] & 0x7fffu) + shift) | (p << 16);
+      pair_slot[q] = ((dtab[p] & 0x7fffu) + shift) | (((p & 3)*128 + (p >> 2)) << 16);
     }
   }
   const dev::NodeWQ c7 = wq[127 + tid], c8a = wq[255 + 2*tid], c8b = wq[256 + 2*tid];
+#ifdef CEDR_B200_FASTDIV
+  const double rq7 = rqv[127 + tid], rq8a = rqv[255 + 2*tid], rq8b = rqv[256 + 2*tid];
+#else
+  const double rq7 = 0, rq8a = 0, rq8b = 0;
+#endif
 
   auto issue = [&] (const int i) {
     const int t = a.tracers[g0 + i];
@@ -602,104 +680,120 @@ down2_kernel (const FastArgs a) {
     if (gn > 1) issue(1);
   }
 
-  for (int i = 0; i <= gn; ++i) {
-    if (i < gn) {
-      // ---- A(i): depth-7 sums of tracer i into un[i & 1].
-      mbar_wait(&mbar[i & 1], (i >> 1) & 1);
-      const double* const s = stage + (i & 1)*3*sbuf;
-      double* const u = un + (i & 1)*3*256;
-      double n7[3] = {0, 0, 0};
+  CEDR_PHASE_DECL;
+  for (int k = 0; k < gn; ++k) {
+    // ---- C(k): the micro-subtrees of tracer k.
+    const int t = a.tracers[g0 + k];
+    double* const s = stage + (k & 1)*3*sbuf;
+    double* const xout = s + sbuf;                 // solved leaves replace the Qm row
+    const double* const x = xs + (k & 1)*256;
+    CEDR_PHASE(0);
+    mbar_wait(&mbar[k & 1], (k >> 1) & 1);
+    CEDR_PHASE(1);
+    // Constants of this lane's pairs: issued now, used after the depth-8 solves.
+    dev::NodeWQ cp[2];
+    double rqp[2] = {0, 0};
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        double n8[3];
-#pragma unroll
-        for (int f = 0; f < 3; ++f) {
-          const int ka = 2*hf, kb = 2*hf + 1;
-          const double a0 = s[f*sbuf + off[ka]], a1 = s[f*sbuf + off[ka] + 1];
-          const double b0 = s[f*sbuf + off[kb]], b1 = s[f*sbuf + off[kb] + 1];
-          n8[f] = (pr[ka] ? a0 + a1 : a0) + (pr[kb] ? b0 + b1 : b0);
-        }
-#pragma unroll
-        for (int f = 0; f < 3; ++f) n7[f] = hf ? n7[f] + n8[f] : n8[f];
+    for (int q = 0; q < 2; ++q)
+      if (pair_slot[q] != 0xffffffffu) {
+        cp[q] = wq[kHeapNodes + ps + lane + 32*q];
+#ifdef CEDR_B200_FASTDIV
+        rqp[q] = rqv[kHeapNodes + ps + lane + 32*q];
+#endif
       }
+    // Sums of this thread's depth-9 nodes (a leaf or a pair), depth-8 and depth-7 nodes.
+    double n9[4][3], n8[2][3], n7[3];
 #pragma unroll
-      for (int f = 0; f < 3; ++f) u[f*256 + 127 + tid] = n7[f];
-      bar_arrive<BAR_A, kDown2Threads>(i & 1);
-    }
-    if (i >= 1) {
-      // ---- C(i-1): the micro-subtrees of tracer i-1, from the top warp's x.
-      const int k = i - 1;
-      const int t = a.tracers[g0 + k];
-      double* const s = stage + (k & 1)*3*sbuf;
-      double* const xout = s + sbuf;                 // solved leaves replace the Qm row
-      double* const d9x = un + (k & 1)*3*256;        // the sums are dead once T(k) is done
-      const double* const x = xs + (k & 1)*256;
-      auto node9 = [&] (const int q, double* n9) {
-#pragma unroll
-        for (int f = 0; f < 3; ++f) {
-          const double v0 = s[f*sbuf + off[q]], v1 = s[f*sbuf + off[q] + 1];
-          n9[f] = pr[q] ? v0 + v1 : v0;
-        }
-      };
-      dev::NodeWQ cp[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-        if (pair_slot[q] != 0xffffffffu) cp[q] = wq[kHeapNodes + ps + lane + 32*q];
-      double n9[4][3], n8[2][3], n7[3];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) node9(q, n9[q]);
+    for (int q = 0; q < 4; ++q) {
+      const double* const r0 = s + off[q];
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
-        n8[0][f] = n9[0][f] + n9[1][f];
-        n8[1][f] = n9[2][f] + n9[3][f];
-        n7[f] = n8[0][f] + n8[1][f];
+        const double v0 = r0[f*sbuf];
+        n9[q][f] = v0;
+        if (pr[q]) n9[q][f] = v0 + r0[f*sbuf + 1];
       }
-      bar_sync<BAR_T, kDown2Threads>(k & 1);     // T(k) done
-      double x8[2];
-      solve(c7, 127 + tid, n7, x[127 + tid], n8[0], n8[1], x8[0], x8[1]);
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        double x9[2];
-        solve(hf ? c8b : c8a, 255 + 2*tid + hf, n8[hf], x8[hf], n9[2*hf], n9[2*hf + 1],
-              x9[0], x9[1]);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int q = 2*hf + j;
-          if (pr[q]) d9x[4*tid + q] = x9[j];
-          else xout[off[q]] = x9[j];
-        }
-      }
-      __syncwarp();
-      auto solve_pair = [&] (const dev::NodeWQ& c, const int j, const int o, const int p) {
-        double k0[3], k1[3], nd[3];
-#pragma unroll
-        for (int f = 0; f < 3; ++f) {
-          k0[f] = s[f*sbuf + o];
-          k1[f] = s[f*sbuf + o + 1];
-          nd[f] = k0[f] + k1[f];
-        }
-        double x0, x1;
-        solve(c, kHeapNodes + j, nd, d9x[p], k0, k1, x0, x1);
-        xout[o] = x0;
-        xout[o + 1] = x1;
-      };
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-        if (pair_slot[q] != 0xffffffffu)
-          solve_pair(cp[q], ps + lane + 32*q, pair_slot[q] & 0xffff, pair_slot[q] >> 16);
-      for (int j = ps + lane + 64; j < pe; j += 32) {   // blocks with > 64 pairs per warp
-        const int p = ptab[j];
-        solve_pair(wq[kHeapNodes + j], j, (dtab[p] & 0x7fff) + shift, p);
-      }
-      bar_sync_i<BAR_LEAF, kLeafThreads>();
-      {
-        double* const o = a.out + static_cast<long long>(t)*a.out_ld + B.leaf0;
-        for (int q = tid; q < B.nl; q += kLeafThreads) o[q] = xout[shift + q];
-      }
-      bar_sync_i<BAR_LEAF, kLeafThreads>();
-      if (tid == 0 && k + 2 < gn) issue(k + 2);
     }
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      n8[0][f] = n9[0][f] + n9[1][f];
+      n8[1][f] = n9[2][f] + n9[3][f];
+      n7[f] = n8[0][f] + n8[1][f];
+    }
+    CEDR_PHASE(2);
+    bar_sync<BAR_T, kDown2Threads>(k & 1);       // T(k) published
+    const double x7 = x[127 + tid];
+    bar_arrive<BAR_C, kDown2Threads>(k & 1);     // xs / un of tracer k may be reused
+    CEDR_PHASE(3);
+    double x8[2];
+    solve(c7, rq7, 127 + tid, n7, x7, n8[0], n8[1], x8[0], x8[1]);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      double x9[2];
+      solve(hf ? c8b : c8a, hf ? rq8b : rq8a, 255 + 2*tid + hf, n8[hf], x8[hf], n9[2*hf],
+            n9[2*hf + 1], x9[0], x9[1]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int q = 2*hf + j;
+        if (pr[q]) d9x[q*128 + tid] = x9[j];
+        else xout[off[q]] = x9[j];
+      }
+    }
+    __syncwarp();
+    CEDR_PHASE(4);
+    auto solve_pair = [&] (const dev::NodeWQ& c, const double rq, const int j, const int o,
+                           const int slot) {
+      double k0[3], k1[3], nd[3];
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        k0[f] = s[f*sbuf + o];
+        k1[f] = s[f*sbuf + o + 1];
+        nd[f] = k0[f] + k1[f];
+      }
+      double x0, x1;
+      solve(c, rq, kHeapNodes + j, nd, d9x[slot], k0, k1, x0, x1);
+      xout[o] = x0;
+      xout[o + 1] = x1;
+    };
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (pair_slot[q] != 0xffffffffu)
+        solve_pair(cp[q], rqp[q], ps + lane + 32*q, pair_slot[q] & 0xffff,
+                   pair_slot[q] >> 16);
+    for (int j = ps + lane + 64; j < pe; j += 32) {   // blocks with > 64 pairs per warp
+      const int p = ptab[j];
+      solve_pair(wq[kHeapNodes + j], rqv[kHeapNodes + j], j, (dtab[p] & 0x7fff) + shift,
+                 (p & 3)*128 + (p >> 2));
+    }
+    CEDR_PHASE(5);
+    // Write-back: the solved leaves sit in block order in xout; one TMA bulk store moves
+    // the 16-byte aligned interior, thread 0 stores the (at most two) edge elements. No
+    // other thread waits: the stage is refilled only after the store has read it.
+#ifdef CEDR_B200_NO_TMASTORE
+    bar_sync_i<BAR_LEAF, kLeafThreads>();
+    {
+      double* const o = a.out + static_cast<long long>(t)*a.out_ld + B.leaf0;
+      for (int q = tid; q < B.nl; q += kLeafThreads) o[q] = xout[shift + q];
+    }
+    bar_sync_i<BAR_LEAF, kLeafThreads>();
+    if (tid == 0 && k + 2 < gn) issue(k + 2);
+#else
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    bar_sync_i<BAR_LEAF, kLeafThreads>();
+    if (tid == 0) {
+      double* const o = a.out + static_cast<long long>(t)*a.out_ld + B.leaf0;
+      const int q0 = B.leaf0 & 1;
+      const int nint = (B.nl - q0) & ~1;
+      if (nint) tma_store(o + q0, xout + shift + q0, 8u*static_cast<unsigned>(nint));
+      tma_store_commit();
+      if (q0) o[0] = xout[shift];
+      if (q0 + nint < B.nl) o[B.nl - 1] = xout[shift + B.nl - 1];
+      tma_store_wait_read();
+      if (k + 2 < gn) issue(k + 2);
+    }
+#endif
+    CEDR_PHASE(6);
   }
+  if (tid == 0) CEDR_PHASE_FLUSH(0);
 }
 
 } // namespace fast

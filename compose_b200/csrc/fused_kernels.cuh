@@ -333,10 +333,10 @@ run_kernel (const Args a) {
                         const double bm, const double* k0, const double* k1, double& x0,
                         double& x1) {
         if (prefer)
-          dev::solve_bounded_lean<true>(c, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
+          dev::solve_bounded_lean<true>(c, 0.0, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
                                         k0[2], k1[0], k1[1], k1[2], x0, x1);
         else
-          dev::solve_bounded_lean<false>(c, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
+          dev::solve_bounded_lean<false>(c, 0.0, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
                                          k0[2], k1[0], k1[1], k1[2], x0, x1);
       };
       // Sums of the depth-9 node k of this thread (a leaf or a pair), from the rows.

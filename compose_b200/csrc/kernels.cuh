@@ -269,6 +269,7 @@ struct RhomArgs {
   const unsigned short* fpos;  // fast-path const positions (may be null)
   FastWQ* fwq;
   FastRh* frh;
+  double* frq;                 // RN(1/(q0 + q1)) or 0, see node_solve.cuh div_by_qmass
 };
 
 __global__ void __launch_bounds__(256)
@@ -303,6 +304,7 @@ rhom_kernel (const RhomArgs a) {
         FastRh r;
         r.rh0 = rh0; r.rh1 = rh1;
         a.frh[pos] = r;
+        a.frq[pos] = dev::reciprocal_for_div(c.q0 + c.q1);
       }
     }
     __syncthreads();

@@ -231,6 +231,9 @@ enum {
 int cedr_b200_set_profiling(cedr_b200_cdr* cdr, int on);
 int cedr_b200_get_launch_times(cedr_b200_cdr* cdr, int cap, float* ms_host,
                                int* tags_host, int* tiers_host, int* n);
+/* Debug builds only (-DCEDR_B200_PHASE_CLOCKS): clock sums per phase of the
+ * specialised down-sweep, [0..8) leaf warp 0, [8..16) top warp; zeros otherwise. */
+int cedr_b200_debug_phase_clocks(cedr_b200_cdr* cdr, unsigned long long* out16);
 /* Tree plan facts: tiers, blocks in tier 0, max leaves per block, reference level
  * count (tree height + 1, cedr_tree.cpp:215-231). Any pointer may be NULL. */
 int cedr_b200_plan_info(const cedr_b200_cdr* cdr, int* ntiers, int* nblocks0,
