@@ -164,6 +164,14 @@ struct cedr_b200_cdr {
   int fused_capacity = 0;     // co-resident CTAs of the fused kernel on this device
   DevBuf<unsigned long long> d_phase_clk;   // debug (CEDR_B200_PHASE_CLOCKS builds)
   DevBuf<double> d_n7;        // depth-7 sums per own block x tracer (fast path)
+  // Expanded tier above the fast blocks (FastArgs::split): its leaves are the 2^split
+  // depth-`split` nodes of every tier-0 block; one block, swept by the generic kernels.
+  int split = 0;
+  int x_nl = 0, x_ni = 0;
+  long long x_ld = 0;
+  DevBuf<BlockDev> d_xblock;
+  DevBuf<dev::NodeConst> d_xnc;
+  DevBuf<double> d_xrhom, d_xrec, d_xsol;
   DevBuf<unsigned> d_sync;    // [2 nt]: arrival counters, flags
   DevBuf<int> d_status;
   std::vector<DevBuf<BlockDev> > d_blocks;   // per tier
@@ -219,17 +227,22 @@ size_t sweep_smem_bytes (const cedr_b200_cdr& c, int tier) {
   return sizeof(double)*4*static_cast<size_t>(2*c.plan.tiers[tier].max_nl);
 }
 
+// Raise (never lower) the dynamic shared memory limit of sweep_kernel<CLS, MODE>.
+template <int CLS, int MODE> void sweep_smem_configure (const size_t smem) {
+  static size_t configured = 48*1024;
+  if (smem > configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(sweep_kernel<CLS, MODE>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+    configured = smem;
+  }
+}
+
 template <int CLS, int MODE>
 void launch_sweep (cedr_b200_cdr& c, int tier, const SweepArgs& a) {
   if (a.ntr == 0 || a.nblocks == 0) return;
   const size_t smem = sweep_smem_bytes(c, tier);
-  static size_t configured = 0;
-  if (smem > configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(sweep_kernel<CLS, MODE>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(std::max<size_t>(smem, 48*1024))));
-    configured = smem;
-  }
+  sweep_smem_configure<CLS, MODE>(smem);
   const long long grid = static_cast<long long>(a.nblocks)*a.ntr;
   cedr_b200_throw_if(grid > 0x7fffffffLL, "grid too large");
   LaunchTimer lt(c, MODE == MODE_UP ? CEDR_B200_TAG_UP : MODE == MODE_TOP ?
@@ -345,6 +358,13 @@ fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
   if (const char* e = std::getenv("CEDR_B200_GROUP")) a.group = std::max(1, std::atoi(e));
   a.n7buf = std::getenv("CEDR_B200_DOWN1") ? nullptr : c.d_n7.p;
   a.rq = c.d_frq.p;
+  if (c.split && cls != CLS_CAAS) {
+    a.split = c.split;
+    a.rec_out = c.d_xrec.p;
+    a.rec_ld = c.x_ld;
+    a.sol_in = c.d_xsol.p;
+    a.sol_in_ld = c.x_ld;
+  }
 #ifdef CEDR_B200_PHASE_CLOCKS
   if ( ! c.d_phase_clk.p) {
     c.d_phase_clk.alloc(16);
@@ -506,12 +526,144 @@ void run_rhom (cedr_b200_cdr& c, int k0, int k1) {
     a.fwq = c.d_fwq.p;
     a.frh = c.d_frh.p;
     a.frq = c.d_frq.p;
+    a.sub_out = (k == 0 && c.split) ? c.d_xrhom.p : nullptr;
+    a.split = c.split;
     const size_t smem = sizeof(double)*2*static_cast<size_t>(c.plan.tiers[k].max_nl);
     LaunchTimer lt(c, CEDR_B200_TAG_RHOM, k);
     rhom_kernel<<<a.nblocks, kThreads, smem, c.stream>>>(a);
     CUDA_CHECK(cudaGetLastError());
     ++c.last_launches;
   }
+}
+
+// ---- expanded tier above the fast blocks (FastArgs::split)
+
+// rhom sums and node constants of the expanded tier, from the sub-root rhom the tier-0
+// rhom sweep left in d_xrhom.
+void run_rhom_x (cedr_b200_cdr& c) {
+  if ( ! c.split) return;
+  RhomArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.blocks = c.d_xblock.p;
+  a.nblocks = 1;
+  a.lvlptr = c.d_lvlptr.p;
+  a.kid0 = c.d_kid0.p;
+  a.kid1 = c.d_kid1.p;
+  a.in = c.d_xrhom.p;
+  a.nc = c.d_xnc.p;
+  const size_t smem = sizeof(double)*2*static_cast<size_t>(c.x_nl);
+  LaunchTimer lt(c, CEDR_B200_TAG_RHOM, 1);
+  rhom_kernel<<<1, kThreads, smem, c.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++c.last_launches;
+}
+
+// Sweep of the expanded tier for a fast class: up over the sub-roots, root_compute, down.
+template <int CLS> void launch_top_x_cls (cedr_b200_cdr& c, int cls) {
+  SweepArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.blocks = c.d_xblock.p;
+  a.nblocks = 1;
+  a.lvlptr = c.d_lvlptr.p;
+  a.kid0 = c.d_kid0.p;
+  a.kid1 = c.d_kid1.p;
+  a.nc = c.d_xnc.p;
+  a.in = c.d_xrec.p;
+  a.in_ld = c.x_ld;
+  a.out = c.d_xsol.p;
+  a.out_ld = c.x_ld;
+  a.trcr_row = c.d_trcr_row.p;
+  a.trcr_prob = c.d_trcr_prob.p;
+  a.tracers = c.d_cls_tracers[cls].p;
+  a.ntr = static_cast<int>(c.cls_tracers[cls].size());
+  a.prefer_mass_con = c.prefer_mass_con;
+  a.qglob = c.d_qglob.p;
+  a.caas_scal = c.d_caas_scal.p;
+  const size_t smem = sizeof(double)*4*static_cast<size_t>(c.x_nl + c.x_ni);
+  sweep_smem_configure<CLS, MODE_TOP>(smem);
+  LaunchTimer lt(c, CEDR_B200_TAG_TOP, 1);
+  sweep_kernel<CLS, MODE_TOP><<<a.ntr, kThreads, smem, c.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++c.last_launches;
+}
+
+void launch_top_x (cedr_b200_cdr& c, int cls) {
+  if (cls == CLS_ST) launch_top_x_cls<CLS_ST>(c, cls);
+  else launch_top_x_cls<CLS_CST>(c, cls);
+}
+
+// Build the expanded tier: every leaf b of the tier-1 block (a tier-0 block root) becomes
+// a perfect subtree of depth S whose 2^S leaves are block b's depth-S nodes.
+void build_split (cedr_b200_cdr& c) {
+  c.split = 0;
+  if ( ! c.fast_ok || c.is_caas || std::getenv("CEDR_B200_NO_SPLIT") ||
+      std::getenv("CEDR_B200_DOWN1")) return;
+  if (c.plan.tiers.size() != 2 || c.plan.tiers[1].blocks.size() != 1) return;
+  const int nl = c.plan.tiers[1].nleaves;
+  const int S = 8*nl <= 2048 ? 3 : 4*nl <= 2048 ? 2 : 0;
+  if (S == 0) return;
+  // Multi-rank runs exchange block roots (the expanded tier would multiply the message by
+  // 2^S and its replicated sweep does not shrink with the rank count).
+  if (c.nranks > 1) return;
+  const Shape& s1 = c.plan.shapes[c.plan.tiers[1].blocks[0].shape];
+  const int E = 1 << S, nx = (E - 1)*nl;     // expansion nodes
+  Shape x;
+  x.nl = E*nl;
+  x.ni = nx + s1.ni;
+  x.nlev = s1.nlev + S;
+  // Heights 1..S: expansion nodes of depth d = S - h, per block b and position p.
+  std::vector<int> hstart(S + 2, 0);   // first internal index of height h
+  for (int h = 1; h <= S; ++h) hstart[h + 1] = hstart[h] + nl*(1 << (S - h));
+  auto xnode = [&] (int b, int d, int p) { return x.nl + hstart[S - d] + b*(1 << d) + p; };
+  x.kid0.resize(x.ni);
+  x.kid1.resize(x.ni);
+  x.lvlptr.assign(1, 0);
+  for (int h = 1; h <= S; ++h) {
+    const int d = S - h;
+    for (int b = 0; b < nl; ++b)
+      for (int p = 0; p < (1 << d); ++p) {
+        const int me = xnode(b, d, p) - x.nl;
+        if (d == S - 1) { x.kid0[me] = b*E + 2*p; x.kid1[me] = b*E + 2*p + 1; }
+        else { x.kid0[me] = xnode(b, d + 1, 2*p); x.kid1[me] = xnode(b, d + 1, 2*p + 1); }
+      }
+    x.lvlptr.push_back(hstart[h + 1]);
+  }
+  // The tier-1 block's own internal nodes, with its leaves replaced by the block roots.
+  auto map1 = [&] (int id) { return id < nl ? xnode(id, 0, 0) : x.nl + nx + (id - nl); };
+  for (int j = 0; j < s1.ni; ++j) {
+    x.kid0[nx + j] = map1(s1.kid0[j]);
+    x.kid1[nx + j] = map1(s1.kid1[j]);
+  }
+  for (int l = 1; l <= s1.nlev; ++l) x.lvlptr.push_back(nx + s1.lvlptr[l]);
+  if (s1.ni == 0) {
+    // One tier-0 block: its depth-0 expansion node is the root (nothing to append).
+  }
+  x.dev_lvlptr_off = static_cast<int>(c.plan.dev_lvlptr.size());
+  x.dev_kid_off = static_cast<int>(c.plan.dev_kid0.size());
+  c.plan.dev_lvlptr.insert(c.plan.dev_lvlptr.end(), x.lvlptr.begin(), x.lvlptr.end());
+  c.plan.dev_kid0.insert(c.plan.dev_kid0.end(), x.kid0.begin(), x.kid0.end());
+  c.plan.dev_kid1.insert(c.plan.dev_kid1.end(), x.kid1.begin(), x.kid1.end());
+  BlockDev bd;
+  std::memset(&bd, 0, sizeof(bd));
+  bd.leaf0 = 0;
+  bd.nl = x.nl;
+  bd.ni = x.ni;
+  bd.nlev = x.nlev;
+  bd.lvlptr_off = x.dev_lvlptr_off;
+  bd.kid_off = x.dev_kid_off;
+  bd.ibase = 0;
+  bd.ftab_off = -1;
+  bd.gidx = 0;
+  c.d_xblock.upload(std::vector<BlockDev>(1, bd));
+  c.split = S;
+  c.x_nl = x.nl;
+  c.x_ni = x.ni;
+  c.x_ld = round_up(x.nl, 16);
+  const size_t nt = std::max<size_t>(1, c.trcr_prob.size());
+  c.d_xnc.alloc(x.ni);
+  c.d_xrhom.alloc(c.x_ld);
+  c.d_xrec.alloc(4*nt*c.x_ld);
+  c.d_xsol.alloc(nt*c.x_ld);
 }
 
 void launch_up (cedr_b200_cdr& c, int cls, int k) {
@@ -524,8 +676,10 @@ void launch_down (cedr_b200_cdr& c, int cls, int k) {
   else launch_sweep_any(c, cls, k, MODE_DOWN, base_args(c, cls, k));
 }
 
+// Doubles per rank in the exchange message: per owned block its index, its root's rhom
+// and the 4 nt record words. (Multi-rank runs exchange block roots: split == 0.)
 size_t exchange_count (const cedr_b200_cdr& c) {
-  return static_cast<size_t>(c.nown_max)*(4*c.trcr_prob.size() + 2);
+  return static_cast<size_t>(c.nown_max)*(1 + (4*c.trcr_prob.size() + 1));
 }
 
 int grid_for (long long n) {
@@ -536,9 +690,11 @@ int grid_for (long long n) {
 // This rank's tier-0 block roots -> the exchange message.
 void exchange_pack (cedr_b200_cdr& c, bool with_rhom) {
   LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 0);
+  const int E = 1 << c.split;
   pack_kernel<<<grid_for(exchange_count(c)), kThreads, 0, c.stream>>>(
-    c.d_blocks[0].p, nblocks_dev(c, 0), c.nown_max, static_cast<int>(c.trcr_prob.size()),
-    with_rhom ? c.d_rhom_tier[1].p : nullptr, c.d_rec[1].p, c.tier_ld[1], c.xsend);
+    c.d_blocks[0].p, nblocks_dev(c, 0), c.nown_max, static_cast<int>(c.trcr_prob.size()), E,
+    with_rhom ? (c.split ? c.d_xrhom.p : c.d_rhom_tier[1].p) : nullptr,
+    c.split ? c.d_xrec.p : c.d_rec[1].p, c.split ? c.x_ld : c.tier_ld[1], c.xsend);
   CUDA_CHECK(cudaGetLastError());
   ++c.last_launches;
 }
@@ -546,9 +702,12 @@ void exchange_pack (cedr_b200_cdr& c, bool with_rhom) {
 // Every rank's message -> the (replicated) tier-1 leaves.
 void exchange_unpack (cedr_b200_cdr& c, bool with_rhom) {
   LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 1);
+  const int E = 1 << c.split;
   unpack_kernel<<<grid_for(exchange_count(c)*c.nranks), kThreads, 0, c.stream>>>(
-    c.xrecv, c.nranks, c.nown_max, static_cast<int>(c.trcr_prob.size()),
-    with_rhom ? c.d_rhom_tier[1].p : nullptr, c.d_rec[1].p, c.tier_ld[1]);
+    c.xrecv, c.nranks, c.nown_max, static_cast<int>(c.trcr_prob.size()), E,
+    with_rhom ? (c.split ? c.d_xrhom.p : c.d_rhom_tier[1].p) : nullptr,
+    c.split ? c.d_xrec.p : c.d_rec[1].p, c.split ? c.x_ld : c.tier_ld[1],
+    static_cast<long long>(exchange_count(c)));
   CUDA_CHECK(cudaGetLastError());
   ++c.last_launches;
 }
@@ -566,8 +725,14 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
   const int ntiers = static_cast<int>(c.plan.tiers.size());
   const int top = ntiers - 1;
   const bool multi = c.nranks > 1;
+  // Classes on the fast kernels hand their blocks' sub-roots to the expanded tier.
+  auto via_x = [&] (int cls) {
+    return c.split && c.fast_ok && fast_class(cls, MODE_DOWN) &&
+      ! (c.fused_ok && fused_class(cls));
+  };
   if (phase <= 0) {
     run_rhom(c, 0, multi ? 1 : ntiers);
+    if ( ! multi) run_rhom_x(c);
     if (multi) {
       for (int cls = 0; cls < CLS_CAAS; ++cls)
         if ( ! c.cls_tracers[cls].empty()) launch_up(c, cls, 0);
@@ -578,11 +743,17 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
   if (phase != 0) {
     if (multi) {
       exchange_unpack(c, true);
-      run_rhom(c, 1, ntiers);
+      if (c.split) run_rhom_x(c); else run_rhom(c, 1, ntiers);
     }
     for (int cls = 0; cls < CLS_CAAS; ++cls) {
       if (c.cls_tracers[cls].empty()) continue;
       if (c.fused_ok && fused_class(cls)) { launch_fused(c, cls); continue; }
+      if (via_x(cls)) {
+        if ( ! multi) launch_up(c, cls, 0);
+        launch_top_x(c, cls);
+        launch_down(c, cls, 0);
+        continue;
+      }
       for (int k = multi ? 1 : 0; k < top; ++k) launch_up(c, cls, k);
       launch_sweep_any(c, cls, top, MODE_TOP, base_args(c, cls, top));
       for (int k = top - 1; k >= 0; --k) launch_down(c, cls, k);
@@ -694,6 +865,11 @@ void finish_setup (cedr_b200_cdr& c) {
   c.d_trcr_row.upload(c.trcr_row);
   c.d_trcr_prob.upload(c.trcr_prob);
   for (int k = 0; k < NCLS; ++k) c.d_cls_tracers[k].upload(c.cls_tracers[k]);
+  c.fast_ok = c.fast_enabled && c.plan.tier0_fast &&
+    reinterpret_cast<uintptr_t>(c.in) % 16 == 0 &&
+    (c.is_caas || reinterpret_cast<uintptr_t>(c.out) % 16 == 0) &&
+    ! std::getenv("CEDR_B200_NO_FAST");
+  build_split(c);
   c.d_lvlptr.upload(c.plan.dev_lvlptr);
   c.d_kid0.upload(c.plan.dev_kid0);
   c.d_kid1.upload(c.plan.dev_kid1);
@@ -740,10 +916,6 @@ void finish_setup (cedr_b200_cdr& c) {
   c.d_dtab.upload(c.plan.dev_dtab);
   c.d_ptab.upload(c.plan.dev_ptab);
   c.d_fpos.upload(c.plan.dev_fpos);
-  c.fast_ok = c.fast_enabled && c.plan.tier0_fast &&
-    reinterpret_cast<uintptr_t>(c.in) % 16 == 0 &&
-    (c.is_caas || reinterpret_cast<uintptr_t>(c.out) % 16 == 0) &&
-    ! std::getenv("CEDR_B200_NO_FAST");
   if (c.fast_ok) {
     c.d_fwq.alloc(std::max(1, c.plan.ninternal));
     c.d_frh.alloc(std::max(1, c.plan.ninternal));

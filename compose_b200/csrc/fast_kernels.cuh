@@ -113,6 +113,12 @@ struct FastArgs {
   // down2_kernel's top warp: [(t nblocks + block)*384 + f*128 + depth-7 node].
   double* n7buf;
   const double* rq;             // per block, fast order: RN(1/(q0 + q1)) or 0 (node_solve.cuh)
+  // split = S > 0: the block's depth-S nodes (2^S "sub-roots"), not its root, are the
+  // leaves of the tier above: rec_out / sol_in hold 2^S entries per block, at
+  // [.. + gidx 2^S + j], and depths 0..S-1 of the block are swept by the tier above. This
+  // takes the narrowest levels of the dependent chain out of the block kernels. S is 0, 2
+  // or 3.
+  int split;
 };
 
 #ifdef CEDR_B200_PHASE_CLOCKS
@@ -263,6 +269,27 @@ up_kernel (const FastArgs a) {
         else if (R::consistent_only && f == 2) r[f] = dev::rmax(r[f], o);
         else r[f] = r[f] + o;
       }
+      // After level L the lanes with lane % 2^(L+1) == 0 hold depth 6-L nodes; depth 3
+      // after L = 3 (two per warp), depth 2 after L = 4 (one per warp).
+      if (a.split && L == 6 - a.split && (lane & ((2 << L) - 1)) == 0) {
+        const int E = 1 << a.split;
+        const int j = (warp << (a.split - 2)) + (lane >> (L + 1));
+        double* rec = a.rec_out + static_cast<long long>(t)*4*a.rec_ld +
+          static_cast<long long>(B.gidx)*E + j;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          if ((f == 0 || f == 2) && ! bounds) continue;
+          if (f == 3 && ! prev) continue;
+          rec[f*a.rec_ld] = r[f];
+        }
+      }
+    }
+    if (a.split) {
+      // The shuffle tree above was also run past the sub-root depth; lanes that held a
+      // sub-root at its level saved it (see `sub` below).
+      __syncthreads();   // all threads are past their reads of this stage
+      if (tid == 0 && i + 2 < gn) issue(i + 2);
+      continue;
     }
     double* const wr = wroot + (i & 1)*16;
     if (lane == 0) {
@@ -573,8 +600,11 @@ down2_kernel (const FastArgs a) {
       double* const u = un + (i & 1)*384;
       double* const x = xs + (i & 1)*256;
       // The block root's mass, from the tier above (issued before the waits).
+      const int S = a.split, E = 1 << S;
       double xroot = 0;
-      if (lane == 0) xroot = __ldcg(a.sol_in + static_cast<long long>(t)*a.sol_in_ld + B.gidx);
+      if (lane < E)
+        xroot = __ldcg(a.sol_in + static_cast<long long>(t)*a.sol_in_ld +
+                       static_cast<long long>(B.gidx)*E + lane);
       CEDR_PHASE(0);
       mbar_wait(&mbar[2 + (i & 1)], (i >> 1) & 1);
       if (i >= 2) bar_sync<BAR_C, kDown2Threads>(i & 1);   // C(i-2) is done with x, u
@@ -592,15 +622,16 @@ down2_kernel (const FastArgs a) {
         u[f*128 + 31 + lane] = r;
 #pragma unroll
         for (int Lv = 0; Lv < 5; ++Lv) {
+          if (Lv > 4 - S) break;     // depths above the sub-roots belong to the tier above
           r = r + __shfl_down_sync(0xffffffffu, r, 1 << Lv);
           if ((lane & ((2 << Lv) - 1)) == 0) u[f*128 + (16 >> Lv) - 1 + (lane >> (Lv + 1))] = r;
         }
       }
-      if (lane == 0) x[0] = xroot;
+      if (lane < E) x[E - 1 + lane] = xroot;
       __syncwarp();
       CEDR_PHASE(2);
-      // Node problems of depths 0..6 (the kids of depth 6 are the depth-7 sums).
-      for (int dd = 0; dd <= 6; ++dd) {
+      // Node problems of depths S..6 (the kids of depth 6 are the depth-7 sums).
+      for (int dd = S; dd <= 6; ++dd) {
         for (int p = lane; p < (1 << dd); p += 32) {
           const int h = (1 << dd) - 1 + p;
           const double nd[3] = {u[h], u[128 + h], u[256 + h]};

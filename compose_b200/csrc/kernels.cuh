@@ -270,6 +270,10 @@ struct RhomArgs {
   FastWQ* fwq;
   FastRh* frh;
   double* frq;                 // RN(1/(q0 + q1)) or 0, see node_solve.cuh div_by_qmass
+  // rhom of the block's 2^split depth-`split` nodes, [gidx 2^split + j] (fast shapes; may
+  // be null): the leaf rhom of the expanded tier above (FastArgs::split).
+  double* sub_out;
+  int split;
 };
 
 __global__ void __launch_bounds__(256)
@@ -305,6 +309,10 @@ rhom_kernel (const RhomArgs a) {
         r.rh0 = rh0; r.rh1 = rh1;
         a.frh[pos] = r;
         a.frq[pos] = dev::reciprocal_for_div(c.q0 + c.q1);
+        // Fast positions of depths < 9 are heap indices: depth d holds [2^d - 1, 2^(d+1) - 1).
+        const int E = 1 << a.split, hp = a.fpos[B.fpos_off + j];
+        if (a.sub_out && a.split && hp >= E - 1 && hp < 2*E - 1)
+          a.sub_out[static_cast<long long>(B.gidx)*E + hp - (E - 1)] = rh0 + rh1;
       }
     }
     __syncthreads();
@@ -319,16 +327,22 @@ rhom_kernel (const RhomArgs a) {
 // every rank scatters all entries into its (replicated) tier-1 leaf arrays.
 __global__ void __launch_bounds__(256)
 pack_kernel (const BlockDev* blocks, const int nown, const int nown_max, const int nt,
-             const double* rhom1, const double* rec, const long long rec_ld, double* send) {
-  const long long stride = 4LL*nt + 2, n = stride*nown_max;
+             const int E, const double* rhom1, const double* rec, const long long rec_ld,
+             double* send) {
+  // Entry of a block: [gidx | E x (rhom, 4 nt record words)], word index w = 1 + e*(4nt+1) + i.
+  const long long per = 4LL*nt + 1, stride = 1 + E*per, n = stride*nown_max;
   for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
        k += (long long) gridDim.x*blockDim.x) {
     const int j = (int) (k / stride);
     const long long w = k % stride;
     double v = w == 0 ? -1.0 : 0.0;
     if (j < nown) {
-      const int g = blocks[j].gidx;
-      v = w == 0 ? (double) g : w == 1 ? (rhom1 ? rhom1[g] : 0.0) : rec[(w - 2)*rec_ld + g];
+      const long long g = blocks[j].gidx;
+      if (w == 0) v = (double) g;
+      else {
+        const long long e = (w - 1)/per, i = (w - 1) % per, leaf = g*E + e;
+        v = i == 0 ? (rhom1 ? rhom1[leaf] : 0.0) : rec[(i - 1)*rec_ld + leaf];
+      }
     }
     send[k] = v;
   }
@@ -336,15 +350,20 @@ pack_kernel (const BlockDev* blocks, const int nown, const int nown_max, const i
 
 __global__ void __launch_bounds__(256)
 unpack_kernel (const double* recv, const int nranks, const int nown_max, const int nt,
-               double* rhom1, double* rec, const long long rec_ld) {
-  const long long stride = 4LL*nt + 2, n = stride*nown_max*nranks;
+               const int E, double* rhom1, double* rec, const long long rec_ld,
+               const long long rank_stride) {
+  const long long per = 4LL*nt + 1, stride = 1 + E*per, nper = stride*nown_max;
+  const long long n = nper*nranks;
   for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
        k += (long long) gridDim.x*blockDim.x) {
-    const long long e = k / stride, w = k % stride;
-    const int g = (int) recv[e*stride];
+    const long long r = k / nper, kk = k % nper;
+    const double* const msg = recv + r*rank_stride;
+    const long long ent = kk / stride, w = kk % stride;
+    const long long g = (long long) msg[ent*stride];
     if (g < 0 || w == 0) continue;
-    if (w == 1) { if (rhom1) rhom1[g] = recv[k]; }
-    else rec[(w - 2)*rec_ld + g] = recv[k];
+    const long long e = (w - 1)/per, i = (w - 1) % per, leaf = g*E + e;
+    if (i == 0) { if (rhom1) rhom1[leaf] = msg[kk]; }
+    else rec[(i - 1)*rec_ld + leaf] = msg[kk];
   }
 }
 
