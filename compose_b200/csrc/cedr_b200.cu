@@ -410,7 +410,8 @@ void launch_fast_down (cedr_b200_cdr& c, int cls) {
       launch_fast(c, fast::down_kernel<CLS_CST>, a, smem, CEDR_B200_TAG_DOWN);
     return;
   }
-  const size_t smem = fast::down2_smem_bytes(a.sbuf);
+  size_t smem = fast::down2_smem_bytes(a.sbuf);
+  if (const char* e = std::getenv("CEDR_B200_SMEM_PAD")) smem += std::atoi(e);  // occupancy experiments
   if (cls == CLS_ST)
     launch_fast(c, fast::down2_kernel<CLS_ST>, a, smem, CEDR_B200_TAG_DOWN,
                 fast::kDown2Threads);

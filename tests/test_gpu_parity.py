@@ -374,3 +374,49 @@ def test_partition_must_be_whole_blocks():
     q.declare_tracer(7)
     with pytest.raises(cb.CedrError, match="whole blocks"):
         q.end_tracer_declarations()
+
+
+# ------------------------------------------------------------------ config 5 (1-D transport)
+
+def test_transport1d_every_step_bitwise(oracle):
+    """BASELINE.json config 5: the advection loop of cedr_test_1d_transport.cpp calling
+    CDR::run every step (many tiny runs), for qltnn / qlt / caas. Each step's CUDA result
+    must equal the oracle's bit for bit, so the two 351-step trajectories never part."""
+    import torch
+    import compose_b200 as cb
+    import transport1d as T
+    from test_oracle_golden import t1d_runners
+    ncells = 111
+    p, oruns = t1d_runners(oracle, ncells, caas_tree=True)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a[None])).cuda()
+
+    def gpu_runner(kind, pt):
+        c = cb.QLT(ncells) if kind == "qlt" else cb.CAAS(ncells)
+        c.declare_tracer(pt)
+        c.end_tracer_declarations()
+        c.finish_setup()
+        g = c.get_owned_glblcells() if kind == "qlt" else np.arange(ncells)
+        c.set_rhom(torch.from_numpy(np.ascontiguousarray(p.area[g])).cuda())
+
+        def run(q, lo, hi, prev):
+            c.set_Qm(dev(q[g]), dev(lo[g]), dev(hi[g]), dev(prev[g]))
+            c.run()
+            out = np.empty(ncells)
+            out[g] = c.get_Qm().cpu().numpy()[0]
+            return out
+        return run
+
+    gruns = {"yqltnn": gpu_runner("qlt", 1 | 8), "yqlt": gpu_runner("qlt", 1 | 2),
+             "ycaas": gpu_runner("caas", 3)}
+    nsteps = int(3.17*ncells)
+    y0 = p.y0()
+    for name in ("yqltnn", "yqlt", "ycaas"):
+        def both(q, lo, hi, prev, name=name):
+            a = gruns[name](q, lo, hi, prev)
+            b = oruns[name](q, lo, hi, prev)
+            assert np.array_equal(a, b), name
+            return a
+        yf = p.cycle(nsteps, y0, both)
+        # mass is conserved over the whole run to rounding
+        m0, m1 = (y0[:ncells]*p.area).sum(), (yf[:ncells]*p.area).sum()
+        assert abs(m1 - m0) <= 1e-12*abs(m0)
