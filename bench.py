@@ -275,15 +275,40 @@ def main():
         for c in (qlt, caas):
             c.set_profiling(False)
 
-    # ---- roofline of the dominant reconstructor pass (QLT run())
+    # ---- roofline of the dominant reconstructor pass (QLT run()): algorithmic bytes
+    # (40 B x the updates one run() processes on this GPU) over the CUDA-event duration
+    # of the run's launches; traffic = DRAM bytes of the same launches from the committed
+    # ncu capture (profiles/r01_traffic.json, bytes per update x updates).
     peak, peak_src = measured_peaks()
-    ach = BYTES_PER_UPDATE*(updates/world)/(ms_qlt*1e-3)/1e9
+    upd_gpu = updates/world
+    ach = BYTES_PER_UPDATE*upd_gpu/(ms_qlt*1e-3)/1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    bpu = json.load(open(tpath))["bytes_per_update"] if os.path.exists(tpath) else None
+    per_kernel = {}
+    if kernels:
+        # Each kernel against the bytes it must move itself: up reads 4 rows (32 B), down
+        # reads 3 rows and writes 1 (32 B), caas_adjust likewise.
+        for kind in ("qlt", "caas"):
+            for name, tier, ms in kernels[kind]:
+                if tier == 0 and name in ("up", "down", "caas_adjust", "fused") and ms > 0:
+                    b = 40.0 if name == "fused" else 32.0
+                    g = b*upd_gpu/(ms*1e-3)/1e9
+                    per_kernel["%s.%s" % (kind, name)] = {
+                        "ms": ms, "bytes_per_update": b, "achieved": g, "frac": g/peak}
+    if bpu:
+        traffic = bpu["qlt"]["run_total"]*upd_gpu
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach/peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "QLT::run() = rhom + up + top + down sweeps (per GPU)",
+                "frac": ach/peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel": "QLT::run(): fast::up_kernel + tier-1 sweep + fast::down2_kernel "
+                          "(dominant: down2_kernel); per GPU",
                 "algorithmic_bytes_per_update": BYTES_PER_UPDATE,
-                "caas": {"achieved": BYTES_PER_UPDATE*(updates/world)/(ms_caas*1e-3)/1e9,
-                         "frac": BYTES_PER_UPDATE*(updates/world)/(ms_caas*1e-3)/1e9/peak}}
+                "algorithmic_bytes": BYTES_PER_UPDATE*upd_gpu,
+                "traffic_bytes_per_update": bpu["qlt"]["run_total"] if bpu else None,
+                "kernels": per_kernel,
+                "caas": {"achieved": BYTES_PER_UPDATE*upd_gpu/(ms_caas*1e-3)/1e9,
+                         "frac": BYTES_PER_UPDATE*upd_gpu/(ms_caas*1e-3)/1e9/peak,
+                         "traffic": bpu["caas"]["run_total"]*upd_gpu if bpu else None}}
 
     # ---- end to end through the public API with HOST buffers
     e2e = None
