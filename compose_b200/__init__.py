@@ -48,6 +48,9 @@ SYMBOLS = [
                                           C.c_int]),
     ("cedr_b200_caas_create", C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.c_int64,
                                         C.c_int64, C.c_int, C.c_int]),
+    ("cedr_b200_bfb_create", C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.c_int, _ip, _lp,
+                                       _ip, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("cedr_b200_bfb_allreduce", C.c_int, [_H, _vp, _vp, C.c_int, C.c_int]),
     ("cedr_b200_destroy", C.c_int, [_H]),
     ("cedr_b200_declare_tracer", C.c_int, [_H, C.c_int, C.c_int]),
     ("cedr_b200_end_tracer_declarations", C.c_int, [_H]),
@@ -384,6 +387,37 @@ class QLT(CDR):
                 kids.ctypes.data_as(_ip), cellidx.ctypes.data_as(_lp),
                 None if nr is None else nr.ctypes.data_as(_ip), prefer, int(rank),
                 int(nranks)))
+
+
+class BfbTreeAllReducer(CDR):
+    """cedr::BfbTreeAllReducer (cedr_bfb_tree_allreduce.hpp:15-55), device-resident."""
+
+    def __init__(self, nleaf, nfield, tree=None, max_block_leaves=0, rank=0, nranks=1,
+                 node_rank=None):
+        super().__init__()
+        import numpy as np
+        self.nfield = nfield
+        if tree is None:
+            args = (0, 0, None, None, None)
+        else:
+            kids, cellidx, root = tree
+            kids = _as_i32(kids).reshape(-1)
+            cellidx = np.ascontiguousarray(cellidx, dtype=np.int64)
+            nr = None if node_rank is None else _as_i32(node_rank)
+            self._keep = (kids, cellidx, nr)
+            args = (int(cellidx.size), int(root), kids.ctypes.data_as(_ip),
+                    cellidx.ctypes.data_as(_lp), None if nr is None else nr.ctypes.data_as(_ip))
+        _check(self._lib.cedr_b200_bfb_create(C.byref(self._h), int(nleaf), *args, int(nfield),
+                                              int(max_block_leaves), int(rank), int(nranks)))
+        self.use_current_stream()
+
+    def allreduce(self, send, recv=None, transpose=False, phase=-1):
+        import torch
+        if recv is None:
+            recv = torch.empty(self.nfield, dtype=torch.float64, device="cuda")
+        _check(self._lib.cedr_b200_bfb_allreduce(self._h, _ptr(send), _ptr(recv),
+                                                 int(bool(transpose)), int(phase)))
+        return recv
 
 
 class CAAS(CDR):

@@ -114,6 +114,7 @@ const int kThreads = 256;
 
 struct cedr_b200_cdr {
   bool is_caas = false;
+  bool is_bfb = false;          // a BfbTreeAllReducer: "tracers" are the fields
   int rank = 0, nranks = 1;
   bool prefer_mass_con = false;
   int caas_sum_mode = CEDR_B200_CAAS_SUM_TREE;
@@ -272,6 +273,10 @@ void launch_sweep_any (cedr_b200_cdr& c, int cls, int tier, int mode, const Swee
   case CLS_CAAS:
     if (mode == MODE_UP) launch_sweep<CLS_CAAS, MODE_UP>(c, tier, a);
     else launch_sweep<CLS_CAAS, MODE_TOP>(c, tier, a);
+    break;
+  case CLS_BFB:
+    if (mode == MODE_UP) launch_sweep<CLS_BFB, MODE_UP>(c, tier, a);
+    else launch_sweep<CLS_BFB, MODE_TOP>(c, tier, a);
     break;
   }
 }
@@ -443,6 +448,7 @@ void fused_setup (cedr_b200_cdr& c) {
   c.fused_ok = false;
   if ( ! c.fused_enabled || ! c.fast_ok || std::getenv("CEDR_B200_NO_FUSED")) return;
   if (c.nranks > 1) return;
+  if (c.is_caas && c.caas_sum_mode != CEDR_B200_CAAS_SUM_TREE) return;
   if (c.plan.tiers.size() != 2 || c.plan.tiers[1].blocks.size() != 1) return;
   const int sbuf = fused_sbuf(c);
   const size_t nl1 = c.plan.tiers[1].nleaves;
@@ -764,9 +770,28 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
 
 // CAAS::run, cedr_caas.cpp:258-270; phases as for run_qlt.
 void run_caas (cedr_b200_cdr& c, int phase) {
-  cedr_b200_throw_if(c.caas_sum_mode != CEDR_B200_CAAS_SUM_TREE,
-                     "CAAS sequential-order sums are not implemented yet");
   const bool multi = c.nranks > 1;
+  if (c.caas_sum_mode == CEDR_B200_CAAS_SUM_SEQUENTIAL) {
+    cedr_b200_throw_if(multi, "CEDR_B200_CAAS_SUM_SEQUENTIAL is a one-rank mode (the order of "
+                       "an MPI_Allreduce is unspecified, cedr_caas.cpp:203-209)");
+    if (phase == 1) return;
+    const int nt = static_cast<int>(c.trcr_prob.size());
+    {
+      LaunchTimer lt(c, CEDR_B200_TAG_UP, 0);
+      caas_seq_sums_kernel<<<(nt + 127)/128, 128, 0, c.stream>>>(
+        c.in, c.ld, c.nlcl, c.d_trcr_row.p, c.d_trcr_prob.p, nt, c.d_caas_scal.p);
+      CUDA_CHECK(cudaGetLastError());
+      ++c.last_launches;
+    }
+    const long long n = static_cast<long long>(c.nlcl)*nt;
+    LaunchTimer lt(c, CEDR_B200_TAG_CAAS_ADJUST, 0);
+    caas_adjust_kernel<<<grid_for(n), kThreads, 0, c.stream>>>(c.in, c.ld, c.nlcl,
+                                                             c.d_trcr_row.p,
+                                                             c.d_caas_scal.p, nt);
+    CUDA_CHECK(cudaGetLastError());
+    ++c.last_launches;
+    return;
+  }
   if (c.fused_ok) { launch_fused(c, CLS_CAAS); return; }
   const int ntiers = static_cast<int>(c.plan.tiers.size());
   const int top = ntiers - 1;
@@ -837,8 +862,27 @@ void build_plan (cedr_b200_cdr& c) {
   }
 }
 
+// BfbTreeAllReducer::allreduce after the leaf fill: tree-ordered sums of every field up
+// to the root (one all-gather of block roots when nranks > 1); results in d_qglob[field].
+void run_bfb (cedr_b200_cdr& c, int phase) {
+  const bool multi = c.nranks > 1;
+  const int ntiers = static_cast<int>(c.plan.tiers.size());
+  const int top = ntiers - 1;
+  if (phase <= 0 && multi) {
+    launch_up(c, CLS_BFB, 0);
+    exchange_pack(c, false);
+  }
+  if (multi && phase < 0) exchange_allgather(c);
+  if (phase == 0) return;
+  if (multi) exchange_unpack(c, false);
+  for (int k = multi ? 1 : 0; k < top; ++k) launch_up(c, CLS_BFB, k);
+  launch_sweep_any(c, CLS_BFB, top, MODE_TOP, base_args(c, CLS_BFB, top));
+}
+
 void run_any (cedr_b200_cdr& c, int phase) {
-  if (c.is_caas) run_caas(c, phase); else run_qlt(c, phase);
+  if (c.is_bfb) run_bfb(c, phase);
+  else if (c.is_caas) run_caas(c, phase);
+  else run_qlt(c, phase);
 }
 
 void get_buffers_sizes (cedr_b200_cdr& c, size_t& b1, size_t& b2) {
@@ -1043,6 +1087,79 @@ int cedr_b200_caas_create (cedr_b200_cdr** out, int nlclcells, int sum_mode,
   });
 }
 
+// ---- BfbTreeAllReducer (cedr_bfb_tree_allreduce.hpp:15-55)
+
+namespace {
+void bfb_finish (cedr_b200_cdr& c, int nfield) {
+  cedr_b200_throw_if(nfield < 1, "nfield must be >= 1");
+  c.is_bfb = true;
+  c.fast_enabled = false;      // the generic sweeps carry the one-word records
+  c.fused_enabled = false;
+  for (int j = 0; j < nfield; ++j) {
+    c.trcr_prob.push_back(0);
+    c.trcr_cls.push_back(CLS_BFB);
+    c.trcr_row.push_back(j);
+    c.cls_tracers[CLS_BFB].push_back(j);
+  }
+  c.nrows = nfield;
+  c.ld = round_up(std::max(1, c.nlcl), 16);
+  c.declaring = false;
+  cedr_b200_throw_if( ! c.partition_error.empty(), c.partition_error);
+  cedr_b200_throw_if(c.nranks > 1 && c.plan.tiers.size() < 2,
+                     "with nranks > 1 the tree plan needs >= 2 tiers");
+}
+}
+
+int cedr_b200_bfb_create (cedr_b200_cdr** out, int nleaf, int nnodes, int root,
+                          const int* kids, const int64_t* cellidx, const int* node_rank,
+                          int nfield, int max_block_leaves, int rank, int nranks) {
+  return guarded([&] {
+    cedr_b200_throw_if( ! out, "null output pointer");
+    require_device();
+    std::unique_ptr<cedr_b200_cdr> c(new cedr_b200_cdr);
+    c->rank = rank;
+    c->nranks = nranks;
+    c->ncells = nleaf;
+    if (max_block_leaves > 0) c->max_block_leaves = max_block_leaves;
+    if (kids) {
+      cedr_b200_throw_if(nnodes < 1 || ! cellidx, "bad tree arrays");
+      c->tree_kids.assign(kids, kids + 2*static_cast<size_t>(nnodes));
+      c->tree_cellidx.assign(cellidx, cellidx + nnodes);
+      if (node_rank) c->tree_rank.assign(node_rank, node_rank + nnodes);
+      c->tree_root = root;
+    } else {
+      fill_1d_tree(*c, nleaf, false);
+    }
+    build_plan(*c);
+    cedr_b200_throw_if(c->nlcl == 0, "BfbTreeAllReducer: this rank owns no leaf");
+    bfb_finish(*c, nfield);
+    finish_setup(*c);
+    *out = c.release();
+  });
+}
+
+int cedr_b200_bfb_allreduce (cedr_b200_cdr* c, const double* send, double* recv,
+                             int transpose, int phase) {
+  return guarded([&] {
+    cedr_b200_throw_if( ! c->is_bfb, "not a BfbTreeAllReducer");
+    cedr_b200_throw_if(phase < -1 || phase > 1, "phase must be -1 (all), 0 or 1");
+    const int nf = static_cast<int>(c->trcr_prob.size());
+    if (phase <= 0) {
+      c->last_launches = 0;
+      c->ntimed = 0;
+      bfb_fill_kernel<<<grid_for(static_cast<long long>(c->nlcl)*nf), kThreads, 0,
+                        c->stream>>>(c->in, c->ld, c->nlcl, nf, transpose, send);
+      CUDA_CHECK(cudaGetLastError());
+      ++c->last_launches;
+    }
+    if (c->nranks == 1) { if (phase <= 0) run_bfb(*c, -1); }
+    else run_bfb(*c, phase);
+    if (phase != 0)
+      CUDA_CHECK(cudaMemcpyAsync(recv, c->d_qglob.p, sizeof(double)*nf,
+                                 cudaMemcpyDeviceToDevice, c->stream));
+  });
+}
+
 int cedr_b200_destroy (cedr_b200_cdr* c) {
   return guarded([&] { delete c; });
 }
@@ -1160,7 +1277,6 @@ int cedr_b200_get_exchange_count (const cedr_b200_cdr* c, size_t* count) {
 
 int cedr_b200_set_exchange_buffers (cedr_b200_cdr* c, double* send, double* recv) {
   return guarded([&] {
-    cedr_b200_throw_if(c->finished, "set_exchange_buffers must precede finish_setup");
     c->xsend = send;
     c->xrecv = recv;
   });

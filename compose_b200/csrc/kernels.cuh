@@ -39,7 +39,10 @@ typedef dev::NodeRh FastRh;
 // Tracer classes: the six canonical QLT problem classes in the reference's
 // order (cedr_qlt_inl.hpp:101-108), plus CAAS.
 enum { CLS_ST = 0, CLS_CST = 1, CLS_T = 2, CLS_CT = 3, CLS_NN = 4, CLS_CNN = 5,
-       CLS_CAAS = 6, NCLS = 7 };
+       CLS_CAAS = 6,
+       // One scalar field of a BfbTreeAllReducer (cedr_bfb_tree_allreduce.cpp:78-159):
+       // leaves as given, every node d = 0; d += kid0; d += kid1.
+       CLS_BFB = 7, NCLS = 8 };
 enum { MODE_UP = 0, MODE_TOP = 1, MODE_DOWN = 2 };
 
 struct SweepArgs {
@@ -80,14 +83,15 @@ template <int CLS, int MODE>
 __device__ __forceinline__ void
 sweep_block (const SweepArgs& a, const int b, const int t, double* const sm) {
   constexpr bool caas = CLS == CLS_CAAS;
-  constexpr bool nonneg = CLS == CLS_NN || CLS == CLS_CNN;
+  constexpr bool bfb = CLS == CLS_BFB;
+  constexpr bool nonneg = CLS == CLS_NN || CLS == CLS_CNN || bfb;   // one word: row 0
   constexpr bool consistent_only = CLS == CLS_T || CLS == CLS_CT;
   constexpr bool has_prev = CLS == CLS_CST || CLS == CLS_CT || CLS == CLS_CNN || caas;
   // Which fields this mode needs in shared memory. The down-sweep of the
   // bounded classes needs (min, Qm, max); consistent-only and nonnegative
   // classes need only Qm (their bounds are global q * rhom, resp. [0, b]).
   constexpr bool need_bounds = ! nonneg && (MODE != MODE_DOWN || ! consistent_only);
-  constexpr bool need_prev = has_prev && MODE != MODE_DOWN;
+  constexpr bool need_prev = has_prev && MODE != MODE_DOWN && ! bfb;
 
   const BlockDev B = a.blocks[b];
   const int nn = B.nl + B.ni;
@@ -144,7 +148,9 @@ sweep_block (const SweepArgs& a, const int b, const int t, double* const sm) {
     const int je = lvlptr[l+1];
     for (int j = lvlptr[l] + tid; j < je; j += nth) {
       const int k0 = kid0[j], k1 = kid1[j], me = B.nl + j;
-      if (caas) {
+      if (bfb) {
+        f1[me] = (0.0 + f1[k0]) + f1[k1];
+      } else if (caas) {
         // BfbTreeAllReducer: d = 0; d += kid0; d += kid1
         // (cedr_bfb_tree_allreduce.cpp:115-124).
         f0[me] = (0.0 + f0[k0]) + f0[k1];
@@ -179,6 +185,11 @@ sweep_block (const SweepArgs& a, const int b, const int t, double* const sm) {
     return;
   }
 
+  if (bfb) {
+    // MODE_TOP: the reduced field is at the root.
+    if (tid == 0) a.qglob[t] = f1[root];
+    return;
+  }
   if (caas) {
     // MODE_TOP: the four global sums are at the root. CAAS::finish_locally,
     // cedr_caas.cpp:211-253, scalar part.
@@ -392,8 +403,57 @@ caas_adjust_kernel (double* data, const long long ld, const int ncells,
   }
 }
 
+// CAAS with the reference's own host summation order (CEDR_B200_CAAS_SUM_SEQUENTIAL):
+// reduce_locally on a host backend runs each tracer's cells i = 0..n-1 through one
+// accumulator per sum (team size 1, cedr_caas.cpp:171-199, cedr_kokkos.hpp:118), so the
+// four sums are ((0 + v0) + v1) + ... One thread per tracer walks its rows in that order
+// (a compatibility mode for one rank: bit parity with the reference's default CAAS, not
+// speed), then forms the redistribution scalars of finish_locally (cedr_caas.cpp:211-253).
+__global__ void __launch_bounds__(128)
+caas_seq_sums_kernel (const double* data, const long long ld, const int ncells,
+                      const int* trcr_row, const int* trcr_prob, const int nt, double* scal) {
+  const int t = blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  const double* row = data + (long long) trcr_row[t]*ld;
+  const bool conserve = trcr_prob[t] & 1;
+  double clip_sum = 0, term_sum = 0, min_sum = 0, max_sum = 0;
+  for (int i = 0; i < ncells; ++i) {
+    const double lo = row[i], q = row[ld + i], hi = row[2*ld + i];
+    const double term = conserve ? row[3*ld + i] : q;
+    clip_sum += dev::rmin(hi, dev::rmax(lo, q));
+    term_sum += term;
+    min_sum += lo;
+    max_sum += hi;
+  }
+  const double m = term_sum - clip_sum;
+  double mode = 0, fac = 0;
+  if (m < 0) {
+    fac = clip_sum - min_sum;
+    if (fac > 0) { fac = m/fac; mode = -1; }
+  } else if (m > 0) {
+    fac = max_sum - clip_sum;
+    if (fac > 0) { fac = m/fac; mode = 1; }
+  }
+  scal[2*t] = mode;
+  scal[2*t+1] = fac;
+}
+
 // Bulk DeviceOp::set_Qm (cedr_qlt_inl.hpp:21-58, cedr_caas_inl.hpp:21-34) from
 // SoA caller arrays a[t*lda + lci].
+// BfbTreeAllReducer leaf fill: send is (nfield fastest, nlocal) unless transpose, then
+// (nlocal fastest, nfield) (cedr_bfb_tree_allreduce.cpp:92-103); row j of `in` is field j.
+__global__ void __launch_bounds__(256)
+bfb_fill_kernel (double* in, const long long ld, const int nlocal, const int nfield,
+                 const int transpose, const double* send) {
+  const long long n = (long long) nlocal*nfield;
+  for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
+       k += (long long) gridDim.x*blockDim.x) {
+    const int j = (int) (k / nlocal), id = (int) (k % nlocal);
+    in[(long long) j*ld + id] = transpose ? send[(long long) nlocal*j + id]
+                                          : send[(long long) id*nfield + j];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 set_qm_bulk_kernel (double* in, const long long ld, const int ncells,
                     const int* trcr_row, const int* trcr_prob, const int t0,

@@ -46,7 +46,9 @@ enum {
    * independent of the GPU decomposition. Default. */
   CEDR_B200_CAAS_SUM_TREE = 0,
   /* Sequential over cells 0..n-1: what the reference's own reduce_locally
-   * computes on a host backend (team size 1, cedr_kokkos.hpp:118). One rank. */
+   * computes on a host backend (team size 1, cedr_kokkos.hpp:118). One rank; a
+   * compatibility mode (one thread per tracer), bit-identical to the reference's
+   * default CAAS. */
   CEDR_B200_CAAS_SUM_SEQUENTIAL = 1
 };
 
@@ -177,7 +179,7 @@ int cedr_b200_set_allgather(cedr_b200_cdr* cdr, cedr_b200_allgather_fn fn, void*
  * then sweeps the replicated tiers above in the fixed tree order, so results are
  * bit-identical to a one-rank run (the reference gets the same property from
  * cedr_bfb_tree_allreduce.cpp:115-124). get_exchange_count is valid after
- * end_tracer_declarations. set_exchange_buffers (before finish_setup) hands in caller
+ * end_tracer_declarations. set_exchange_buffers (before the first run) hands in caller
  * device buffers of `count` and `nranks*count` doubles, e.g. registered NCCL or
  * torch tensors; otherwise they are allocated internally. */
 int cedr_b200_get_exchange_count(const cedr_b200_cdr* cdr, size_t* count);
@@ -196,6 +198,29 @@ int cedr_b200_partition_probe(int ncells, int imbalanced, int max_block_leaves, 
                               int nranks, int cap, int* nlclcells, int* nown, int* nown_max,
                               int* nblocks_global, int* gidx_host, int* leaf0_host,
                               int* nl_host);
+
+/* ---- BfbTreeAllReducer, cedr_bfb_tree_allreduce.hpp:15-55 ----------------- */
+
+/* BfbTreeAllReducer<ES>(p, tree, nleaf, nfield): an all-reduce (sum) of `nfield` scalars
+ * per leaf whose result is bit-for-bit independent of the rank decomposition, because it
+ * adds in the order of the tree (every node: d = 0; d += kid0; d += kid1,
+ * cedr_bfb_tree_allreduce.cpp:115-124). Device-resident here (the reference stages
+ * through the host on GPUs, :55-76): the same block plan and sweep kernels as QLT's
+ * up-sweep, one all-gather of block roots when nranks > 1. The tree is given flattened as
+ * for cedr_b200_qlt_create; kids == NULL builds make_tree_over_1d_mesh(nleaf).
+ * max_block_leaves <= 0 keeps the default. The handle is destroyed with
+ * cedr_b200_destroy and takes cedr_b200_set_stream / set_allgather / exchange buffers
+ * (before the first allreduce) like a CDR. */
+int cedr_b200_bfb_create(cedr_b200_cdr** reducer, int nleaf, int nnodes, int root,
+                         const int* kids, const int64_t* cellidx, const int* node_rank,
+                         int nfield, int max_block_leaves, int rank, int nranks);
+/* BfbTreeAllReducer::allreduce(send, recv, transpose), :78-159. Device pointers; send is
+ * (nfield fastest, nlocal) or, if transpose, (nlocal fastest, nfield), leaves in local
+ * leaf order; recv gets nfield sums (send and recv may alias). Asynchronous on the
+ * handle's stream. phase = -1 does everything; 0 / 1 split at the exchange as
+ * cedr_b200_run_phase does. */
+int cedr_b200_bfb_allreduce(cedr_b200_cdr* reducer, const double* send, double* recv,
+                            int transpose, int phase);
 
 /* ---- introspection for tests / benches --------------------------------- */
 

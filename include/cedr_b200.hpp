@@ -343,8 +343,13 @@ public:
     return lci;
   }
 
-private:
   // Pre-order flattening of the caller's tree::Node graph; node 0 is the root.
+  static void flatten_tree (const tree::Node* root, std::vector<int>& kids,
+                            std::vector<int64_t>& cellidx, std::vector<int>& rank) {
+    flatten(root, kids, cellidx, rank);
+  }
+
+private:
   static void flatten (const tree::Node* root, std::vector<int>& kids,
                        std::vector<int64_t>& cellidx, std::vector<int>& rank) {
     if ( ! root) throw std::logic_error("cedr_b200: null tree");
@@ -407,6 +412,46 @@ public:
   }
 };
 } // namespace caas
+
+// cedr_bfb_tree_allreduce.hpp:15-55. Device-resident: send and recv are device pointers
+// (the reference takes Kokkos device views and stages through the host). The host-buffer
+// calls of the reference are accepted and ignored.
+template <typename ES = DefaultExecutionSpace>
+struct BfbTreeAllReducer {
+  typedef BfbTreeAllReducer<ES> Me;
+  typedef std::shared_ptr<Me> Ptr;
+
+  BfbTreeAllReducer (const mpi::Parallel::Ptr& p, const tree::Node::Ptr& tree, const Int nleaf,
+                     const Int nfield) : h_(nullptr), nfield_(nfield) {
+    std::vector<int> kids, rank;
+    std::vector<int64_t> cellidx;
+    qlt::QLT<ES>::flatten_tree(tree.get(), kids, cellidx, rank);
+    impl::check(cedr_b200_bfb_create(&h_, nleaf, static_cast<int>(cellidx.size()), 0,
+                                     kids.data(), cellidx.data(), rank.data(), nfield, 0,
+                                     p ? p->rank() : 0, p ? p->size() : 1));
+    if (p && p->size() > 1 && p->allgather())
+      impl::check(cedr_b200_set_allgather(h_, p->allgather(), p->allgather_ctx()));
+  }
+  BfbTreeAllReducer (const BfbTreeAllReducer&) = delete;
+  BfbTreeAllReducer& operator= (const BfbTreeAllReducer&) = delete;
+  ~BfbTreeAllReducer () { if (h_) cedr_b200_destroy(h_); }
+
+  void get_host_buffers_sizes (size_t& buf1, size_t& buf2) { buf1 = buf2 = 0; }
+  void set_host_buffers (Real*, Real*) {}
+  void finish_setup () {}
+  Int get_nfield () const { return nfield_; }
+
+  // recv(nfield); send(nfield, nlocal) with the fastest index first, or
+  // send(nlocal, nfield) if transpose (cedr_bfb_tree_allreduce.hpp:37-41). Synchronous.
+  void allreduce (const Real* send, Real* recv, const bool transpose = false) const {
+    impl::check(cedr_b200_bfb_allreduce(h_, send, recv, transpose, -1));
+    impl::check(cedr_b200_synchronize(h_));
+  }
+
+private:
+  cedr_b200_cdr* h_;
+  Int nfield_;
+};
 
 } // namespace cedr
 

@@ -191,6 +191,27 @@ int main () {
     }
   }
 
+  { // BfbTreeAllReducer: device sums in tree order == the oracle's, both layouts.
+    const int nleaf = 777, nf = 5;
+    std::vector<double> data((size_t) nleaf*nf), ref(nf), got(nf);
+    for (size_t i = 0; i < data.size(); ++i) data[i] = std::sin(0.37*i)*(1 + (i % 11));
+    const int nn = 2*nleaf - 1;
+    std::vector<int> kids(2*nn);
+    std::vector<int64_t> cellidx(nn);
+    oracle_make_bisection_tree(nleaf, 0, kids.data(), cellidx.data());
+    BfbTreeAllReducer<> red(par, tree::make_tree_over_1d_mesh(par, nleaf), nleaf, nf);
+    double* d = to_dev(data);
+    for (int transpose = 0; transpose < 2; ++transpose) {
+      REQUIRE(oracle_bfb_allreduce(nleaf, nn, 0, kids.data(), cellidx.data(), nf, transpose,
+                                   data.data(), ref.data()) == 0);
+      red.allreduce(d, d, transpose != 0);    // in place, like the reference allows
+      cudaMemcpy(got.data(), d, nf*sizeof(double), cudaMemcpyDeviceToHost);
+      REQUIRE(same_bits(got, ref));
+      cudaMemcpy(d, data.data(), data.size()*sizeof(double), cudaMemcpyHostToDevice);
+    }
+    cudaFree(d);
+  }
+
   { // Error behaviour: std::logic_error, message shaped like cedr_throw_if's.
     QLTT q(par, 8, tree::make_tree_over_1d_mesh(par, 8));
     q.declare_tracer(cst, 0);

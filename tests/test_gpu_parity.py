@@ -420,3 +420,84 @@ def test_transport1d_every_step_bitwise(oracle):
         # mass is conserved over the whole run to rounding
         m0, m1 = (y0[:ncells]*p.area).sum(), (yf[:ncells]*p.area).sum()
         assert abs(m1 - m0) <= 1e-12*abs(m0)
+
+
+@pytest.mark.parametrize("ncells", [1, 2, 11, 111, 1000, 5400])
+def test_caas_sequential_sums_bitwise(oracle, ncells):
+    """CEDR_B200_CAAS_SUM_SEQUENTIAL reproduces the reference's DEFAULT CAAS (host-order
+    sums, cedr_caas.cpp:171-199) bit for bit."""
+    import torch
+    import compose_b200 as cb
+    ts, v = R.generate(ncells, seed=900 + ncells)
+    sel = caas_tracers()
+    idx = [t.idx for t in sel]
+    pts = [t.problem_type for t in sel]
+    a = [x[idx] for x in (v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev)]
+    ref = oracle.caas(ncells, pts, *a)          # tree=None: sequential sums
+    c = cb.CAAS(ncells, sum_mode=cb.CAAS_SUM_SEQUENTIAL)
+    for p in pts:
+        c.declare_tracer(int(p))
+    c.end_tracer_declarations()
+    c.finish_setup()
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    c.set_rhom(dev(v.rhom))
+    c.set_Qm(dev(a[1]), dev(a[0]), dev(a[2]), dev(a[3]))
+    c.run()
+    c.synchronize()
+    assert np.array_equal(c.get_Qm().cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------- BfbTreeAllReducer (8f-2)
+
+@pytest.mark.parametrize("nleaf,nfield,mbl", [(1, 3, 0), (2, 1, 0), (17, 5, 0), (111, 4, 8),
+                                              (1000, 7, 32), (5400, 16, 0)])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_bfb_tree_allreduce_bitwise(oracle, nleaf, nfield, mbl, transpose):
+    """The device-resident BfbTreeAllReducer against the reference's (through the pinned
+    oracle, oracle_bfb_allreduce): same tree order, same bits; and within the reference's
+    own unit-test tolerance of a plain sum (cedr_bfb_tree_allreduce.cpp:211-217)."""
+    import torch
+    import compose_b200 as cb
+    rng = np.random.default_rng(nleaf + nfield)
+    data = rng.standard_normal((nleaf, nfield))*10.0**rng.integers(-3, 4, (nleaf, nfield))
+    send = np.ascontiguousarray(data.T if transpose else data).reshape(-1)
+    tree = oracle.bisection_tree(nleaf)
+    ref = oracle.bfb_allreduce(tree, send, nfield, transpose)
+    r = cb.BfbTreeAllReducer(nleaf, nfield, max_block_leaves=mbl)
+    got = r.allreduce(torch.from_numpy(send).cuda(), transpose=transpose)
+    r.synchronize()
+    got = got.cpu().numpy()
+    assert np.array_equal(got, ref)
+    tol = 2*np.log(max(nleaf, 2))*np.finfo(float).eps*np.abs(data).sum(0)
+    assert np.all(np.abs(got - data.sum(0)) <= tol + 1e-300)
+
+
+def test_bfb_tree_allreduce_partition_invariant(oracle):
+    """4 emulated ranks, each with its own leaves: same bits as one rank."""
+    import torch
+    import compose_b200 as cb
+    nleaf, nfield, P, mbl = 4096, 6, 4, 64
+    rng = np.random.default_rng(3)
+    data = rng.standard_normal((nleaf, nfield))
+    tree = oracle.bisection_tree(nleaf)
+    ref = oracle.bfb_allreduce(tree, data.reshape(-1), nfield, False)
+    nl = nleaf//P
+    rs, recvs = [], []
+    for r in range(P):
+        red = cb.BfbTreeAllReducer(nleaf, nfield, max_block_leaves=mbl, rank=r, nranks=P)
+        red.use_tensor_exchange_buffers(P)
+        rs.append(red)
+    sends = [torch.from_numpy(np.ascontiguousarray(data[r*nl:(r + 1)*nl]).reshape(-1)).cuda()
+             for r in range(P)]
+    recvs = [torch.empty(nfield, dtype=torch.float64, device="cuda") for _ in range(P)]
+    for red, s, rv in zip(rs, sends, recvs):
+        red.allreduce(s, rv, phase=0)
+    torch.cuda.synchronize()
+    msg = torch.cat([red._xsend for red in rs])
+    for red in rs:
+        red._xrecv.copy_(msg)
+    for red, s, rv in zip(rs, sends, recvs):
+        red.allreduce(s, rv, phase=1)
+    torch.cuda.synchronize()
+    for rv in recvs:
+        assert np.array_equal(rv.cpu().numpy(), ref)
