@@ -361,7 +361,7 @@ fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
   const long long work = static_cast<long long>(a.nblocks)*a.ntr;
   a.group = static_cast<int>(std::max<long long>(1, std::min<long long>(32, work/(148*5*4))));
   if (const char* e = std::getenv("CEDR_B200_GROUP")) a.group = std::max(1, std::atoi(e));
-  a.n7buf = std::getenv("CEDR_B200_DOWN1") ? nullptr : c.d_n7.p;
+  a.n7buf = c.d_n7.p;
   a.rq = c.d_frq.p;
   if (c.split && cls != CLS_CAAS) {
     a.split = c.split;
@@ -407,14 +407,6 @@ void launch_fast_up (cedr_b200_cdr& c, int cls) {
 
 void launch_fast_down (cedr_b200_cdr& c, int cls) {
   const fast::FastArgs a = fast_args(c, cls);
-  if (std::getenv("CEDR_B200_DOWN1")) {   // the unspecialised kernel, for A/B timing
-    const size_t smem = sizeof(double)*(7*a.sbuf + 4*256 + fast::kD9) + 16;
-    if (cls == CLS_ST)
-      launch_fast(c, fast::down_kernel<CLS_ST>, a, smem, CEDR_B200_TAG_DOWN);
-    else
-      launch_fast(c, fast::down_kernel<CLS_CST>, a, smem, CEDR_B200_TAG_DOWN);
-    return;
-  }
   size_t smem = fast::down2_smem_bytes(a.sbuf);
   if (const char* e = std::getenv("CEDR_B200_SMEM_PAD")) smem += std::atoi(e);  // occupancy experiments
   if (cls == CLS_ST)
@@ -603,8 +595,7 @@ void launch_top_x (cedr_b200_cdr& c, int cls) {
 // a perfect subtree of depth S whose 2^S leaves are block b's depth-S nodes.
 void build_split (cedr_b200_cdr& c) {
   c.split = 0;
-  if ( ! c.fast_ok || c.is_caas || std::getenv("CEDR_B200_NO_SPLIT") ||
-      std::getenv("CEDR_B200_DOWN1")) return;
+  if ( ! c.fast_ok || c.is_caas || std::getenv("CEDR_B200_NO_SPLIT")) return;
   if (c.plan.tiers.size() != 2 || c.plan.tiers[1].blocks.size() != 1) return;
   const int nl = c.plan.tiers[1].nleaves;
   const int S = 8*nl <= 2048 ? 3 : 4*nl <= 2048 ? 2 : 0;

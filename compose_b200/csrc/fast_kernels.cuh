@@ -12,9 +12,9 @@
 //     i is being swept;
 //   - thread `tid` owns the depth-7 node `tid` (4 depth-9 nodes, 4..8 leaves): its
 //     micro-subtree is summed and solved in registers;
-//   - the 7 levels above the depth-7 nodes go through warp shuffles (sums) and shared
-//     memory (node problems);
-//   - solved leaf masses are staged in shared memory and written back coalesced.
+//   - the levels above the depth-7 nodes go through warp shuffles (sums) and, in the
+//     down-sweep, through a dedicated top warp working a tracer ahead of the leaf warps;
+//   - solved leaf masses are staged in shared memory and leave by a TMA bulk store.
 // The node arithmetic is the same device code as the generic path (node_solve.cuh), in
 // the same tree order, so results are bit-identical to it and to the reference.
 #ifndef CEDR_B200_FAST_KERNELS_CUH
@@ -322,176 +322,8 @@ up_kernel (const FastArgs a) {
 // ---------------------------------------------------------------------- DOWN
 //
 // QLT::r2l_solve_qp (cedr_qlt.cpp:490-604) over a fast-path block for the
-// shape-preserving classes (st, cst): recompute the block's sums (the up-sweep kept
-// nothing but the block-root record), then solve every node problem from the block
-// root's mass (solved by the tier above) down to the leaves.
-template <int CLS>
-__global__ void __launch_bounds__(kThreads)
-down_kernel (const FastArgs a) {
-  static_assert(CLS == CLS_ST || CLS == CLS_CST, "fast down-sweep: st / cst only");
-  constexpr int nrows = 3;   // Qm_min, Qm, Qm_max are the tracer's first three rows
-  extern __shared__ __align__(16) unsigned char smraw[];
-  double* const stage = reinterpret_cast<double*>(smraw);            // [2][3][sbuf]
-  double* const xout = stage + 2*nrows*a.sbuf;                       // [sbuf]
-  double* const un = xout + a.sbuf;                                  // [4][256]
-  double* const d9x = un + 4*256;                                    // [512]
-  uint64_t* const mbar = reinterpret_cast<uint64_t*>(d9x + kD9);     // [2]
-
-  const int b = blockIdx.x % a.nblocks, grp = blockIdx.x / a.nblocks;
-  const BlockDev B = a.blocks[b];
-  const int tid = threadIdx.x;
-  const int src0 = B.leaf0 & ~1, shift = B.leaf0 - src0;
-  const unsigned bytes = 8u*static_cast<unsigned>(((B.leaf0 + B.nl + 1) & ~1) - src0);
-  const int g0 = grp*a.group;
-  const int gn = min(a.group, a.ntr - g0);
-  const bool prefer = a.prefer_mass_con != 0;
-  const unsigned short* const dtab = a.dtab + B.ftab_off;
-  const unsigned short* const ptab = a.ptab + B.fpair_off;
-  const NodeWQ* const wq = a.wq + B.fbase;
-  const NodeRh* const rh = a.rh + B.fbase;
-
-  const ushort4 e = reinterpret_cast<const ushort4*>(dtab)[tid];
-  const int off[4] = {(e.x & 0x7fff) + shift, (e.y & 0x7fff) + shift,
-                      (e.z & 0x7fff) + shift, (e.w & 0x7fff) + shift};
-  const bool pr[4] = {(e.x >> 15) != 0, (e.y >> 15) != 0, (e.z >> 15) != 0,
-                      (e.w >> 15) != 0};
-  // Node constants of this thread's micro-subtree (depth 7: heap 127 + tid; depth 8:
-  // heap 255 + 2 tid, + 1) are the same for every tracer: keep them in registers.
-  const NodeWQ c7 = wq[127 + tid], c8a = wq[255 + 2*tid], c8b = wq[256 + 2*tid];
-
-  if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  auto issue = [&] (const int i) {
-    const int t = a.tracers[g0 + i];
-    const double* src = a.in + static_cast<long long>(a.trcr_row[t])*a.in_ld + src0;
-    double* dst = stage + (i & 1)*nrows*a.sbuf;
-    mbar_expect_tx(&mbar[i & 1], nrows*bytes);
-#pragma unroll
-    for (int f = 0; f < nrows; ++f)
-      tma_load(dst + f*a.sbuf, src + f*a.in_ld, bytes, &mbar[i & 1]);
-  };
-  if (tid == 0) {
-    issue(0);
-    if (gn > 1) issue(1);
-  }
-
-  // Solve one node through node_solve.cuh; the rare bound-adjustment branch reads
-  // the kids' rhom from global memory.
-  auto solve = [&] (const NodeWQ& c, const int cpos, const double* nd, const double bm,
-                    const double* k0, const double* k1, double& x0, double& x1) {
-    dev::NodeConst nc;
-    nc.w0 = c.w0; nc.w1 = c.w1; nc.q0 = c.q0; nc.q1 = c.q1;
-    const bool lo = bm < nd[0], hi = bm > nd[2];
-    if (lo || hi) {
-      // cedr_qlt_inl.hpp:131-143 needs rhom of the kids; fetch only here.
-      const NodeRh r = rh[cpos];
-      nc.rh0 = r.rh0; nc.rh1 = r.rh1;
-    } else {
-      nc.rh0 = nc.rh1 = 1;
-    }
-    dev::solve_node_bounded(nc, prefer, nd[0], nd[1], nd[2], bm, k0[0], k0[1], k0[2],
-                            k1[0], k1[1], k1[2], x0, x1);
-  };
-
-  for (int i = 0; i < gn; ++i) {
-    const int t = a.tracers[g0 + i];
-    mbar_wait(&mbar[i & 1], (i >> 1) & 1);
-    const double* const s = stage + (i & 1)*nrows*a.sbuf;
-    // ---- micro-subtree sums in registers: 4 depth-9 nodes, 2 depth-8, 1 depth-7.
-    double n9[4][3], n8[2][3], n7[3];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-      for (int f = 0; f < 3; ++f) {
-        const double v0 = s[f*a.sbuf + off[k]];
-        n9[k][f] = pr[k] ? v0 + s[f*a.sbuf + off[k] + 1] : v0;
-      }
-    }
-#pragma unroll
-    for (int f = 0; f < 3; ++f) {
-      n8[0][f] = n9[0][f] + n9[1][f];
-      n8[1][f] = n9[2][f] + n9[3][f];
-      n7[f] = n8[0][f] + n8[1][f];
-      un[f*256 + 127 + tid] = n7[f];
-    }
-    __syncthreads();
-    // ---- sums of depths 6..0 (heap node h has kids 2h+1, 2h+2).
-    for (int d = 6; d >= 0; --d) {
-      if (tid < (1 << d)) {
-        const int h = (1 << d) - 1 + tid;
-#pragma unroll
-        for (int f = 0; f < 3; ++f)
-          un[f*256 + h] = un[f*256 + 2*h + 1] + un[f*256 + 2*h + 2];
-      }
-      if (d > 5) __syncthreads(); else __syncwarp();
-    }
-    // ---- node problems of depths 0..6. Depths 0..5 fit in warp 0.
-    if (tid == 0) un[3*256] = a.sol_in[static_cast<long long>(t)*a.sol_in_ld + B.gidx];
-    __syncwarp();
-    for (int d = 0; d <= 6; ++d) {
-      if (d == 6) __syncthreads();
-      if (tid < (1 << d)) {
-        const int h = (1 << d) - 1 + tid;
-        const double nd[3] = {un[h], un[256 + h], un[512 + h]};
-        const double k0[3] = {un[2*h + 1], un[256 + 2*h + 1], un[512 + 2*h + 1]};
-        const double k1[3] = {un[2*h + 2], un[256 + 2*h + 2], un[512 + 2*h + 2]};
-        double x0, x1;
-        solve(wq[h], h, nd, un[768 + h], k0, k1, x0, x1);
-        un[768 + 2*h + 1] = x0;
-        un[768 + 2*h + 2] = x1;
-      }
-      if (d < 5) __syncwarp();
-    }
-    __syncthreads();
-    // ---- micro-subtree node problems in registers.
-    {
-      const double x7 = un[768 + 127 + tid];
-      double x8[2], x9[4];
-      solve(c7, 127 + tid, n7, x7, n8[0], n8[1], x8[0], x8[1]);
-      solve(c8a, 255 + 2*tid, n8[0], x8[0], n9[0], n9[1], x9[0], x9[1]);
-      solve(c8b, 256 + 2*tid, n8[1], x8[1], n9[2], n9[3], x9[2], x9[3]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (pr[k]) d9x[4*tid + k] = x9[k];
-        else xout[off[k]] = x9[k];
-      }
-    }
-    __syncthreads();
-    // ---- the depth-9 pairs, densely over the threads.
-    for (int j = tid; j < B.npairs; j += kThreads) {
-      const int p = ptab[j];
-      const int o = (dtab[p] & 0x7fff) + shift;
-      double k0[3], k1[3], nd[3];
-#pragma unroll
-      for (int f = 0; f < 3; ++f) {
-        k0[f] = s[f*a.sbuf + o];
-        k1[f] = s[f*a.sbuf + o + 1];
-        nd[f] = k0[f] + k1[f];
-      }
-      double x0, x1;
-      solve(wq[kHeapNodes + j], kHeapNodes + j, nd, d9x[p], k0, k1, x0, x1);
-      xout[o] = x0;
-      xout[o + 1] = x1;
-    }
-    __syncthreads();
-    // ---- coalesced write-back of the block's solved leaf masses.
-    {
-      double* const o = a.out + static_cast<long long>(t)*a.out_ld + B.leaf0;
-      for (int k = tid; k < B.nl; k += kThreads) o[k] = xout[shift + k];
-    }
-    __syncthreads();
-    if (tid == 0 && i + 2 < gn) issue(i + 2);
-  }
-}
-
-// ---------------------------------------------------------------- DOWN, specialised
-//
-// Same work as down_kernel, organised so that no warp ever waits for the serial part of
-// the block. The block's node problems split into
+// shape-preserving classes (st, cst), organised so that no warp ever waits for the serial
+// part of the block. The block's node problems split into
 //   - the block top, depths 0..6 (127 nodes): a chain of 7 dependent levels, at most 64
 //     problems wide -- one TOP warp walks it;
 //   - the micro-subtrees, depths 7..9 (~80% of the nodes): 128 independent columns, one
@@ -560,27 +392,18 @@ down2_kernel (const FastArgs a) {
   const dev::NodeWQ* const wq = a.wq + B.fbase;
   const dev::NodeRh* const rh = a.rh + B.fbase;
   const double* const rqv = a.rq + B.fbase;
+  // (Making `prefer` a template argument halves the code but ptxas then spills twice as
+  // much: measured 8.0 vs 6.65 ms at ne120.)
   const bool prefer = a.prefer_mass_con != 0;
-
   auto solve = [&] (const dev::NodeWQ& c, const double rq, const int cpos, const double* nd,
                     const double bm, const double* k0, const double* k1, double& x0,
                     double& x1) {
-#ifndef CEDR_B200_FLAT_SOLVE   // the branch-free form measured 4% slower here (more FP64 work per warp)
     if (prefer)
       dev::solve_bounded_lean<true>(c, rq, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
                                     k0[2], k1[0], k1[1], k1[2], x0, x1);
     else
       dev::solve_bounded_lean<false>(c, rq, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
                                      k0[2], k1[0], k1[1], k1[2], x0, x1);
-#else
-    (void) rq;
-    if (prefer)
-      dev::solve_bounded_flat<true>(c, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
-                                    k0[2], k1[0], k1[1], k1[2], x0, x1);
-    else
-      dev::solve_bounded_flat<false>(c, rh + cpos, nd[0], nd[1], nd[2], bm, k0[0], k0[1],
-                                     k0[2], k1[0], k1[1], k1[2], x0, x1);
-#endif
   };
 
   if (tid < kHeapNodes/4) { topc[tid] = wq[tid]; toprq[tid] = rqv[tid]; }

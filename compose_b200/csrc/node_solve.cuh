@@ -354,80 +354,6 @@ solve_bounded_lean (const NodeWQ& c, const double rq, const NodeRh* rh, const do
   x1 = pin0 ? o : v;
 }
 
-// Branch-free form of solve_bounded_lean: the unconstrained optimum and the boundary
-// candidate do not depend on each other, so both are computed in straight-line code (the
-// two dependency chains overlap instead of running back to back behind a divergent
-// branch -- in a warp of 32 independent problems both branches are almost always taken by
-// someone) and the reference's result is picked by selects at the end. The rare cases
-// (node mass outside the node's bounds; boundary alphas not ordered like a box with
-// nonzero widths) are re-solved afterwards by the literal out-of-line routines.
-template <bool PREFER>
-__device__ __forceinline__ void
-solve_bounded_flat (const NodeWQ& c, const NodeRh* rh, const double pmin, const double pqm,
-                    const double pmax, const double b, const double lo0, const double y0,
-                    const double hi0, const double lo1, const double y1, const double hi1,
-                    double& x0, double& x1) {
-  const bool cold = b < pmin || b > pmax;
-  const bool quick = b == pqm && y0 >= lo0 && y0 <= hi0 && y1 >= lo1 && y1 <= hi1;
-  bool inf_lo = false, inf_hi = false;
-  if ( ! PREFER) {
-    double ab = fabs(b) > fabs(y0) ? b : y0;
-    ab = fabs(ab) > fabs(y1) ? ab : y1;
-    const double r_tol = CEDR_B200_TEN_EPS*fabs(ab);
-    const double r1 = (lo0 - b) + lo1;
-    const double r2 = (hi0 - b) + hi1;
-    const bool c1 = ! (fabs(r1) <= r_tol);
-    inf_lo = c1 && r1 > 0;
-    inf_hi = c1 && ! inf_lo && ! (fabs(r2) <= r_tol) && r2 < 0;
-  }
-  // Unconstrained optimum.
-  const double qmass = c.q0 + c.q1;
-  const double dm = (b - y0) - y1;
-  const double lambda = dm/qmass;
-  const double xu0 = y0 + lambda*c.q0;
-  const double xu1 = y1 + lambda*c.q1;
-  const bool ok = ! (xu0 < lo0 || xu0 > hi0) && ! (xu1 < lo1 || xu1 > hi1);
-  // Boundary candidate.
-  const double xb = 0.5*b;
-  const double a0 = lo1 - xb, a1 = -(hi0 - xb), a2 = hi1 - xb, a3 = -(lo0 - xb);
-  const bool L = a1 >= a0, H = a3 <= a2;
-  const double aL = L ? a1 : a0, aH = H ? a3 : a2;
-  const bool scan = ! (a0 < a2 && a1 < a3);
-  double obj0, obj1;
-  {
-    const double d0 = y0 - (xb - aL), d1 = y1 - (xb + aL);
-    obj0 = c.w0*(d0*d0) + c.w1*(d1*d1);
-  }
-  {
-    const double d0 = y0 - (xb - aH), d1 = y1 - (xb + aH);
-    obj1 = c.w0*(d0*d0) + c.w1*(d1*d1);
-  }
-  const bool first = obj0 <= obj1;
-  const bool pin0 = first ? L : H;
-  const double v = first ? (L ? hi0 : lo1) : (H ? lo0 : hi1);
-  double o = b - v;
-  if ( ! PREFER) {
-    const double olo = pin0 ? lo1 : lo0, ohi = pin0 ? hi1 : hi0;
-    o = rmin(ohi, rmax(olo, o));
-  }
-  // The reference's order of exits: quick; infeasible corner; unconstrained; boundary.
-  x0 = pin0 ? v : o;
-  x1 = pin0 ? o : v;
-  if (ok) { x0 = xu0; x1 = xu1; }
-  if (inf_hi) { x0 = hi0; x1 = hi1; }
-  if (inf_lo) { x0 = lo0; x1 = lo1; }
-  if (quick) { x0 = y0; x1 = y1; }
-  if (cold) {
-    double x[2];
-    solve_bounded_cold(c, rh, PREFER, pmin, pqm, pmax, b, lo0, y0, hi0, lo1, y1, hi1, x);
-    x0 = x[0]; x1 = x[1];
-  } else if (scan && ! quick && ! inf_lo && ! inf_hi && ! ok) {
-    double x[2];
-    qp2d_boundary_cold(c.w0, c.w1, b, lo0, lo1, hi0, hi1, y0, y1, ! PREFER, x);
-    x0 = x[0]; x1 = x[1];
-  }
-}
-
 // The nonnegative node problem, cedr_qlt_inl.hpp:188-197 -> solve_1eq_nonneg
 // (cedr_local_inl.hpp:307-330) with n = 2, least squares: bounds [0, b/a_i],
 // default clip / early-exit flags (independent of the CDR option).
