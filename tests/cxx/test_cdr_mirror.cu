@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "cedr_b200.hpp"
+#include "cedr_b200_local.hpp"
 #include "cedr_oracle.h"
 
 using namespace cedr;
@@ -44,6 +45,27 @@ __global__ void get_all (const Op op, const int n, const int nt, double* out,
   if (k >= (long long) n*nt) return;
   const int t = (int) (k / n), i = (int) (k % n);
   out[(long long) t*n + gcis[i]] = op.get_Qm(i, t);
+}
+
+// The element-local solvers on the device: one thread per problem, 16-wide slots.
+// which: 0 solve_1eq_bc_qp, 1 caas, 2 solve_1eq_nonneg(least_squares), 3 (caas),
+// 4 solve_1eq_bc_qp_2d (n = 2).
+__global__ void local_kernel (const int nprob, const int which, const int* n, const double* w,
+                              const double* a, const double* b, const double* xlo,
+                              const double* xhi, const double* y, double* x, int* info) {
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= nprob) return;
+  const int o = 16*p;
+  namespace L = cedr::local;
+  int r = 0;
+  switch (which) {
+  case 0: r = L::solve_1eq_bc_qp(n[p], w + o, a + o, b[p], xlo + o, xhi + o, y + o, x + o); break;
+  case 1: L::caas(n[p], a + o, b[p], xlo + o, xhi + o, y + o, x + o); break;
+  case 2: r = L::solve_1eq_nonneg(n[p], a + o, b[p], y + o, x + o, w + o, L::Method::least_squares); break;
+  case 3: r = L::solve_1eq_nonneg(n[p], a + o, b[p], y + o, x + o, w + o, L::Method::caas); break;
+  case 4: r = L::solve_1eq_bc_qp_2d(w + o, a + o, b[p], xlo + o, xhi + o, y + o, x + o); break;
+  }
+  info[p] = r;
 }
 
 template <typename T> T* to_dev (const std::vector<T>& h) {
@@ -188,6 +210,63 @@ int main () {
     if (n <= 1350) {
       CAAST c(par, n, nullptr, Memory::managed);
       REQUIRE(same_bits(run_host(c, p, id), ref));
+    }
+  }
+
+  { // cedr::local on the device == the oracle's restatement of the reference, bitwise.
+    const int np = 4096;
+    unsigned long long seed = 12345;
+    auto U = [&] () {   // splitmix64 -> [0, 1)
+      unsigned long long z = (seed += 0x9E3779B97F4A7C15ull);
+      z = (z ^ (z >> 30))*0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27))*0x94D049BB133111EBull;
+      return (double) ((z ^ (z >> 31)) >> 11)*0x1.0p-53;
+    };
+    for (int which = 0; which < 5; ++which) {
+      std::vector<int> n(np), info(np), info_ref(np);
+      std::vector<double> w(16*np, 1), a(16*np, 1), b(np), xlo(16*np, 0), xhi(16*np, 1),
+        y(16*np, 0), x(16*np, 0), x_ref(16*np, 0);
+      for (int p = 0; p < np; ++p) {
+        n[p] = which == 4 ? 2 : 2 + (int) (U()*14.999);
+        double blo = 0, bhi = 0, bmid = 0;
+        for (int i = 0; i < n[p]; ++i) {
+          const int k = 16*p + i;
+          w[k] = 0.1 + U(); a[k] = 0.1 + U();
+          xlo[k] = U() - 0.5; xhi[k] = xlo[k] + U();
+          y[k] = xlo[k] + (xhi[k] - xlo[k])*(1.6*U() - 0.3);   // some outside the bounds
+          if (which == 2 || which == 3) y[k] = U() - 0.2;
+          blo += a[k]*xlo[k]; bhi += a[k]*xhi[k];
+          bmid += a[k]*(xlo[k] + (xhi[k] - xlo[k])*U());
+        }
+        // Mostly feasible masses; some at the corners, some infeasible.
+        const double u = U();
+        b[p] = u < 0.8 ? bmid : u < 0.85 ? blo : u < 0.9 ? bhi : u < 0.95 ? blo - 0.1 : bhi + 0.1;
+        if (which == 2 || which == 3) b[p] = u < 0.9 ? U()*n[p] : -0.1;
+        const int o = 16*p;
+        switch (which) {
+        case 0: info_ref[p] = oracle_solve_1eq_bc_qp(n[p], &w[o], &a[o], b[p], &xlo[o], &xhi[o], &y[o], &x_ref[o], 100); break;
+        case 1: oracle_local_caas(n[p], &a[o], b[p], &xlo[o], &xhi[o], &y[o], &x_ref[o], 1); info_ref[p] = 0; break;
+        case 2: info_ref[p] = oracle_solve_1eq_nonneg(n[p], &a[o], b[p], &y[o], &x_ref[o], &w[o], 0); break;
+        case 3: info_ref[p] = oracle_solve_1eq_nonneg(n[p], &a[o], b[p], &y[o], &x_ref[o], &w[o], 1); break;
+        case 4: info_ref[p] = oracle_solve_1eq_bc_qp_2d(&w[o], &a[o], b[p], &xlo[o], &xhi[o], &y[o], &x_ref[o], 1, 1); break;
+        }
+      }
+      int* dn = to_dev(n), * dinfo = to_dev(info);
+      double* dw = to_dev(w), * da = to_dev(a), * db = to_dev(b), * dlo = to_dev(xlo),
+        * dhi = to_dev(xhi), * dy = to_dev(y), * dx = to_dev(x);
+      local_kernel<<<(np + 127)/128, 128>>>(np, which, dn, dw, da, db, dlo, dhi, dy, dx, dinfo);
+      cudaMemcpy(x.data(), dx, x.size()*sizeof(double), cudaMemcpyDeviceToHost);
+      cudaMemcpy(info.data(), dinfo, np*sizeof(int), cudaMemcpyDeviceToHost);
+      int nfeas = 0;
+      for (int p = 0; p < np; ++p) nfeas += info_ref[p] >= 0;
+      REQUIRE(nfeas > np/2);
+      REQUIRE(info == info_ref);
+      // An infeasible return of solve_1eq_nonneg leaves x untouched in both versions
+      // (zeros here), so the whole array compares.
+      REQUIRE(same_bits(x, x_ref));
+      for (void* d : {(void*) dn, (void*) dinfo, (void*) dw, (void*) da, (void*) db, (void*) dlo,
+            (void*) dhi, (void*) dy, (void*) dx})
+        cudaFree(d);
     }
   }
 
