@@ -344,6 +344,30 @@ def main():
                       % (pipe.nchunks, len(pipe.slots))}
         launches += pipe.launches_per_step*args.steps
 
+    # ---- config 5 flavour: many tiny runs (111 cells x 1 tracer), device time per run()
+    small = None
+    if rank == 0:
+        small = {"workload": "111 cells x 1 tracer (cedr_test_1d_transport size), 200 "
+                             "back-to-back run() calls, CUDA events"}
+        r1, l1, q1, h1, p1 = cb.fill_headline(111, 1, 5)
+        for kind in ("qlt", "caas"):
+            c = cb.QLT(111) if kind == "qlt" else cb.CAAS(111)
+            c.declare_tracer(3)
+            c.end_tracer_declarations()
+            c.finish_setup()
+            c.set_rhom(r1)
+            c.set_Qm(q1, l1, h1, p1)
+            for _ in range(20):
+                c.run()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(200):
+                c.run()
+            e1.record()
+            torch.cuda.synchronize()
+            small[kind + "_us_per_run"] = 1e3*e0.elapsed_time(e1)/200
+            small[kind + "_launches_per_run"] = c.last_run_launches()
+
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -363,6 +387,7 @@ def main():
             "caas": {"value": updates/(ms_caas*1e-3), "ms_per_run": ms_caas},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks, "kernels_ms": kernels,
+            "small_problem": small,
         }
         print(json.dumps(line))
     if world > 1:

@@ -384,8 +384,14 @@ template <typename K>
 void launch_fast (cedr_b200_cdr& c, K kernel, const fast::FastArgs& a, size_t smem, int tag,
                   int threads = fast::kThreads) {
   if (a.ntr == 0) return;
-  CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(std::max<size_t>(smem, 48*1024))));
+  // Raise (never lower) the kernel's dynamic shared memory limit, once per size.
+  static std::unordered_map<const void*, size_t> configured;
+  size_t& have = configured[reinterpret_cast<const void*>(kernel)];
+  if (smem > have) {
+    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(std::max<size_t>(smem, 48*1024))));
+    have = smem;
+  }
   const long long grid = static_cast<long long>(a.nblocks)*((a.ntr + a.group - 1)/a.group);
   cedr_b200_throw_if(grid > 0x7fffffffLL, "grid too large");
   LaunchTimer lt(c, tag, 0);

