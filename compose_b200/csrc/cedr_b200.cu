@@ -850,6 +850,14 @@ void build_plan (cedr_b200_cdr& c) {
   }
   if (c.nranks > 1) {
     c.nown_max = static_cast<int>((blocks.size() + c.nranks - 1)/c.nranks);
+    if ( ! c.is_caas) {
+      // QLT and the reducer know every leaf's rank: size the message for the rank that
+      // owns the most blocks, so any assignment of whole blocks to ranks works.
+      std::vector<int> cnt(c.nranks, 0);
+      for (size_t b = 0; b < blocks.size(); ++b)
+        if (blocks[b].owner >= 0 && blocks[b].owner < c.nranks) ++cnt[blocks[b].owner];
+      c.nown_max = std::max(1, *std::max_element(cnt.begin(), cnt.end()));
+    }
     if (static_cast<int>(c.own_blocks.size()) > c.nown_max && c.partition_error.empty()) {
       std::stringstream ss;
       ss << "this rank owns " << c.own_blocks.size() << " blocks, more than "

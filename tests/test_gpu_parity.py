@@ -572,3 +572,42 @@ def test_headline_full_size_properties():
             for k in env:
                 del os.environ[k]
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_qlt_block_granular_rank_map_bitwise(oracle):
+    """Any assignment of WHOLE blocks to ranks works, not only contiguous ranges: 3 ranks,
+    the 16 blocks of a 16 x 675-cell mesh dealt round-robin with an uneven remainder
+    (6 / 5 / 5), through a caller-provided tree with per-leaf ranks."""
+    import torch
+    import compose_b200 as cb
+    ncells, P = 16*675, 3
+    tree = oracle.bisection_tree(ncells)
+    kids, cellidx = tree.kids, tree.cellidx
+    rank = np.zeros(cellidx.size, np.int32)
+    leaf = cellidx >= 0
+    rank[leaf] = (cellidx[leaf]//675) % P
+    ts, v = R.generate(ncells, seed=4242)
+    ts = ts[:8]
+    pts = [t.problem_type for t in ts]
+    n = len(pts)
+    ref = oracle.qlt(tree, pts, v.rhom, v.Qm_min[:n], v.Qm[:n], v.Qm_max[:n], v.Qm_prev[:n])
+    cdrs, gcis = [], []
+    for r in range(P):
+        q = cb.QLT(ncells, tree=(kids, cellidx, 0), rank=r, nranks=P, node_rank=rank)
+        for p in pts:
+            q.declare_tracer(int(p))
+        q.end_tracer_declarations()
+        q.use_tensor_exchange_buffers(P)
+        q.finish_setup()
+        g = q.get_owned_glblcells()
+        assert q.nlclcells() == len(g) == 675*(6 if r == 0 else 5)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a)[..., g])).cuda()
+        q.set_rhom(dev(v.rhom))
+        q.set_Qm(dev(v.Qm[:n]), dev(v.Qm_min[:n]), dev(v.Qm_max[:n]), dev(v.Qm_prev[:n]))
+        cdrs.append(q)
+        gcis.append(g)
+    _emulate_exchange(cdrs)
+    res = np.empty((n, ncells))
+    for q, g in zip(cdrs, gcis):
+        res[:, g] = q.get_Qm().cpu().numpy()
+    assert np.array_equal(res, ref)
