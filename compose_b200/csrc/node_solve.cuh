@@ -313,6 +313,14 @@ solve_bounded_lean (const NodeWQ& c, const double rq, const NodeRh* rh, const do
       return;
     }
   }
+  // The boundary branch's alphas do not depend on the division below; formed first, they
+  // overlap its latency (in a warp some lane nearly always takes the boundary branch).
+  // a0 bottom, a1 right, a2 top, a3 left.
+  const double xb = 0.5*b;
+  const double a0 = lo1 - xb, a1 = -(hi0 - xb), a2 = hi1 - xb, a3 = -(lo0 - xb);
+  const bool L = a1 >= a0, H = a3 <= a2;       // kept pair = (max(a0,a1), min(a2,a3))
+  const double aL = L ? a1 : a0, aH = H ? a3 : a2;
+  const bool boxed = a0 < a2 && a1 < a3;
   { // Unconstrained optimum, cedr_local_inl.hpp:80-97.
     const double qmass = c.q0 + c.q1;
     const double dm = (b - y0) - y1;
@@ -321,12 +329,8 @@ solve_bounded_lean (const NodeWQ& c, const double rq, const NodeRh* rh, const do
     x1 = y1 + lambda*c.q1;
     if ( ! (x0 < lo0 || x0 > hi0) && ! (x1 < lo1 || x1 > hi1)) return;
   }
-  // Boundary branch. a0 bottom, a1 right, a2 top, a3 left.
-  const double xb = 0.5*b;
-  const double a0 = lo1 - xb, a1 = -(hi0 - xb), a2 = hi1 - xb, a3 = -(lo0 - xb);
-  const bool L = a1 >= a0, H = a3 <= a2;       // kept pair = (max(a0,a1), min(a2,a3))
-  const double aL = L ? a1 : a0, aH = H ? a3 : a2;
-  if ( ! (a0 < a2 && a1 < a3)) {
+  // Boundary branch.
+  if ( ! boxed) {
     double x[2];
     qp2d_boundary_cold(c.w0, c.w1, b, lo0, lo1, hi0, hi1, y0, y1, ! PREFER, x);
     x0 = x[0]; x1 = x[1];
