@@ -159,9 +159,12 @@ def config_dict(args, ncells, nt):
             "l2": "inputs (>= 0.6 GB per reconstructor) exceed the 126 MB L2; no flush",
             "parallelism": ("single GPU" if args.gpus == 1 else
                             "%d GPUs, cells partitioned by subtree (each rank owns "
-                            "ncells/%d contiguous cells = whole tier-0 blocks); one NCCL "
-                            "all-gather of the block roots per run(), tiers above "
-                            "replicated in fixed tree order" % (args.gpus, args.gpus))}
+                            "ncells/%d contiguous cells = whole tier-0 blocks); the block "
+                            "roots are exchanged once per run() (%s), tiers above "
+                            "replicated in fixed tree order"
+                            % (args.gpus, args.gpus,
+                               "NCCL all-gather" if os.environ.get("CEDR_B200_NO_P2P") else
+                               "peer-to-peer stores over NVLink + epoch flags"))}
 
 
 def main():
@@ -203,6 +206,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Multi-GPU exchange: direct stores into the peers' buffers over NVLink (default), or
+    # torch.distributed's NCCL all-gather (CEDR_B200_NO_P2P=1).
+    P2P = world > 1 and not os.environ.get("CEDR_B200_NO_P2P")
     ncells, nt, cid = workload_dims(args.workload)
     # Subtree partition: rank r owns cells [r*nl, (r+1)*nl) of every tracer.
     if ncells % world:
@@ -224,6 +230,8 @@ def main():
         if world > 1:
             c.enable_distributed(world)
         c.finish_setup()
+        if world > 1 and P2P:
+            c.enable_p2p(world)
         c.set_rhom(rhom)
         c.set_Qm(q, lo, hi, prev)
         return c
@@ -315,7 +323,7 @@ def main():
     if not args.no_e2e:
         del qlt, caas
         torch.cuda.empty_cache()
-        pipe = HostStepPipeline(ncells, nt_lcl, rank=rank, nranks=world)
+        pipe = HostStepPipeline(ncells, nt_lcl, rank=rank, nranks=world, p2p=P2P)
         pin = lambda x: x.cpu().pin_memory()
         rhom_h, lo_h, q_h, hi_h, prev_h = (pin(x) for x in (rhom, lo, q, hi, prev))
         out_h = {k: torch.empty((nt_lcl, nl), dtype=torch.float64).pin_memory()

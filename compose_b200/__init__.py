@@ -79,6 +79,9 @@ SYMBOLS = [
     ("cedr_b200_run_phase", C.c_int, [_H, C.c_int]),
     ("cedr_b200_partition_probe", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, _ip, _ip, _ip, _ip, _ip, _ip, _ip]),
+    ("cedr_b200_p2p_get_handle", C.c_int, [_H, _vp]),
+    ("cedr_b200_p2p_set_peer", C.c_int, [_H, C.c_int, _vp]),
+    ("cedr_b200_p2p_enable", C.c_int, [_H, C.c_int]),
     ("cedr_b200_last_run_launches", C.c_int, [_H, _ip]),
     ("cedr_b200_set_fast_path", C.c_int, [_H, C.c_int]),
     ("cedr_b200_uses_fast_path", C.c_int, [_H, _ip]),
@@ -292,6 +295,20 @@ class CDR:
                 return 1
         self._cb = ALLGATHER_FN(gather)
         _check(self._lib.cedr_b200_set_allgather(self._h, self._cb, None))
+
+    def enable_p2p(self, nranks, group=None):
+        """After finish_setup on every rank: swap CUDA IPC handles through
+        torch.distributed and switch run()'s exchange to direct stores into the peers'
+        buffers over NVLink (no NCCL call inside run())."""
+        import torch.distributed as dist
+        buf = C.create_string_buffer(64)
+        _check(self._lib.cedr_b200_p2p_get_handle(self._h, buf))
+        handles = [None]*nranks
+        dist.all_gather_object(handles, bytes(buf.raw), group=group)
+        for r, h in enumerate(handles):
+            _check(self._lib.cedr_b200_p2p_set_peer(self._h, r, C.create_string_buffer(h, 64)))
+        _check(self._lib.cedr_b200_p2p_enable(self._h, 1))
+        dist.barrier(group=group)
 
     def run_phase(self, phase):
         _check(self._lib.cedr_b200_run_phase(self._h, int(phase)))

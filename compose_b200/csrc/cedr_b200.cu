@@ -188,6 +188,12 @@ struct cedr_b200_cdr {
   DevBuf<double> xsend_own, xrecv_own;   // exchange message / gathered messages
   double* xsend = nullptr;
   double* xrecv = nullptr;
+  // Peer-to-peer exchange (cedr_b200_p2p_*): one allocation [64 epoch flags | receive
+  // buffer, parity 0 | receive buffer, parity 1], mapped by every peer through CUDA IPC.
+  DevBuf<double> p2p_arena;
+  std::vector<void*> p2p_peer;           // peer r's arena in this process's address space
+  bool p2p_on = false;
+  unsigned long long p2p_epoch = 0;
   int last_launches = 0;
 
   // Optional per-launch timing (cedr_b200_set_profiling).
@@ -197,6 +203,8 @@ struct cedr_b200_cdr {
   size_t ntimed = 0;
   ~cedr_b200_cdr () {
     for (auto& t : timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    for (size_t r = 0; r < p2p_peer.size(); ++r)
+      if (p2p_peer[r] && static_cast<int>(r) != rank) cudaIpcCloseMemHandle(p2p_peer[r]);
   }
 };
 
@@ -716,6 +724,44 @@ void exchange_unpack (cedr_b200_cdr& c, bool with_rhom) {
   ++c.last_launches;
 }
 
+size_t p2p_arena_doubles (const cedr_b200_cdr& c) {
+  return 64 + 2*exchange_count(c)*c.nranks;
+}
+
+// pack + all-gather in one step over peer memory, then the epoch barrier.
+void exchange_p2p (cedr_b200_cdr& c, bool with_rhom) {
+  ++c.p2p_epoch;
+  const size_t cnt = exchange_count(c);
+  const int parity = static_cast<int>(c.p2p_epoch & 1);
+  PeerPtrs pp;
+  std::memset(&pp, 0, sizeof(pp));
+  for (int r = 0; r < c.nranks; ++r) {
+    double* base = static_cast<double*>(c.p2p_peer[r]);
+    pp.flags[r] = reinterpret_cast<unsigned long long*>(base);
+    pp.recv[r] = base + 64 + parity*cnt*c.nranks;
+  }
+  const int E = 1 << c.split;
+  {
+    LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 0);
+    pack_p2p_kernel<<<grid_for(cnt), kThreads, 0, c.stream>>>(
+      c.d_blocks[0].p, nblocks_dev(c, 0), c.nown_max, static_cast<int>(c.trcr_prob.size()), E,
+      with_rhom ? (c.split ? c.d_xrhom.p : c.d_rhom_tier[1].p) : nullptr,
+      c.split ? c.d_xrec.p : c.d_rec[1].p, c.split ? c.x_ld : c.tier_ld[1], pp, c.rank,
+      c.nranks, static_cast<long long>(cnt));
+    CUDA_CHECK(cudaGetLastError());
+    ++c.last_launches;
+  }
+  {
+    LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 2);
+    p2p_barrier_kernel<<<1, 32, 0, c.stream>>>(
+      pp, reinterpret_cast<unsigned long long*>(c.p2p_arena.p), c.rank, c.nranks, c.p2p_epoch,
+      c.d_status.p);
+    CUDA_CHECK(cudaGetLastError());
+    ++c.last_launches;
+  }
+  c.xrecv = c.p2p_arena.p + 64 + parity*cnt*c.nranks;
+}
+
 void exchange_allgather (cedr_b200_cdr& c) {
   cedr_b200_throw_if( ! c.allgather, "nranks > 1 but no all-gather was set "
                      "(cedr_b200_set_allgather)");
@@ -740,10 +786,10 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
     if (multi) {
       for (int cls = 0; cls < CLS_CAAS; ++cls)
         if ( ! c.cls_tracers[cls].empty()) launch_up(c, cls, 0);
-      exchange_pack(c, true);
+      if (c.p2p_on && phase < 0) exchange_p2p(c, true); else exchange_pack(c, true);
     }
   }
-  if (multi && phase < 0) exchange_allgather(c);
+  if (multi && phase < 0 && ! c.p2p_on) exchange_allgather(c);
   if (phase != 0) {
     if (multi) {
       exchange_unpack(c, true);
@@ -794,9 +840,9 @@ void run_caas (cedr_b200_cdr& c, int phase) {
   const int top = ntiers - 1;
   if (phase <= 0 && multi) {
     launch_up(c, CLS_CAAS, 0);
-    exchange_pack(c, false);
+    if (c.p2p_on && phase < 0) exchange_p2p(c, false); else exchange_pack(c, false);
   }
-  if (multi && phase < 0) exchange_allgather(c);
+  if (multi && phase < 0 && ! c.p2p_on) exchange_allgather(c);
   if (phase == 0) return;
   if (multi) exchange_unpack(c, false);
   for (int k = multi ? 1 : 0; k < top; ++k) launch_up(c, CLS_CAAS, k);
@@ -875,9 +921,9 @@ void run_bfb (cedr_b200_cdr& c, int phase) {
   const int top = ntiers - 1;
   if (phase <= 0 && multi) {
     launch_up(c, CLS_BFB, 0);
-    exchange_pack(c, false);
+    if (c.p2p_on && phase < 0) exchange_p2p(c, false); else exchange_pack(c, false);
   }
-  if (multi && phase < 0) exchange_allgather(c);
+  if (multi && phase < 0 && ! c.p2p_on) exchange_allgather(c);
   if (phase == 0) return;
   if (multi) exchange_unpack(c, false);
   for (int k = multi ? 1 : 0; k < top; ++k) launch_up(c, CLS_BFB, k);
@@ -976,6 +1022,10 @@ void finish_setup (cedr_b200_cdr& c) {
   }
   c.d_qglob.alloc(2*static_cast<size_t>(nt));
   c.d_caas_scal.alloc(2*static_cast<size_t>(nt));
+  if (c.nranks > 1 && ! c.d_status.p) {
+    c.d_status.alloc(1);
+    CUDA_CHECK(cudaMemsetAsync(c.d_status.p, 0, sizeof(int), c.stream));
+  }
   if (c.nranks > 1 && ! c.xsend) {
     c.xsend_own.alloc(exchange_count(c));
     c.xrecv_own.alloc(exchange_count(c)*c.nranks);
@@ -1440,6 +1490,47 @@ int cedr_b200_uses_fused (const cedr_b200_cdr* c, int* on) {
 
 int cedr_b200_set_allgather (cedr_b200_cdr* c, cedr_b200_allgather_fn fn, void* ctx) {
   return guarded([&] { c->allgather = fn; c->allgather_ctx = ctx; });
+}
+
+int cedr_b200_p2p_get_handle (cedr_b200_cdr* c, void* handle64) {
+  return guarded([&] {
+    cedr_b200_throw_if( ! c->finished, "finish_setup must be called first.");
+    cedr_b200_throw_if(c->nranks < 2, "peer-to-peer exchange needs nranks > 1");
+    cedr_b200_throw_if(c->nranks > 16, "peer-to-peer exchange supports up to 16 ranks");
+    if ( ! c->p2p_arena.p) {
+      c->p2p_arena.alloc(p2p_arena_doubles(*c));
+      CUDA_CHECK(cudaMemset(c->p2p_arena.p, 0, p2p_arena_doubles(*c)*sizeof(double)));
+      c->p2p_peer.assign(c->nranks, nullptr);
+      c->p2p_peer[c->rank] = c->p2p_arena.p;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_CHECK(cudaIpcGetMemHandle(&h, c->p2p_arena.p));
+    std::memcpy(handle64, &h, 64);
+  });
+}
+
+int cedr_b200_p2p_set_peer (cedr_b200_cdr* c, int peer_rank, const void* handle64) {
+  return guarded([&] {
+    cedr_b200_throw_if( ! c->p2p_arena.p, "call p2p_get_handle first");
+    cedr_b200_throw_if(peer_rank < 0 || peer_rank >= c->nranks, "peer rank out of range");
+    if (peer_rank == c->rank) return;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->p2p_peer[peer_rank] = p;
+  });
+}
+
+int cedr_b200_p2p_enable (cedr_b200_cdr* c, int on) {
+  return guarded([&] {
+    if (on)
+      for (int r = 0; r < c->nranks; ++r)
+        cedr_b200_throw_if(r >= static_cast<int>(c->p2p_peer.size()) || ! c->p2p_peer[r],
+                           "peer " << r << " was not set (cedr_b200_p2p_set_peer)");
+    c->p2p_on = on != 0;
+  });
 }
 
 int cedr_b200_last_run_launches (const cedr_b200_cdr* c, int* n) {

@@ -359,6 +359,60 @@ pack_kernel (const BlockDev* blocks, const int nown, const int nown_max, const i
   }
 }
 
+// The same message, stored straight into every rank's receive buffer over peer-mapped
+// memory (NVLink): rank `me` owns slot `me` of each peer's rank-major buffer. Replaces
+// pack + all-gather; p2p_barrier_kernel then publishes and awaits the epoch.
+struct PeerPtrs { double* recv[16]; unsigned long long* flags[16]; };
+
+__global__ void __launch_bounds__(256)
+pack_p2p_kernel (const BlockDev* blocks, const int nown, const int nown_max, const int nt,
+                 const int E, const double* rhom1, const double* rec, const long long rec_ld,
+                 const PeerPtrs peers, const int me, const int nranks,
+                 const long long rank_stride) {
+  const long long per = 4LL*nt + 1, stride = 1 + E*per, n = stride*nown_max;
+  for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
+       k += (long long) gridDim.x*blockDim.x) {
+    const int j = (int) (k / stride);
+    const long long w = k % stride;
+    double v = w == 0 ? -1.0 : 0.0;
+    if (j < nown) {
+      const long long g = blocks[j].gidx;
+      if (w == 0) v = (double) g;
+      else {
+        const long long e = (w - 1)/per, i = (w - 1) % per, leaf = g*E + e;
+        v = i == 0 ? (rhom1 ? rhom1[leaf] : 0.0) : rec[(i - 1)*rec_ld + leaf];
+      }
+    }
+    for (int r = 0; r < nranks; ++r) peers.recv[r][me*rank_stride + k] = v;
+  }
+  __threadfence_system();
+}
+
+// Epoch barrier across the ranks' GPUs: publish "rank me has delivered epoch e" into every
+// peer's flag array, then wait until every rank has delivered to this one. One warp; lane
+// r talks to rank r. The ranks are different devices, each running its own stream, so the
+// wait cannot starve the writer (unlike two spinning kernels on ONE device).
+__global__ void p2p_barrier_kernel (const PeerPtrs peers, unsigned long long* my_flags,
+                                    const int me, const int nranks,
+                                    const unsigned long long epoch, int* status) {
+  const int r = threadIdx.x;
+  __threadfence_system();
+  if (r < nranks) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(peers.flags[r] + me), "l"(epoch)
+                 : "memory");
+    unsigned long long v = 0;
+    unsigned spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(my_flags + r)
+                   : "memory");
+      if (v >= epoch) break;
+      __nanosleep(100);
+      if (++spins > (1u << 24)) { atomicExch(status, 2); break; }   // ~2 s: a rank is gone
+    }
+  }
+  __threadfence_system();
+}
+
 __global__ void __launch_bounds__(256)
 unpack_kernel (const double* recv, const int nranks, const int nown_max, const int nt,
                const int E, double* rhom1, double* rec, const long long rec_ld,

@@ -16,7 +16,7 @@ import compose_b200 as cb
 
 class HostStepPipeline:
     def __init__(self, ncells, nt, problem_type=7, chunk_nt=640, nslots=3,
-                 reconstructors=("qlt", "caas"), rank=0, nranks=1):
+                 reconstructors=("qlt", "caas"), rank=0, nranks=1, p2p=False):
         """With nranks > 1 (one process per GPU, torch.distributed initialised) this rank
         holds cells [rank*ncells/nranks, (rank+1)*ncells/nranks) of every tracer and each
         chunk's run() all-gathers the block roots (subtree partition)."""
@@ -48,6 +48,8 @@ class HostStepPipeline:
                     if nranks > 1:
                         c.enable_distributed(nranks)
                     c.finish_setup()   # binds the slot's stream
+                    if nranks > 1 and p2p:
+                        c.enable_p2p(nranks)
                     s["cdr"][k] = c
             self.slots.append(s)
         torch.cuda.synchronize()

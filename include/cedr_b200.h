@@ -190,6 +190,18 @@ int cedr_b200_get_exchange_buffers(const cedr_b200_cdr* cdr, double** send, doub
  * in `send`; the caller fills `recv` with every rank's message (rank-major); phase 1
  * enqueues the rest. On one rank phase 0 is the whole run() and phase 1 does nothing. */
 int cedr_b200_run_phase(cedr_b200_cdr* cdr, int phase);
+/* Peer-to-peer exchange (one process per GPU, NVLink / NVSwitch): instead of handing the
+ * message to an all-gather, the pack kernel stores it straight into every rank's receive
+ * buffer over peer-mapped memory, and a one-warp kernel publishes and awaits an epoch flag
+ * with system-scope release/acquire -- no library collective and no host involvement in
+ * run(). Set-up, after finish_setup on every rank: exchange the 64-byte handles
+ * (cedr_b200_p2p_get_handle; CUDA IPC) by any means, hand each peer's to
+ * cedr_b200_p2p_set_peer, then cedr_b200_p2p_enable(cdr, 1). Receive buffers are
+ * double-buffered by epoch parity, so a rank may start its next run() while a peer still
+ * reads the previous message. Up to 16 ranks on one node. */
+int cedr_b200_p2p_get_handle(cedr_b200_cdr* cdr, void* handle64);
+int cedr_b200_p2p_set_peer(cedr_b200_cdr* cdr, int peer_rank, const void* handle64);
+int cedr_b200_p2p_enable(cedr_b200_cdr* cdr, int on);
 /* Host-only view of the partition of make_tree_over_1d_mesh(ncells, imbalanced) with the
  * contiguous cell->rank map, for `rank` of `nranks`: number of owned cells and blocks,
  * the padded block count of the exchange, and for each owned block (up to `cap`) its

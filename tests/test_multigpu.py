@@ -1,0 +1,90 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise): one process per GPU over NCCL, the
+subtree-partitioned QLT and CAAS with both exchange paths -- torch.distributed's NCCL
+all-gather and the peer-to-peer stores over NVLink (cedr_b200_p2p_*) -- against the
+single-rank oracle on the whole problem, bit for bit, over several run() calls (the
+receive buffers alternate by epoch parity)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, ncells, nt, p2p, q):
+    import torch
+    import torch.distributed as dist
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    from oracle.oracle_py import Oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["NCCL_DEBUG"] = "WARN"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    ok = True
+    try:
+        o = Oracle()
+        rhom, lo, qq, hi, prev = W.headline(ncells, nt, 21)
+        pts = [7]*nt
+        tree = o.bisection_tree(ncells)
+        nl = ncells//world
+        sl = slice(rank*nl, (rank + 1)*nl)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a[..., sl])).cuda()
+        for kind in ("qlt", "caas"):
+            if kind == "qlt":
+                c = cb.QLT(ncells, rank=rank, nranks=world)
+                ref = o.qlt(tree, pts, rhom, lo, qq, hi, prev)
+            else:
+                c = cb.CAAS(nl, cell0=rank*nl, ncells_global=ncells, rank=rank, nranks=world)
+                ref = o.caas(ncells, pts, lo, qq, hi, prev, tree=tree)
+            for p in pts:
+                c.declare_tracer(p)
+            c.end_tracer_declarations()
+            c.enable_distributed(world)
+            c.finish_setup()
+            if p2p:
+                c.enable_p2p(world)
+            c.set_rhom(dev(rhom))
+            for rep in range(3):
+                c.set_Qm(dev(qq), dev(lo), dev(hi), dev(prev))
+                c.run()
+                got = c.get_Qm().cpu().numpy()
+                c.synchronize()
+                ok = ok and np.array_equal(got, ref[:, sl])
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("p2p", [False, True])
+def test_two_gpus_bitwise(p2p):
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 1000) + int(p2p)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 5400, 24, p2p, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in out)
