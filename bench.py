@@ -209,6 +209,7 @@ def main():
     # Multi-GPU exchange: direct stores into the peers' buffers over NVLink (default), or
     # torch.distributed's NCCL all-gather (CEDR_B200_NO_P2P=1).
     P2P = world > 1 and not os.environ.get("CEDR_B200_NO_P2P")
+    p2p_used = []
     ncells, nt, cid = workload_dims(args.workload)
     # Subtree partition: rank r owns cells [r*nl, (r+1)*nl) of every tracer.
     if ncells % world:
@@ -231,7 +232,7 @@ def main():
             c.enable_distributed(world)
         c.finish_setup()
         if world > 1 and P2P:
-            c.enable_p2p(world)
+            p2p_used.append(c.enable_p2p(world))
         c.set_rhom(rhom)
         c.set_Qm(q, lo, hi, prev)
         return c
@@ -396,6 +397,9 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks, "kernels_ms": kernels,
             "small_problem": small,
+            "exchange": (None if world == 1 else
+                         "p2p (NVLink stores + epoch flags)" if p2p_used and all(p2p_used)
+                         else "nccl all-gather"),
         }
         print(json.dumps(line))
     if world > 1:

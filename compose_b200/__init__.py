@@ -300,15 +300,32 @@ class CDR:
         """After finish_setup on every rank: swap CUDA IPC handles through
         torch.distributed and switch run()'s exchange to direct stores into the peers'
         buffers over NVLink (no NCCL call inside run())."""
+        import torch
         import torch.distributed as dist
         buf = C.create_string_buffer(64)
-        _check(self._lib.cedr_b200_p2p_get_handle(self._h, buf))
+        ok = 1
+        try:
+            _check(self._lib.cedr_b200_p2p_get_handle(self._h, buf))
+        except CedrError:
+            ok = 0
         handles = [None]*nranks
-        dist.all_gather_object(handles, bytes(buf.raw), group=group)
-        for r, h in enumerate(handles):
-            _check(self._lib.cedr_b200_p2p_set_peer(self._h, r, C.create_string_buffer(h, 64)))
-        _check(self._lib.cedr_b200_p2p_enable(self._h, 1))
-        dist.barrier(group=group)
+        dist.all_gather_object(handles, bytes(buf.raw) if ok else None, group=group)
+        if ok and all(h is not None for h in handles):
+            try:
+                for r, h in enumerate(handles):
+                    _check(self._lib.cedr_b200_p2p_set_peer(self._h, r,
+                                                            C.create_string_buffer(h, 64)))
+            except CedrError:
+                ok = 0
+        else:
+            ok = 0
+        # Every rank must take the same path: peer mapping can fail on one (no IPC in the
+        # container, no peer access); then all keep the all-gather callback.
+        t = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        ok = int(t.item())
+        _check(self._lib.cedr_b200_p2p_enable(self._h, ok))
+        return bool(ok)
 
     def run_phase(self, phase):
         _check(self._lib.cedr_b200_run_phase(self._h, int(phase)))
