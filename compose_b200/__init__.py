@@ -19,7 +19,8 @@ CONSERVE, SHAPEPRESERVE, CONSISTENT, NONNEGATIVE = 1, 2, 4, 8
 CAAS_SUM_TREE, CAAS_SUM_SEQUENTIAL = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcedr_b200.so")
+# CEDR_B200_LIB: a differently built copy of the library (kernel A/B experiments).
+LIB_PATH = os.environ.get("CEDR_B200_LIB") or os.path.join(_HERE, "libcedr_b200.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

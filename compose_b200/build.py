@@ -34,19 +34,22 @@ def _stale():
     return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS if os.path.exists(f))
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, out=None, extra_flags=()):
+    """out / extra_flags: a variant build for kernel A/B experiments (CEDR_B200_LIB)."""
+    if out is None and not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = os.environ.get("CEDR_B200_EXTRA_NVCC_FLAGS", "").split()
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-ccbin", "/usr/bin/g++"] * os.path.exists("/usr/bin/g++") + ["-o", LIB] + SOURCES
+    lib = out or LIB
+    cmd = [nvcc] + NVCC_FLAGS + extra + list(extra_flags) + \
+        (["-Xptxas", "-v"] if verbose else []) + \
+        ["-ccbin", "/usr/bin/g++"] * os.path.exists("/usr/bin/g++") + ["-o", lib] + SOURCES
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout)
     if r.returncode:
-        raise RuntimeError("nvcc failed building %s" % LIB)
-    return LIB
+        raise RuntimeError("nvcc failed building %s" % lib)
+    return lib
 
 
 if __name__ == "__main__":

@@ -512,17 +512,8 @@ down2_kernel (const FastArgs a) {
     ps += __shfl_xor_sync(0xffffffffu, ps, o);
     pe += __shfl_xor_sync(0xffffffffu, pe, o);
   }
-  // Leaf offset | d9x slot << 16 of this lane's (up to two) pairs; d9x slot of depth-9
-  // position p = 4 tid' + q is q*128 + tid' (conflict-free for the owners' stores).
-  unsigned pair_slot[2] = {0xffffffffu, 0xffffffffu};
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int j = ps + lane + 32*q;
-    if (j < pe) {
-      const unsigned p = ptab[j];
-      pair_slot[q] = ((dtab[p] & 0x7fffu) + shift) | (((p & 3)*128 + (p >> 2)) << 16);
-    }
-  }
+  // d9x slot of depth-9 position p = 4 tid' + q is q*128 + tid' (conflict-free for the
+  // owners' stores).
   const dev::NodeWQ c7 = wq[127 + tid], c8a = wq[255 + 2*tid], c8b = wq[256 + 2*tid];
 #ifdef CEDR_B200_FASTDIV
   const double rq7 = rqv[127 + tid], rq8a = rqv[255 + 2*tid], rq8b = rqv[256 + 2*tid];
@@ -554,17 +545,6 @@ down2_kernel (const FastArgs a) {
     CEDR_PHASE(0);
     mbar_wait(&mbar[k & 1], (k >> 1) & 1);
     CEDR_PHASE(1);
-    // Constants of this lane's pairs: issued now, used after the depth-8 solves.
-    dev::NodeWQ cp[2];
-    double rqp[2] = {0, 0};
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-      if (pair_slot[q] != 0xffffffffu) {
-        cp[q] = wq[kHeapNodes + ps + lane + 32*q];
-#ifdef CEDR_B200_FASTDIV
-        rqp[q] = rqv[kHeapNodes + ps + lane + 32*q];
-#endif
-      }
     // Sums of this thread's depth-9 nodes (a leaf or a pair), depth-8 and depth-7 nodes.
     double n9[4][3], n8[2][3], n7[3];
 #pragma unroll
@@ -618,12 +598,11 @@ down2_kernel (const FastArgs a) {
       xout[o] = x0;
       xout[o + 1] = x1;
     };
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-      if (pair_slot[q] != 0xffffffffu)
-        solve_pair(cp[q], rqp[q], ps + lane + 32*q, pair_slot[q] & 0xffff,
-                   pair_slot[q] >> 16);
-    for (int j = ps + lane + 64; j < pe; j += 32) {   // blocks with > 64 pairs per warp
+    // One rolled loop over this lane's pairs, constants fetched as needed (L1 hits): holding
+    // the first two pairs' constants in registers across the depth-7/8 solves, with the two
+    // solves unrolled, cost more in spills and code size than the loads (measured: -5%).
+#pragma unroll 1
+    for (int j = ps + lane; j < pe; j += 32) {
       const int p = ptab[j];
       solve_pair(wq[kHeapNodes + j], rqv[kHeapNodes + j], j, (dtab[p] & 0x7fff) + shift,
                  (p & 3)*128 + (p >> 2));
