@@ -153,7 +153,8 @@ struct cedr_b200_cdr {
   DevBuf<double> in_own, out_own;
   DevBuf<int> d_trcr_row, d_trcr_prob, d_cls_tracers[NCLS];
   DevBuf<int> d_lvlptr, d_kid0, d_kid1;
-  DevBuf<unsigned short> d_dtab, d_ptab, d_fpos;
+  DevBuf<unsigned short> d_dtab, d_ptab, d_fpos, d_perm;
+  DevBuf<unsigned> d_pent;
   DevBuf<FastWQ> d_fwq;
   DevBuf<FastRh> d_frh;
   DevBuf<double> d_frq;
@@ -347,6 +348,8 @@ fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
   a.nblocks = nblocks_dev(c, 0);
   a.dtab = c.d_dtab.p;
   a.ptab = c.d_ptab.p;
+  a.perm = c.d_perm.p;
+  a.pent = c.d_pent.p;
   a.wq = c.d_fwq.p;
   a.rh = c.d_frh.p;
   a.in = c.in;
@@ -995,6 +998,8 @@ void finish_setup (cedr_b200_cdr& c) {
       hb[b].ibase = blk.ibase;
       hb[b].ftab_off = sh.fast ? sh.dev_dtab_off : -1;
       hb[b].fpair_off = sh.dev_ptab_off;
+      hb[b].fperm_off = sh.dev_perm_off;
+      hb[b].fpent_off = sh.dev_pent_off;
       hb[b].fpos_off = sh.dev_fpos_off;
       hb[b].npairs = sh.fast ? static_cast<int>(sh.ptab.size()) : 0;
       hb[b].fbase = blk.ibase;
@@ -1011,6 +1016,8 @@ void finish_setup (cedr_b200_cdr& c) {
   c.d_nc.alloc(std::max(1, c.plan.ninternal));
   c.d_dtab.upload(c.plan.dev_dtab);
   c.d_ptab.upload(c.plan.dev_ptab);
+  c.d_perm.upload(c.plan.dev_perm);
+  c.d_pent.upload(c.plan.dev_pent);
   c.d_fpos.upload(c.plan.dev_fpos);
   if (c.fast_ok) {
     c.d_fwq.alloc(std::max(1, c.plan.ninternal));

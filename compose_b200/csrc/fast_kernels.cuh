@@ -90,6 +90,11 @@ struct FastArgs {
   int nblocks;
   const unsigned short* dtab;   // per shape: 512 depth-9 entries, off | (pair << 15)
   const unsigned short* ptab;   // per shape: pair list (depth-9 positions)
+  // Down-sweep work assignment (tree_plan.cpp build_down_tables), per shape: perm[thread] =
+  // depth-7 node of a leaf thread; pent = [first entry of warp 0..3, end | pair entries],
+  // entry = leaf offset | d9x slot << 11 | pair's const rank << 20.
+  const unsigned short* perm;
+  const unsigned* pent;
   const NodeWQ* wq;             // per block: kHeapNodes + npairs entries, fast order
   const NodeRh* rh;
   const double* in;             // tier-0 rows
@@ -495,28 +500,21 @@ down2_kernel (const FastArgs a) {
   }
 
   // ---------------------------------------------------------------- LEAF warps
-  const ushort4 e = reinterpret_cast<const ushort4*>(dtab)[tid];
+  // This thread's depth-7 node: dealt out so that the leaf offsets of a half-warp's 16
+  // nodes are (nearly) distinct mod 16, the 8-byte shared-memory banks.
+  const int node = a.perm[B.fperm_off + tid];
+  const ushort4 e = reinterpret_cast<const ushort4*>(dtab)[node];
   const int off[4] = {(e.x & 0x7fff) + shift, (e.y & 0x7fff) + shift,
                       (e.z & 0x7fff) + shift, (e.w & 0x7fff) + shift};
   const bool pr[4] = {(e.x >> 15) != 0, (e.y >> 15) != 0, (e.z >> 15) != 0,
                       (e.w >> 15) != 0};
-  // This warp's pairs are ptab[ps .. pe): depth-9 positions in [128 warp, 128 warp + 128).
-  int ps = 0, pe = 0;
-  for (int j = lane; j < B.npairs; j += 32) {
-    const int p = ptab[j];
-    ps += p < 128*warp;
-    pe += p < 128*warp + 128;
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    ps += __shfl_xor_sync(0xffffffffu, ps, o);
-    pe += __shfl_xor_sync(0xffffffffu, pe, o);
-  }
-  // d9x slot of depth-9 position p = 4 tid' + q is q*128 + tid' (conflict-free for the
-  // owners' stores).
-  const dev::NodeWQ c7 = wq[127 + tid], c8a = wq[255 + 2*tid], c8b = wq[256 + 2*tid];
+  // This warp's pairs: the depth-9 pairs below its threads' nodes, pent[ps .. pe). The
+  // solved mass of depth-9 position q of thread t's node goes through d9x[q*128 + t].
+  const unsigned* const pent = a.pent + B.fpent_off;
+  const int ps = pent[warp], pe = pent[warp + 1];
+  const dev::NodeWQ c7 = wq[127 + node], c8a = wq[255 + 2*node], c8b = wq[256 + 2*node];
 #ifdef CEDR_B200_FASTDIV
-  const double rq7 = rqv[127 + tid], rq8a = rqv[255 + 2*tid], rq8b = rqv[256 + 2*tid];
+  const double rq7 = rqv[127 + node], rq8a = rqv[255 + 2*node], rq8b = rqv[256 + 2*node];
 #else
   const double rq7 = 0, rq8a = 0, rq8b = 0;
 #endif
@@ -565,15 +563,15 @@ down2_kernel (const FastArgs a) {
     }
     CEDR_PHASE(2);
     bar_sync<BAR_T, kDown2Threads>(k & 1);       // T(k) published
-    const double x7 = x[127 + tid];
+    const double x7 = x[127 + node];
     bar_arrive<BAR_C, kDown2Threads>(k & 1);     // xs / un of tracer k may be reused
     CEDR_PHASE(3);
     double x8[2];
-    solve(c7, rq7, 127 + tid, n7, x7, n8[0], n8[1], x8[0], x8[1]);
+    solve(c7, rq7, 127 + node, n7, x7, n8[0], n8[1], x8[0], x8[1]);
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       double x9[2];
-      solve(hf ? c8b : c8a, hf ? rq8b : rq8a, 255 + 2*tid + hf, n8[hf], x8[hf], n9[2*hf],
+      solve(hf ? c8b : c8a, hf ? rq8b : rq8a, 255 + 2*node + hf, n8[hf], x8[hf], n9[2*hf],
             n9[2*hf + 1], x9[0], x9[1]);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -603,9 +601,10 @@ down2_kernel (const FastArgs a) {
     // solves unrolled, cost more in spills and code size than the loads (measured: -5%).
 #pragma unroll 1
     for (int j = ps + lane; j < pe; j += 32) {
-      const int p = ptab[j];
-      solve_pair(wq[kHeapNodes + j], rqv[kHeapNodes + j], j, (dtab[p] & 0x7fff) + shift,
-                 (p & 3)*128 + (p >> 2));
+      const unsigned pe_j = pent[j];
+      const int r = pe_j >> 20;
+      solve_pair(wq[kHeapNodes + r], rqv[kHeapNodes + r], r, (pe_j & 0x7ff) + shift,
+                 (pe_j >> 11) & 0x1ff);
     }
     CEDR_PHASE(5);
     // Write-back: the solved leaves sit in block order in xout; one TMA bulk store moves

@@ -1,6 +1,8 @@
 #include "tree_plan.h"
 
 #include <algorithm>
+#include <cmath>
+#include <cstring>
 #include <map>
 #include <sstream>
 #include <stdexcept>
@@ -41,6 +43,90 @@ void bisect (int cs, int ce, bool imbalanced, std::vector<int>& kids,
 }
 
 } // namespace
+
+// Which leaf thread of the down-sweep works on which depth-7 node, and which lane solves
+// which depth-9 pair. A thread reads its micro-subtree's leaves at offsets that advance by
+// the irregular leaf counts of the nodes (5 or 6 for 675 leaves), so with thread = node
+// the 16 lanes of a half-warp -- the unit of a 64-bit shared-memory access, 16 banks of
+// 8 bytes -- hit the same bank up to 5 times (measured 8.75 wavefronts per load against
+// an ideal of 2 at ne120). The leaf threads need no particular order among themselves in
+// the down-sweep (no shuffles), so nodes are dealt to the 8 half-warps such that the leaf
+// offsets within each are as distinct mod 16 as possible: simulated annealing over
+// swaps, on the exact wavefront count of the kernel's 8 leaf accesses (first / second
+// leaf of each of a thread's 4 depth-9 nodes). Deterministic (fixed seed).
+static void build_down_tables (Shape& sh) {
+  const std::vector<unsigned short>& dtab = sh.dtab;
+  auto off9 = [&] (int p) { return dtab[p] & 0x7fff; };
+  auto pair9 = [&] (int p) { return (dtab[p] >> 15) != 0; };
+  // Wavefronts of the 8 accesses for a half-warp of 16 nodes.
+  auto cost = [&] (const int* nodes) {
+    int tot = 0;
+    for (int q = 0; q < 4; ++q)
+      for (int j = 0; j < 2; ++j) {
+        int cnt[16] = {0}, mx = 0;
+        for (int i = 0; i < 16; ++i) {
+          const int p = 4*nodes[i] + q;
+          if (j == 1 && ! pair9(p)) continue;
+          mx = std::max(mx, ++cnt[(off9(p) + j) & 15]);
+        }
+        tot += mx;
+      }
+    return tot;
+  };
+  int g[8][16];
+  for (int i = 0; i < 128; ++i) g[i >> 4][i & 15] = i;
+  int gc[8], cur = 0;
+  for (int k = 0; k < 8; ++k) { gc[k] = cost(g[k]); cur += gc[k]; }
+  int best = cur, bestg[8][16];
+  std::memcpy(bestg, g, sizeof(g));
+  unsigned long long rng = 0x9E3779B97F4A7C15ull;
+  auto next = [&] () { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+  double T = 2.0;
+  for (int it = 0; it < 120000 && best > 64; ++it) {
+    const int g1 = static_cast<int>(next() % 8), g2 = static_cast<int>((g1 + 1 + next() % 7) % 8);
+    const int i1 = static_cast<int>(next() % 16), i2 = static_cast<int>(next() % 16);
+    std::swap(g[g1][i1], g[g2][i2]);
+    const int c1 = cost(g[g1]), c2 = cost(g[g2]);
+    const int d = c1 + c2 - gc[g1] - gc[g2];
+    const double u = (next() >> 11)*(1.0/9007199254740992.0);
+    if (d <= 0 || u < std::exp(-d/T)) {
+      gc[g1] = c1; gc[g2] = c2; cur += d;
+      if (cur < best) { best = cur; std::memcpy(bestg, g, sizeof(g)); }
+    } else {
+      std::swap(g[g1][i1], g[g2][i2]);
+    }
+    T = std::max(0.05, T*0.99995);
+  }
+  sh.perm.resize(128);
+  std::vector<int> thread_of(128);
+  for (int i = 0; i < 128; ++i) {
+    sh.perm[i] = static_cast<unsigned short>(bestg[i >> 4][i & 15]);
+    thread_of[sh.perm[i]] = i;
+  }
+  // Pairs: solved by the warp that owns their depth-7 node, dealt to its lanes 32 at a
+  // time; within a warp ordered so that consecutive entries have distinct leaf offsets
+  // mod 16 (k-th pair of each residue class first).
+  const int np = static_cast<int>(sh.ptab.size());
+  std::vector<std::vector<unsigned> > per_warp(4);
+  std::vector<std::vector<std::pair<int,unsigned> > > keyed(4);
+  int seen[4][16];
+  std::memset(seen, 0, sizeof(seen));
+  for (int r = 0; r < np; ++r) {
+    const int p = sh.ptab[r], owner = thread_of[p >> 2], w = owner >> 5;
+    const unsigned o = off9(p), slot = (p & 3)*128 + owner;
+    const unsigned e = o | (slot << 11) | (static_cast<unsigned>(r) << 20);
+    keyed[w].push_back(std::make_pair(seen[w][o & 15]++*16 + static_cast<int>(o & 15), e));
+  }
+  sh.pent.assign(5, 0);
+  for (int w = 0; w < 4; ++w) {
+    std::stable_sort(keyed[w].begin(), keyed[w].end(),
+                     [] (const std::pair<int,unsigned>& a, const std::pair<int,unsigned>& b) {
+                       return a.first < b.first; });
+    sh.pent[w] = static_cast<unsigned>(sh.pent.size());
+    for (size_t i = 0; i < keyed[w].size(); ++i) sh.pent.push_back(keyed[w][i].second);
+  }
+  sh.pent[4] = static_cast<unsigned>(sh.pent.size());
+}
 
 // Try to describe `sh` as "perfect to depth 9, leaves or pairs below" (see
 // fast_kernels.cuh). Leaves sh.fast false if it is not of that form.
@@ -102,6 +188,7 @@ static void build_fast_tables (Shape& sh) {
   sh.ptab.swap(ptab);
   sh.fpos.swap(fpos);
   sh.fast = true;
+  build_down_tables(sh);
 }
 
 void make_bisection_tree (int ncells, bool imbalanced, std::vector<int>& kids,
@@ -130,6 +217,8 @@ void Plan::build (int ncells_, int nnodes, int root, const int* kids,
   dev_dtab.clear();
   dev_ptab.clear();
   dev_fpos.clear();
+  dev_perm.clear();
+  dev_pent.clear();
   tier0_fast = false;
 
   // ---- DFS: leaf order (= the reference's lci), post-order, heights.
@@ -293,6 +382,10 @@ void Plan::build (int ncells_, int nnodes, int root, const int* kids,
           // keep ptab/dtab offsets even so ushort4 loads stay aligned
           while (dev_ptab.size() % 4) dev_ptab.push_back(0);
           dev_fpos.insert(dev_fpos.end(), sh.fpos.begin(), sh.fpos.end());
+          sh.dev_perm_off = static_cast<int>(dev_perm.size());
+          dev_perm.insert(dev_perm.end(), sh.perm.begin(), sh.perm.end());
+          sh.dev_pent_off = static_cast<int>(dev_pent.size());
+          dev_pent.insert(dev_pent.end(), sh.pent.begin(), sh.pent.end());
         }
         sh.dev_lvlptr_off = static_cast<int>(dev_lvlptr.size());
         sh.dev_kid_off = static_cast<int>(dev_kid0.size());

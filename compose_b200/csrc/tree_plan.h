@@ -46,7 +46,14 @@ struct Shape {
   std::vector<unsigned short> dtab;  // [512] leaf offset | (is pair << 15)
   std::vector<unsigned short> ptab;  // depth-9 positions of the pairs, increasing
   std::vector<unsigned short> fpos;  // [ni] internal node j -> fast const position
-  int dev_dtab_off = 0, dev_ptab_off = 0, dev_fpos_off = 0;
+  // Down-sweep work assignment chosen to avoid shared-memory bank conflicts (see
+  // build_down_tables in tree_plan.cpp): perm[thread] = depth-7 node of a leaf thread;
+  // pent = [start of warp 0..3's pair entries, end | entries], an entry being
+  // leaf offset | d9x slot << 11 | pair's const rank << 20.
+  std::vector<unsigned short> perm;
+  std::vector<unsigned> pent;
+  int dev_dtab_off = 0, dev_ptab_off = 0, dev_fpos_off = 0, dev_perm_off = 0,
+    dev_pent_off = 0;
 };
 
 struct Block {
@@ -76,7 +83,8 @@ struct Plan {
 
   // Packed topology for the device.
   std::vector<int> dev_lvlptr, dev_kid0, dev_kid1;
-  std::vector<unsigned short> dev_dtab, dev_ptab, dev_fpos;
+  std::vector<unsigned short> dev_dtab, dev_ptab, dev_fpos, dev_perm;
+  std::vector<unsigned> dev_pent;
   // True if every tier-0 block has a fast shape (then the fast kernels can run it).
   bool tier0_fast = false;
 
