@@ -73,24 +73,47 @@ static void build_down_tables (Shape& sh) {
       }
     return tot;
   };
+  // Pairs are solved 32 at a time by the warp that owns their nodes: the number of such
+  // rounds, sum over warps of ceil(pairs / 32), comes first (nodes with few pairs dealt
+  // together; a round is a whole node problem for the warp, a conflict one wavefront).
+  auto npairs_of = [&] (int n) {
+    return static_cast<int>(pair9(4*n)) + pair9(4*n + 1) + pair9(4*n + 2) + pair9(4*n + 3);
+  };
+  const int kRound = 200;
+  auto rounds = [&] (const int* h0, const int* h1) {
+    int np = 0;
+    for (int i = 0; i < 16; ++i) np += npairs_of(h0[i]) + npairs_of(h1[i]);
+    return (np + 31)/32;
+  };
   int g[8][16];
-  for (int i = 0; i < 128; ++i) g[i >> 4][i & 15] = i;
-  int gc[8], cur = 0;
+  {
+    std::vector<int> order(128);
+    for (int i = 0; i < 128; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(),
+                     [&] (int x, int y) { return npairs_of(x) < npairs_of(y); });
+    for (int i = 0; i < 128; ++i) g[i >> 4][i & 15] = order[i];
+  }
+  // gc[k]: wavefronts of half-warp k; wc[w]: pair rounds of warp w (half-warps 2w, 2w+1).
+  int gc[8], wc[4], cur = 0;
   for (int k = 0; k < 8; ++k) { gc[k] = cost(g[k]); cur += gc[k]; }
+  for (int w = 0; w < 4; ++w) { wc[w] = rounds(g[2*w], g[2*w + 1]); cur += kRound*wc[w]; }
   int best = cur, bestg[8][16];
   std::memcpy(bestg, g, sizeof(g));
   unsigned long long rng = 0x9E3779B97F4A7C15ull;
   auto next = [&] () { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
   double T = 2.0;
-  for (int it = 0; it < 120000 && best > 64; ++it) {
+  for (int it = 0; it < 150000; ++it) {
     const int g1 = static_cast<int>(next() % 8), g2 = static_cast<int>((g1 + 1 + next() % 7) % 8);
     const int i1 = static_cast<int>(next() % 16), i2 = static_cast<int>(next() % 16);
     std::swap(g[g1][i1], g[g2][i2]);
     const int c1 = cost(g[g1]), c2 = cost(g[g2]);
-    const int d = c1 + c2 - gc[g1] - gc[g2];
+    const int w1 = g1 >> 1, w2 = g2 >> 1;
+    const int r1 = rounds(g[2*w1], g[2*w1 + 1]), r2 = rounds(g[2*w2], g[2*w2 + 1]);
+    const int d = c1 + c2 - gc[g1] - gc[g2] +
+      (w1 == w2 ? 0 : kRound*(r1 + r2 - wc[w1] - wc[w2]));
     const double u = (next() >> 11)*(1.0/9007199254740992.0);
     if (d <= 0 || u < std::exp(-d/T)) {
-      gc[g1] = c1; gc[g2] = c2; cur += d;
+      gc[g1] = c1; gc[g2] = c2; wc[w1] = r1; wc[w2] = r2; cur += d;
       if (cur < best) { best = cur; std::memcpy(bestg, g, sizeof(g)); }
     } else {
       std::swap(g[g1][i1], g[g2][i2]);
