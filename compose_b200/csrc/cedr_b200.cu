@@ -772,6 +772,38 @@ void exchange_allgather (cedr_b200_cdr& c) {
   cedr_b200_throw_if(e != 0, "the all-gather callback failed with code " << e);
 }
 
+// One small block is the whole problem: run() is a single launch (solo_kernel).
+constexpr int kSoloMaxLeaves = 256;
+
+bool solo_ok (const cedr_b200_cdr& c) {
+  return c.nranks == 1 && c.plan.tiers.size() == 1 && c.plan.tiers[0].blocks.size() == 1 &&
+    c.plan.tiers[0].max_nl <= kSoloMaxLeaves && ! std::getenv("CEDR_B200_NO_SOLO") &&
+    (! c.is_caas || c.caas_sum_mode == CEDR_B200_CAAS_SUM_TREE);
+}
+
+template <int CLS> void launch_solo_cls (cedr_b200_cdr& c, int cls) {
+  const SweepArgs a = base_args(c, cls, 0);
+  if (a.ntr == 0) return;
+  const size_t nn = 2*static_cast<size_t>(c.plan.tiers[0].max_nl);
+  const size_t smem = sizeof(double)*(5*nn + 2) + sizeof(dev::NodeConst)*nn;
+  LaunchTimer lt(c, CEDR_B200_TAG_TOP, 0);
+  solo_kernel<CLS><<<a.ntr, kThreads, smem, c.stream>>>(a);
+  CUDA_CHECK(cudaGetLastError());
+  ++c.last_launches;
+}
+
+void launch_solo (cedr_b200_cdr& c, int cls) {
+  switch (cls) {
+  case CLS_ST: launch_solo_cls<CLS_ST>(c, cls); break;
+  case CLS_CST: launch_solo_cls<CLS_CST>(c, cls); break;
+  case CLS_T: launch_solo_cls<CLS_T>(c, cls); break;
+  case CLS_CT: launch_solo_cls<CLS_CT>(c, cls); break;
+  case CLS_NN: launch_solo_cls<CLS_NN>(c, cls); break;
+  case CLS_CNN: launch_solo_cls<CLS_CNN>(c, cls); break;
+  case CLS_CAAS: launch_solo_cls<CLS_CAAS>(c, cls); break;
+  }
+}
+
 // QLT::run, cedr_qlt.cpp:618-640. phase < 0: everything (one rank: no exchange);
 // phase 0: up to the exchange message; phase 1: from the gathered messages on.
 void run_qlt (cedr_b200_cdr& c, int phase) {
@@ -783,6 +815,11 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
     return c.split && c.fast_ok && fast_class(cls, MODE_DOWN) &&
       ! (c.fused_ok && fused_class(cls));
   };
+  if (solo_ok(c)) {
+    for (int cls = 0; cls < CLS_CAAS; ++cls)
+      if ( ! c.cls_tracers[cls].empty()) launch_solo(c, cls);
+    return;
+  }
   if (phase <= 0) {
     run_rhom(c, 0, multi ? 1 : ntiers);
     if ( ! multi) run_rhom_x(c);
@@ -839,6 +876,7 @@ void run_caas (cedr_b200_cdr& c, int phase) {
     return;
   }
   if (c.fused_ok) { launch_fused(c, CLS_CAAS); return; }
+  if (solo_ok(c)) { launch_solo(c, CLS_CAAS); return; }
   const int ntiers = static_cast<int>(c.plan.tiers.size());
   const int top = ntiers - 1;
   if (phase <= 0 && multi) {

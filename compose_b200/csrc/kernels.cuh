@@ -81,7 +81,8 @@ struct SweepArgs {
 // 4*(nl + ni) doubles. Contains __syncthreads: every thread of the CTA must call it.
 template <int CLS, int MODE>
 __device__ __forceinline__ void
-sweep_block (const SweepArgs& a, const int b, const int t, double* const sm) {
+sweep_block (const SweepArgs& a, const int b, const int t, double* const sm,
+             const dev::NodeConst* const nc_block = nullptr) {
   constexpr bool caas = CLS == CLS_CAAS;
   constexpr bool bfb = CLS == CLS_BFB;
   constexpr bool nonneg = CLS == CLS_NN || CLS == CLS_CNN || bfb;   // one word: row 0
@@ -227,7 +228,7 @@ sweep_block (const SweepArgs& a, const int b, const int t, double* const sm) {
   __syncthreads();
 
   // Down-sweep: parents before kids.
-  const dev::NodeConst* const nc = a.nc + B.ibase;
+  const dev::NodeConst* const nc = nc_block ? nc_block : a.nc + B.ibase;
   const bool prefer = a.prefer_mass_con != 0;
   for (int l = B.nlev - 1; l >= 0; --l) {
     const int je = lvlptr[l+1];
@@ -263,6 +264,62 @@ __global__ void __launch_bounds__(256)
 sweep_kernel (const SweepArgs a) {
   extern __shared__ double sm[];
   sweep_block<CLS, MODE>(a, blockIdx.x % a.nblocks, a.tracers[blockIdx.x / a.nblocks], sm);
+}
+
+// A whole run() in ONE launch for problems that are a single small block (the whole tree
+// in one tier: cedr_test_1d_transport's 111 cells, the randomized unit test's trees): one
+// CTA per tracer forms the rhom sums and node constants of the block in shared memory
+// (what rhom_kernel leaves in global memory for larger problems; the same operations),
+// sweeps the block up and down (QLT), or forms the four sums and adjusts the block's
+// cells (CAAS). These problems are launch-latency bound: one launch instead of two.
+// Shared memory: 4 (nl + ni) doubles for the sweep, then nl + ni doubles of rhom sums,
+// then ni node constants.
+template <int CLS>
+__global__ void __launch_bounds__(256)
+solo_kernel (const SweepArgs a) {
+  extern __shared__ double sm[];
+  const int t = a.tracers[blockIdx.x];
+  const BlockDev B = a.blocks[0];
+  const int nn = B.nl + B.ni, tid = threadIdx.x, nth = blockDim.x;
+  if (CLS == CLS_CAAS) {
+    sweep_block<CLS_CAAS, MODE_TOP>(a, 0, t, sm);
+    __syncthreads();
+    // CAAS::finish_locally (cedr_caas.cpp:211-253) on this tracer's cells.
+    const double mode = a.caas_scal[2*t], fac = a.caas_scal[2*t+1];
+    double* const row = const_cast<double*>(a.in) + (long long) a.trcr_row[t]*a.in_ld + B.leaf0;
+    for (int i = tid; i < B.nl; i += nth) {
+      const double lo = row[i], hi = row[2*a.in_ld + i];
+      double q = dev::rmin(hi, dev::rmax(lo, row[a.in_ld + i]));
+      if (mode < 0) { q += fac*(q - lo); q = dev::rmax(lo, q); }
+      else if (mode > 0) { q += fac*(hi - q); q = dev::rmin(hi, q); }
+      row[a.in_ld + i] = q;
+    }
+    return;
+  }
+  double* const rh = sm + 4*nn;
+  dev::NodeConst* const nc = reinterpret_cast<dev::NodeConst*>(rh + nn + (nn & 1));
+  for (int i = tid; i < B.nl; i += nth) rh[i] = a.in[B.leaf0 + i];   // row 0: rhom
+  __syncthreads();
+  const int* const lvlptr = a.lvlptr + B.lvlptr_off;
+  const int* const kid0 = a.kid0 + B.kid_off;
+  const int* const kid1 = a.kid1 + B.kid_off;
+  for (int l = 0; l < B.nlev; ++l) {
+    const int je = lvlptr[l+1];
+    for (int j = lvlptr[l] + tid; j < je; j += nth) {
+      const double rh0 = rh[kid0[j]], rh1 = rh[kid1[j]];
+      rh[B.nl + j] = rh0 + rh1;
+      dev::NodeConst c;
+      c.w0 = 1/rh0;
+      c.w1 = 1/rh1;
+      c.q0 = 1/c.w0;
+      c.q1 = 1/c.w1;
+      c.rh0 = rh0;
+      c.rh1 = rh1;
+      nc[j] = c;
+    }
+    __syncthreads();
+  }
+  sweep_block<CLS, MODE_TOP>(a, 0, t, sm, nc);
 }
 
 // rhom sweep: word 0 of every slot in the reference (cedr_qlt.cpp:356-360),

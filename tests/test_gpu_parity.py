@@ -161,6 +161,32 @@ def test_caas_headline_inputs_bitwise(oracle):
     assert np.all(got >= lo) and np.all(got <= hi)
 
 
+@pytest.mark.parametrize("ncells", [1, 2, 21, 111, 256])
+def test_single_block_problems_run_in_one_launch(oracle, ncells, monkeypatch):
+    """A tree that is one small block (cedr_test_1d_transport's 111 cells, the randomized
+    unit test's trees) runs as ONE launch per problem class (solo_kernel: rhom sums, node
+    constants and the sweep in one CTA per tracer); bits equal to the oracle and to the
+    two-launch path."""
+    import os
+    from compose_b200 import workloads as W
+    from gpu_util import run_qlt_gpu, run_caas_gpu
+    nt = 5
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, 4)
+    pts = [7]*nt
+    tree = oracle.bisection_tree(ncells)
+    got, c = run_qlt_gpu(ncells, pts, rhom, lo, q, hi, prev)
+    assert c.last_run_launches() == 1
+    assert np.array_equal(got, oracle.qlt(tree, pts, rhom, lo, q, hi, prev))
+    gotc, c = run_caas_gpu(ncells, pts, rhom, lo, q, hi, prev)
+    assert c.last_run_launches() == 1
+    assert np.array_equal(gotc, oracle.caas(ncells, pts, lo, q, hi, prev, tree=tree))
+    monkeypatch.setenv("CEDR_B200_NO_SOLO", "1")
+    got2, c = run_qlt_gpu(ncells, pts, rhom, lo, q, hi, prev)
+    assert c.last_run_launches() >= 2 and np.array_equal(got, got2)
+    gotc2, c = run_caas_gpu(ncells, pts, rhom, lo, q, hi, prev)
+    assert c.last_run_launches() >= 2 and np.array_equal(gotc, gotc2)
+
+
 def test_errors_mirror_reference():
     import compose_b200 as cb
     q = cb.QLT(8)
