@@ -169,6 +169,7 @@ struct cedr_b200_cdr {
   // Expanded tier above the fast blocks (FastArgs::split): its leaves are the 2^split
   // depth-`split` nodes of every tier-0 block; one block, swept by the generic kernels.
   int split = 0;
+  bool x_tier = false;        // the expanded tier exists (one rank); else the split is local
   int x_nl = 0, x_ni = 0;
   long long x_ld = 0;
   DevBuf<BlockDev> d_xblock;
@@ -557,7 +558,7 @@ void run_rhom (cedr_b200_cdr& c, int k0, int k1) {
 // rhom sums and node constants of the expanded tier, from the sub-root rhom the tier-0
 // rhom sweep left in d_xrhom.
 void run_rhom_x (cedr_b200_cdr& c) {
-  if ( ! c.split) return;
+  if ( ! c.split || ! c.x_tier) return;
   RhomArgs a;
   std::memset(&a, 0, sizeof(a));
   a.blocks = c.d_xblock.p;
@@ -615,11 +616,23 @@ void build_split (cedr_b200_cdr& c) {
   if ( ! c.fast_ok || c.is_caas || std::getenv("CEDR_B200_NO_SPLIT")) return;
   if (c.plan.tiers.size() != 2 || c.plan.tiers[1].blocks.size() != 1) return;
   const int nl = c.plan.tiers[1].nleaves;
+  // Multi-rank runs exchange block roots (the expanded tier would multiply the message by
+  // 2^S and its replicated sweep does not shrink with the rank count): the split is local,
+  // depths 0..S-1 of the OWN blocks are summed / solved by the mid kernels either side of
+  // the replicated tier-1 sweep (run_qlt).
+  if (c.nranks > 1) {
+    if (std::getenv("CEDR_B200_NO_MULTI_SPLIT")) return;
+    c.split = 3;
+    c.x_tier = false;
+    c.x_ld = round_up(static_cast<long long>(8)*nl, 16);
+    const size_t nt = std::max<size_t>(1, c.trcr_prob.size());
+    c.d_xrhom.alloc(c.x_ld);
+    c.d_xrec.alloc(4*nt*c.x_ld);
+    c.d_xsol.alloc(nt*c.x_ld);
+    return;
+  }
   const int S = 8*nl <= 2048 ? 3 : 4*nl <= 2048 ? 2 : 0;
   if (S == 0) return;
-  // Multi-rank runs exchange block roots (the expanded tier would multiply the message by
-  // 2^S and its replicated sweep does not shrink with the rank count).
-  if (c.nranks > 1) return;
   const Shape& s1 = c.plan.shapes[c.plan.tiers[1].blocks[0].shape];
   const int E = 1 << S, nx = (E - 1)*nl;     // expansion nodes
   Shape x;
@@ -671,6 +684,7 @@ void build_split (cedr_b200_cdr& c) {
   bd.gidx = 0;
   c.d_xblock.upload(std::vector<BlockDev>(1, bd));
   c.split = S;
+  c.x_tier = true;
   c.x_nl = x.nl;
   c.x_ni = x.ni;
   c.x_ld = round_up(x.nl, 16);
@@ -705,11 +719,9 @@ int grid_for (long long n) {
 // This rank's tier-0 block roots -> the exchange message.
 void exchange_pack (cedr_b200_cdr& c, bool with_rhom) {
   LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 0);
-  const int E = 1 << c.split;
   pack_kernel<<<grid_for(exchange_count(c)), kThreads, 0, c.stream>>>(
-    c.d_blocks[0].p, nblocks_dev(c, 0), c.nown_max, static_cast<int>(c.trcr_prob.size()), E,
-    with_rhom ? (c.split ? c.d_xrhom.p : c.d_rhom_tier[1].p) : nullptr,
-    c.split ? c.d_xrec.p : c.d_rec[1].p, c.split ? c.x_ld : c.tier_ld[1], c.xsend);
+    c.d_blocks[0].p, nblocks_dev(c, 0), c.nown_max, static_cast<int>(c.trcr_prob.size()), 1,
+    with_rhom ? c.d_rhom_tier[1].p : nullptr, c.d_rec[1].p, c.tier_ld[1], c.xsend);
   CUDA_CHECK(cudaGetLastError());
   ++c.last_launches;
 }
@@ -717,11 +729,9 @@ void exchange_pack (cedr_b200_cdr& c, bool with_rhom) {
 // Every rank's message -> the (replicated) tier-1 leaves.
 void exchange_unpack (cedr_b200_cdr& c, bool with_rhom) {
   LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 1);
-  const int E = 1 << c.split;
   unpack_kernel<<<grid_for(exchange_count(c)*c.nranks), kThreads, 0, c.stream>>>(
-    c.xrecv, c.nranks, c.nown_max, static_cast<int>(c.trcr_prob.size()), E,
-    with_rhom ? (c.split ? c.d_xrhom.p : c.d_rhom_tier[1].p) : nullptr,
-    c.split ? c.d_xrec.p : c.d_rec[1].p, c.split ? c.x_ld : c.tier_ld[1],
+    c.xrecv, c.nranks, c.nown_max, static_cast<int>(c.trcr_prob.size()), 1,
+    with_rhom ? c.d_rhom_tier[1].p : nullptr, c.d_rec[1].p, c.tier_ld[1],
     static_cast<long long>(exchange_count(c)));
   CUDA_CHECK(cudaGetLastError());
   ++c.last_launches;
@@ -743,13 +753,11 @@ void exchange_p2p (cedr_b200_cdr& c, bool with_rhom) {
     pp.flags[r] = reinterpret_cast<unsigned long long*>(base);
     pp.recv[r] = base + 64 + parity*cnt*c.nranks;
   }
-  const int E = 1 << c.split;
   {
     LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 0);
     pack_p2p_kernel<<<grid_for(cnt), kThreads, 0, c.stream>>>(
-      c.d_blocks[0].p, nblocks_dev(c, 0), c.nown_max, static_cast<int>(c.trcr_prob.size()), E,
-      with_rhom ? (c.split ? c.d_xrhom.p : c.d_rhom_tier[1].p) : nullptr,
-      c.split ? c.d_xrec.p : c.d_rec[1].p, c.split ? c.x_ld : c.tier_ld[1], pp, c.rank,
+      c.d_blocks[0].p, nblocks_dev(c, 0), c.nown_max, static_cast<int>(c.trcr_prob.size()), 1,
+      with_rhom ? c.d_rhom_tier[1].p : nullptr, c.d_rec[1].p, c.tier_ld[1], pp, c.rank,
       c.nranks, static_cast<long long>(cnt));
     CUDA_CHECK(cudaGetLastError());
     ++c.last_launches;
@@ -770,6 +778,24 @@ void exchange_allgather (cedr_b200_cdr& c) {
                      "(cedr_b200_set_allgather)");
   const int e = c.allgather(c.allgather_ctx, c.xsend, c.xrecv, exchange_count(c), c.stream);
   cedr_b200_throw_if(e != 0, "the all-gather callback failed with code " << e);
+}
+
+// Depths 0..S-1 of this rank's own fast blocks, either side of the replicated tier-1 sweep
+// (multi-rank, local split): sub-root records -> block-root records, and block-root
+// masses -> sub-root masses.
+void launch_mid (cedr_b200_cdr& c, int cls, bool down) {
+  const fast::FastArgs a = fast_args(c, cls);
+  if (a.ntr == 0 || a.nblocks == 0) return;
+  const long long n = static_cast<long long>(a.nblocks)*a.ntr;
+  LaunchTimer lt(c, down ? CEDR_B200_TAG_DOWN : CEDR_B200_TAG_UP, 1);
+  if (down)
+    fast::mid_down_kernel<<<grid_for(n), kThreads, 0, c.stream>>>(
+      a, c.d_sol[1].p, c.tier_ld[1], cls == CLS_CST);
+  else
+    fast::mid_up_kernel<<<grid_for(n), kThreads, 0, c.stream>>>(
+      a, c.d_rec[1].p, c.tier_ld[1], cls == CLS_CST);
+  CUDA_CHECK(cudaGetLastError());
+  ++c.last_launches;
 }
 
 // One small block is the whole problem: run() is a single launch (solo_kernel).
@@ -812,7 +838,7 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
   const bool multi = c.nranks > 1;
   // Classes on the fast kernels hand their blocks' sub-roots to the expanded tier.
   auto via_x = [&] (int cls) {
-    return c.split && c.fast_ok && fast_class(cls, MODE_DOWN) &&
+    return c.split && c.x_tier && c.fast_ok && fast_class(cls, MODE_DOWN) &&
       ! (c.fused_ok && fused_class(cls));
   };
   if (solo_ok(c)) {
@@ -820,12 +846,19 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
       if ( ! c.cls_tracers[cls].empty()) launch_solo(c, cls);
     return;
   }
+  // Multi-rank: the fast classes' blocks are split locally (build_split).
+  auto local_split = [&] (int cls) {
+    return c.split && ! c.x_tier && c.fast_ok && fast_class(cls, MODE_DOWN);
+  };
   if (phase <= 0) {
     run_rhom(c, 0, multi ? 1 : ntiers);
     if ( ! multi) run_rhom_x(c);
     if (multi) {
       for (int cls = 0; cls < CLS_CAAS; ++cls)
-        if ( ! c.cls_tracers[cls].empty()) launch_up(c, cls, 0);
+        if ( ! c.cls_tracers[cls].empty()) {
+          launch_up(c, cls, 0);
+          if (local_split(cls)) launch_mid(c, cls, false);
+        }
       if (c.p2p_on && phase < 0) exchange_p2p(c, true); else exchange_pack(c, true);
     }
   }
@@ -833,7 +866,7 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
   if (phase != 0) {
     if (multi) {
       exchange_unpack(c, true);
-      if (c.split) run_rhom_x(c); else run_rhom(c, 1, ntiers);
+      run_rhom(c, 1, ntiers);
     }
     for (int cls = 0; cls < CLS_CAAS; ++cls) {
       if (c.cls_tracers[cls].empty()) continue;
@@ -846,7 +879,10 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
       }
       for (int k = multi ? 1 : 0; k < top; ++k) launch_up(c, cls, k);
       launch_sweep_any(c, cls, top, MODE_TOP, base_args(c, cls, top));
-      for (int k = top - 1; k >= 0; --k) launch_down(c, cls, k);
+      for (int k = top - 1; k >= 0; --k) {
+        if (k == 0 && multi && local_split(cls)) launch_mid(c, cls, true);
+        launch_down(c, cls, k);
+      }
     }
   }
 }

@@ -324,6 +324,113 @@ up_kernel (const FastArgs a) {
   }
 }
 
+// ----------------------------------------------------------------------- MID
+//
+// Multi-rank runs with split = 3: the ranks exchange BLOCK-ROOT records, so depths 0..2 of
+// a rank's own blocks are handled here, one thread per (own block, tracer), either side of
+// the replicated tier-1 sweep. The 8 sub-root records of a block x tracer are 8 consecutive
+// doubles per field in a.rec_out (written by up_kernel); sums pairwise in tree order.
+struct MidSums { double s2[4][3], s1[2][3], s0[3]; };
+
+__device__ __forceinline__ void mid_load (const FastArgs& a, const int t, const int gidx,
+                                          double (&sub)[8][3], MidSums& m) {
+  const double* const r = a.rec_out + static_cast<long long>(t)*4*a.rec_ld +
+    static_cast<long long>(gidx)*8;
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    const double* const rf = r + f*a.rec_ld;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(rf + j));
+      sub[j][f] = v.x; sub[j + 1][f] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m.s2[j][f] = sub[2*j][f] + sub[2*j + 1][f];
+    m.s1[0][f] = m.s2[0][f] + m.s2[1][f];
+    m.s1[1][f] = m.s2[2][f] + m.s2[3][f];
+    m.s0[f] = m.s1[0][f] + m.s1[1][f];
+  }
+}
+
+__device__ __forceinline__ void
+mid_solve (const dev::NodeWQ& c, const double rq, const dev::NodeRh* rh, const bool prefer,
+           const double pmin, const double pqm, const double pmax, const double b,
+           const double lo0, const double y0, const double hi0, const double lo1,
+           const double y1, const double hi1, double& x0, double& x1) {
+  if (prefer)
+    dev::solve_bounded_lean<true>(c, rq, rh, pmin, pqm, pmax, b, lo0, y0, hi0, lo1, y1, hi1,
+                                  x0, x1);
+  else
+    dev::solve_bounded_lean<false>(c, rq, rh, pmin, pqm, pmax, b, lo0, y0, hi0, lo1, y1, hi1,
+                                   x0, x1);
+}
+
+// Block-root records (QLT::l2r_combine_kid_data, cedr_qlt.cpp:339-430, depths 2..0) for the
+// tier above: rec1[(4 t + f) ld1 + gidx].
+__global__ void __launch_bounds__(256)
+mid_up_kernel (const FastArgs a, double* rec1, const long long ld1, const bool has_prev) {
+  const long long n = static_cast<long long>(a.nblocks)*a.ntr;
+  for (long long k = blockIdx.x*static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<long long>(gridDim.x)*blockDim.x) {
+    const int b = static_cast<int>(k % a.nblocks), t = a.tracers[k / a.nblocks];
+    const int gidx = a.blocks[b].gidx;
+    double sub[8][3];
+    MidSums m;
+    mid_load(a, t, gidx, sub, m);
+    double* const o = rec1 + static_cast<long long>(t)*4*ld1 + gidx;
+#pragma unroll
+    for (int f = 0; f < 3; ++f) o[f*ld1] = m.s0[f];
+    if (has_prev) {
+      const double* const rp = a.rec_out + (static_cast<long long>(t)*4 + 3)*a.rec_ld +
+        static_cast<long long>(gidx)*8;
+      double p[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p[j] = __ldcg(rp + j);
+      o[3*ld1] = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+    }
+  }
+}
+
+// Node problems of depths 0..2 (QLT::r2l_solve_qp, cedr_qlt.cpp:490-604): the block root's
+// solved mass sol1[t ld1 + gidx] -> the 8 sub-root masses a.sol_in[t sol_in_ld + 8 gidx + j]
+// that down2_kernel starts from.
+__global__ void __launch_bounds__(256)
+mid_down_kernel (const FastArgs a, const double* sol1, const long long ld1, const bool) {
+  const long long n = static_cast<long long>(a.nblocks)*a.ntr;
+  const bool prefer = a.prefer_mass_con != 0;
+  for (long long k = blockIdx.x*static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<long long>(gridDim.x)*blockDim.x) {
+    const int b = static_cast<int>(k % a.nblocks), t = a.tracers[k / a.nblocks];
+    const BlockDev B = a.blocks[b];
+    const dev::NodeWQ* const wq = a.wq + B.fbase;
+    const dev::NodeRh* const rh = a.rh + B.fbase;
+    double sub[8][3];
+    MidSums m;
+    mid_load(a, t, B.gidx, sub, m);
+    const double x0 = __ldcg(sol1 + static_cast<long long>(t)*ld1 + B.gidx);
+    double x1[2], x2[4], x3[8];
+    mid_solve(wq[0], 0.0, rh, prefer, m.s0[0], m.s0[1], m.s0[2], x0,
+                               m.s1[0][0], m.s1[0][1], m.s1[0][2],
+                               m.s1[1][0], m.s1[1][1], m.s1[1][2], x1[0], x1[1]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      mid_solve(wq[1 + j], 0.0, rh + 1 + j, prefer, m.s1[j][0], m.s1[j][1],
+                                 m.s1[j][2], x1[j], m.s2[2*j][0], m.s2[2*j][1], m.s2[2*j][2],
+                                 m.s2[2*j + 1][0], m.s2[2*j + 1][1], m.s2[2*j + 1][2],
+                                 x2[2*j], x2[2*j + 1]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      mid_solve(wq[3 + j], 0.0, rh + 3 + j, prefer, m.s2[j][0], m.s2[j][1],
+                                 m.s2[j][2], x2[j], sub[2*j][0], sub[2*j][1], sub[2*j][2],
+                                 sub[2*j + 1][0], sub[2*j + 1][1], sub[2*j + 1][2],
+                                 x3[2*j], x3[2*j + 1]);
+    double* const o = const_cast<double*>(a.sol_in) + static_cast<long long>(t)*a.sol_in_ld +
+      static_cast<long long>(B.gidx)*8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = x3[j];
+  }
+}
+
 // ---------------------------------------------------------------------- DOWN
 //
 // QLT::r2l_solve_qp (cedr_qlt.cpp:490-604) over a fast-path block for the
