@@ -1720,6 +1720,38 @@ int cedr_b200_plan_probe (int ncells, int nnodes, int root, const int* kids,
       leaf.swap(next);
     }
     cedr_b200_throw_if(leaf.size() != 1, "top tier must have one block");
+    // Work-assignment tables of the fast shapes (tree_plan.cpp build_down_tables): every
+    // depth-7 node has one leaf thread, every pair one entry, in the warp of its owner.
+    for (const Shape& sh : plan.shapes) {
+      if ( ! sh.fast) continue;
+      std::vector<int> thread_of(128, -1);
+      cedr_b200_throw_if(sh.perm.size() != 128, "perm size");
+      for (int i = 0; i < 128; ++i) {
+        cedr_b200_throw_if(sh.perm[i] >= 128 || thread_of[sh.perm[i]] >= 0,
+                           "perm is not a permutation");
+        thread_of[sh.perm[i]] = i;
+      }
+      const int np = static_cast<int>(sh.ptab.size());
+      cedr_b200_throw_if(sh.pent.size() != static_cast<size_t>(5 + np) || sh.pent[0] != 5 ||
+                         sh.pent[4] != static_cast<unsigned>(5 + np), "pair entry table size");
+      std::vector<int> seen(std::max(1, np), 0);
+      for (int w = 0; w < 4; ++w) {
+        cedr_b200_throw_if(sh.pent[w] > sh.pent[w + 1], "pair entry ranges");
+        for (unsigned j = sh.pent[w]; j < sh.pent[w + 1]; ++j) {
+          const unsigned e = sh.pent[j], o = e & 0x7ff, slot = (e >> 11) & 0x1ff, r = e >> 20;
+          cedr_b200_throw_if(static_cast<int>(r) >= np, "pair rank out of range");
+          const int p = sh.ptab[r], owner = slot & 127;
+          ++seen[r];
+          cedr_b200_throw_if((sh.dtab[p] >> 15) == 0 || o != (sh.dtab[p] & 0x7fffu),
+                             "pair entry does not match its depth-9 node");
+          cedr_b200_throw_if(static_cast<int>(slot >> 7) != (p & 3) ||
+                             sh.perm[owner] != (p >> 2) || (owner >> 5) != w,
+                             "pair entry is not in the warp that owns its node");
+        }
+      }
+      for (int r = 0; r < np; ++r)
+        cedr_b200_throw_if(seen[r] != 1, "pair not assigned exactly once");
+    }
     for (int i = 0; i < plan.ninternal; ++i)
       cedr_b200_throw_if(internal_used[i] != 1, "internal node not used exactly once");
     if (idsum) *idsum = leaf[0];

@@ -10,8 +10,11 @@
 //   - a tracer's leaf rows are staged into shared memory by TMA bulk copies
 //     (cp.async.bulk + mbarrier), double-buffered so tracer i+1 streams in while tracer
 //     i is being swept;
-//   - thread `tid` owns the depth-7 node `tid` (4 depth-9 nodes, 4..8 leaves): its
-//     micro-subtree is summed and solved in registers;
+//   - a thread owns one depth-7 node (4 depth-9 nodes, 4..8 leaves): its micro-subtree
+//     is summed and solved in registers. In the up-sweep thread `tid` owns node `tid`
+//     (the levels above go through shuffles); in the down-sweep the nodes are dealt to
+//     the threads in a per-shape order that minimises shared-memory bank conflicts
+//     (FastArgs::perm, tree_plan.cpp build_down_tables);
 //   - the levels above the depth-7 nodes go through warp shuffles (sums) and, in the
 //     down-sweep, through a dedicated top warp working a tracer ahead of the leaf warps;
 //   - solved leaf masses are staged in shared memory and leave by a TMA bulk store.
@@ -176,8 +179,12 @@ up_kernel (const FastArgs a) {
 
   // This thread's four depth-9 nodes: leaf offset and whether it is a pair.
   const ushort4 e = reinterpret_cast<const ushort4*>(a.dtab + B.ftab_off)[tid];
+#ifdef CEDR_B200_UP_FAKE_OFFSETS   // timing experiment only: conflict-free (wrong) offsets
+  const int o0 = 5*tid + shift, o1 = o0 + 1, o2 = o0 + 2, o3 = o0 + 3;
+#else
   const int o0 = (e.x & 0x7fff) + shift, o1 = (e.y & 0x7fff) + shift,
     o2 = (e.z & 0x7fff) + shift, o3 = (e.w & 0x7fff) + shift;
+#endif
   const bool p0 = e.x >> 15, p1 = e.y >> 15, p2 = e.z >> 15, p3 = e.w >> 15;
 
   if (tid == 0) {
