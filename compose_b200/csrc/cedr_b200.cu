@@ -1074,6 +1074,7 @@ void finish_setup (cedr_b200_cdr& c) {
       hb[b].fpair_off = sh.dev_ptab_off;
       hb[b].fperm_off = sh.dev_perm_off;
       hb[b].fpent_off = sh.dev_pent_off;
+      hb[b].fperm_up_off = sh.dev_perm_up_off;
       hb[b].fpos_off = sh.dev_fpos_off;
       hb[b].npairs = sh.fast ? static_cast<int>(sh.ptab.size()) : 0;
       hb[b].fbase = blk.ibase;
@@ -1730,6 +1731,12 @@ int cedr_b200_plan_probe (int ncells, int nnodes, int root, const int* kids,
         cedr_b200_throw_if(sh.perm[i] >= 128 || thread_of[sh.perm[i]] >= 0,
                            "perm is not a permutation");
         thread_of[sh.perm[i]] = i;
+      }
+      cedr_b200_throw_if(sh.perm_up.size() != 256, "perm_up size");
+      for (int i = 0; i < 128; ++i) {
+        const int nd = sh.perm_up[i];
+        cedr_b200_throw_if(nd >= 128 || (nd >> 5) != (i >> 5) || sh.perm_up[128 + nd] != i,
+                           "perm_up is not a permutation within each warp");
       }
       const int np = static_cast<int>(sh.ptab.size());
       cedr_b200_throw_if(sh.pent.size() != static_cast<size_t>(5 + np) || sh.pent[0] != 5 ||

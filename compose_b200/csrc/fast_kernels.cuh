@@ -177,14 +177,15 @@ up_kernel (const FastArgs a) {
   const int g0 = grp*a.group;
   const int gn = min(a.group, a.ntr - g0);
 
-  // This thread's four depth-9 nodes: leaf offset and whether it is a pair.
-  const ushort4 e = reinterpret_cast<const ushort4*>(a.dtab + B.ftab_off)[tid];
-#ifdef CEDR_B200_UP_FAKE_OFFSETS   // timing experiment only: conflict-free (wrong) offsets
-  const int o0 = 5*tid + shift, o1 = o0 + 1, o2 = o0 + 2, o3 = o0 + 3;
-#else
+  // This thread's depth-7 node -- one of its own warp's 32, in the order that spreads the
+  // half-warps' leaf offsets over the shared-memory banks (FastArgs::perm, second table) --
+  // and, for the shuffle tree above depth 7, the lane that holds node 32 warp + lane.
+  const unsigned short* const pup = a.perm + B.fperm_up_off;
+  const int node = pup[tid], src_lane = pup[128 + tid] & 31;
+  // The node's four depth-9 nodes: leaf offset and whether it is a pair.
+  const ushort4 e = reinterpret_cast<const ushort4*>(a.dtab + B.ftab_off)[node];
   const int o0 = (e.x & 0x7fff) + shift, o1 = (e.y & 0x7fff) + shift,
     o2 = (e.z & 0x7fff) + shift, o3 = (e.w & 0x7fff) + shift;
-#endif
   const bool p0 = e.x >> 15, p1 = e.y >> 15, p2 = e.z >> 15, p3 = e.w >> 15;
 
   if (tid == 0) {
@@ -263,6 +264,13 @@ up_kernel (const FastArgs a) {
         else
           r[f] = (n[0][f] + n[1][f]) + (n[2][f] + n[3][f]);
       }
+    }
+    // Back into lane order: lane l takes the record of node 32 warp + l.
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      if ((f == 0 || f == 2) && ! bounds) continue;
+      if (f == 3 && ! prev) continue;
+      r[f] = __shfl_sync(0xffffffffu, r[f], src_lane);
     }
     if ((CLS == CLS_ST || CLS == CLS_CST) && a.n7buf) {
       double* const n7 = a.n7buf + (static_cast<long long>(t)*a.nblocks + b)*384;

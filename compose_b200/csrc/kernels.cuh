@@ -25,7 +25,7 @@ struct BlockDev {
   int leaf0, nl, ni, nlev;
   int lvlptr_off, kid_off, ibase;
   // Fast-path tables (fast_kernels.cuh); ftab_off < 0 if the shape is not fast.
-  int ftab_off, fpair_off, fpos_off, npairs, fbase, fperm_off, fpent_off;
+  int ftab_off, fpair_off, fpos_off, npairs, fbase, fperm_off, fpent_off, fperm_up_off;
   // Index of this block among ALL blocks of its tier (= its leaf number in the next
   // tier). Equals its position in the device block list except in tier 0 of a
   // multi-rank run, where the list holds only the blocks this rank owns.

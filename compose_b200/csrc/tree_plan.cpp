@@ -149,6 +149,29 @@ static void build_down_tables (Shape& sh) {
     for (size_t i = 0; i < keyed[w].size(); ++i) sh.pent.push_back(keyed[w][i].second);
   }
   sh.pent[4] = static_cast<unsigned>(sh.pent.size());
+
+  // Up-sweep: the same wavefront count, nodes moved only between the two half-warps of
+  // their own warp (the kernel puts the depth-7 records back into lane order with one
+  // shuffle per field before its shuffle tree).
+  for (int i = 0; i < 128; ++i) g[i >> 4][i & 15] = i;
+  for (int k = 0; k < 8; ++k) gc[k] = cost(g[k]);
+  T = 2.0;
+  for (int it = 0; it < 60000; ++it) {
+    const int g1 = static_cast<int>(next() % 8), g2 = g1 ^ 1;
+    const int i1 = static_cast<int>(next() % 16), i2 = static_cast<int>(next() % 16);
+    std::swap(g[g1][i1], g[g2][i2]);
+    const int c1 = cost(g[g1]), c2 = cost(g[g2]);
+    const int d = c1 + c2 - gc[g1] - gc[g2];
+    const double u = (next() >> 11)*(1.0/9007199254740992.0);
+    if (d <= 0 || u < std::exp(-d/T)) { gc[g1] = c1; gc[g2] = c2; }
+    else std::swap(g[g1][i1], g[g2][i2]);
+    T = std::max(0.02, T*0.9999);
+  }
+  sh.perm_up.resize(256);
+  for (int i = 0; i < 128; ++i) {
+    sh.perm_up[i] = static_cast<unsigned short>(g[i >> 4][i & 15]);
+    sh.perm_up[128 + g[i >> 4][i & 15]] = static_cast<unsigned short>(i);
+  }
 }
 
 // Try to describe `sh` as "perfect to depth 9, leaves or pairs below" (see
@@ -407,6 +430,8 @@ void Plan::build (int ncells_, int nnodes, int root, const int* kids,
           dev_fpos.insert(dev_fpos.end(), sh.fpos.begin(), sh.fpos.end());
           sh.dev_perm_off = static_cast<int>(dev_perm.size());
           dev_perm.insert(dev_perm.end(), sh.perm.begin(), sh.perm.end());
+          sh.dev_perm_up_off = static_cast<int>(dev_perm.size());
+          dev_perm.insert(dev_perm.end(), sh.perm_up.begin(), sh.perm_up.end());
           sh.dev_pent_off = static_cast<int>(dev_pent.size());
           dev_pent.insert(dev_pent.end(), sh.pent.begin(), sh.pent.end());
         }

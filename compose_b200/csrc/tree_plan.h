@@ -52,8 +52,11 @@ struct Shape {
   // leaf offset | d9x slot << 11 | pair's const rank << 20.
   std::vector<unsigned short> perm;
   std::vector<unsigned> pent;
+  // Up-sweep: [0, 128) thread -> depth-7 node, a permutation WITHIN each warp (the levels
+  // above go through warp shuffles); [128, 256) node -> thread.
+  std::vector<unsigned short> perm_up;
   int dev_dtab_off = 0, dev_ptab_off = 0, dev_fpos_off = 0, dev_perm_off = 0,
-    dev_pent_off = 0;
+    dev_pent_off = 0, dev_perm_up_off = 0;
 };
 
 struct Block {
