@@ -315,6 +315,8 @@ def main():
                 "algorithmic_bytes": BYTES_PER_UPDATE*upd_gpu,
                 "traffic_bytes_per_update": bpu["qlt"]["run_total"] if bpu else None,
                 "kernels": per_kernel,
+                "kernels_note": "per-kernel frac is against the measured COPY bandwidth (read + "
+                                "write); a read-mostly stream such as the up-sweep can exceed it",
                 "caas": {"achieved": BYTES_PER_UPDATE*upd_gpu/(ms_caas*1e-3)/1e9,
                          "frac": BYTES_PER_UPDATE*upd_gpu/(ms_caas*1e-3)/1e9/peak,
                          "traffic": bpu["caas"]["run_total"]*upd_gpu if bpu else None}}

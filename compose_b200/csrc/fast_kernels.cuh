@@ -684,6 +684,16 @@ down2_kernel (const FastArgs a) {
       n7[f] = n8[0][f] + n8[1][f];
     }
     CEDR_PHASE(2);
+#if !defined(CEDR_B200_STORE_WAIT_NOW) && !defined(CEDR_B200_NO_TMASTORE)
+    // Refill the other stage with tracer k+1: the bulk store of tracer k-1 (issued at the
+    // end of the last iteration) has read it by now, so this wait costs nothing, where
+    // waiting right after the store held thread 0's warp -- and through the next leaf
+    // barrier the whole CTA -- for the store's start-up latency.
+    if (tid == 0 && k >= 1) {
+      tma_store_wait_read();
+      if (k + 1 < gn) issue(k + 1);
+    }
+#endif
     bar_sync<BAR_T, kDown2Threads>(k & 1);       // T(k) published
     const double x7 = x[127 + node];
     bar_arrive<BAR_C, kDown2Threads>(k & 1);     // xs / un of tracer k may be reused
@@ -751,12 +761,18 @@ down2_kernel (const FastArgs a) {
       tma_store_commit();
       if (q0) o[0] = xout[shift];
       if (q0 + nint < B.nl) o[B.nl - 1] = xout[shift + B.nl - 1];
+#ifdef CEDR_B200_STORE_WAIT_NOW
       tma_store_wait_read();
       if (k + 2 < gn) issue(k + 2);
+#endif
+      // (The stage is refilled in the next iteration, once the store has read it.)
     }
 #endif
     CEDR_PHASE(6);
   }
+#if !defined(CEDR_B200_STORE_WAIT_NOW) && !defined(CEDR_B200_NO_TMASTORE)
+  if (tid == 0) tma_store_wait_read();
+#endif
   if (tid == 0) CEDR_PHASE_FLUSH(0);
 }
 

@@ -19,6 +19,8 @@ for _ in range(nt):
 c.end_tracer_declarations()
 c.finish_setup()
 c.set_rhom(rhom)
+if "--noop" in sys.argv:      # Qm = Qm_prev in bounds: every node takes the quick exit
+    q = prev
 c.set_Qm(q, lo, hi, prev)
 c.run(); c.synchronize(); c.debug_phase_clocks()
 c.run(); c.synchronize()
