@@ -515,7 +515,6 @@ down2_kernel (const FastArgs a) {
   const int g0 = grp*a.group;
   const int gn = min(a.group, a.ntr - g0);
   const unsigned short* const dtab = a.dtab + B.ftab_off;
-  const unsigned short* const ptab = a.ptab + B.fpair_off;
   const dev::NodeWQ* const wq = a.wq + B.fbase;
   const dev::NodeRh* const rh = a.rh + B.fbase;
   const double* const rqv = a.rq + B.fbase;
@@ -684,7 +683,6 @@ down2_kernel (const FastArgs a) {
       n7[f] = n8[0][f] + n8[1][f];
     }
     CEDR_PHASE(2);
-#if !defined(CEDR_B200_STORE_WAIT_NOW) && !defined(CEDR_B200_NO_TMASTORE)
     // Refill the other stage with tracer k+1: the bulk store of tracer k-1 (issued at the
     // end of the last iteration) has read it by now, so this wait costs nothing, where
     // waiting right after the store held thread 0's warp -- and through the next leaf
@@ -693,7 +691,6 @@ down2_kernel (const FastArgs a) {
       tma_store_wait_read();
       if (k + 1 < gn) issue(k + 1);
     }
-#endif
     bar_sync<BAR_T, kDown2Threads>(k & 1);       // T(k) published
     const double x7 = x[127 + node];
     bar_arrive<BAR_C, kDown2Threads>(k & 1);     // xs / un of tracer k may be reused
@@ -742,15 +739,6 @@ down2_kernel (const FastArgs a) {
     // Write-back: the solved leaves sit in block order in xout; one TMA bulk store moves
     // the 16-byte aligned interior, thread 0 stores the (at most two) edge elements. No
     // other thread waits: the stage is refilled only after the store has read it.
-#ifdef CEDR_B200_NO_TMASTORE
-    bar_sync_i<BAR_LEAF, kLeafThreads>();
-    {
-      double* const o = a.out + static_cast<long long>(t)*a.out_ld + B.leaf0;
-      for (int q = tid; q < B.nl; q += kLeafThreads) o[q] = xout[shift + q];
-    }
-    bar_sync_i<BAR_LEAF, kLeafThreads>();
-    if (tid == 0 && k + 2 < gn) issue(k + 2);
-#else
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     bar_sync_i<BAR_LEAF, kLeafThreads>();
     if (tid == 0) {
@@ -761,18 +749,11 @@ down2_kernel (const FastArgs a) {
       tma_store_commit();
       if (q0) o[0] = xout[shift];
       if (q0 + nint < B.nl) o[B.nl - 1] = xout[shift + B.nl - 1];
-#ifdef CEDR_B200_STORE_WAIT_NOW
-      tma_store_wait_read();
-      if (k + 2 < gn) issue(k + 2);
-#endif
       // (The stage is refilled in the next iteration, once the store has read it.)
     }
-#endif
     CEDR_PHASE(6);
   }
-#if !defined(CEDR_B200_STORE_WAIT_NOW) && !defined(CEDR_B200_NO_TMASTORE)
   if (tid == 0) tma_store_wait_read();
-#endif
   if (tid == 0) CEDR_PHASE_FLUSH(0);
 }
 
