@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 
@@ -54,7 +55,32 @@ void bisect (int cs, int ce, bool imbalanced, std::vector<int>& kids,
 // offsets within each are as distinct mod 16 as possible: simulated annealing over
 // swaps, on the exact wavefront count of the kernel's 8 leaf accesses (first / second
 // leaf of each of a thread's 4 depth-9 nodes). Deterministic (fixed seed).
+static void build_down_tables_uncached (Shape& sh);
+
+// The search depends on the shape's depth-9 table only; QLT and CAAS objects over the same
+// tree (and every rank's plan) share its result within a process.
 static void build_down_tables (Shape& sh) {
+  struct Tables { std::vector<unsigned short> perm, perm_up; std::vector<unsigned> pent; };
+  static std::mutex mtx;
+  static std::map<std::pair<std::vector<unsigned short>, std::vector<unsigned short> >,
+                  Tables> cache;
+  const auto key = std::make_pair(sh.dtab, sh.ptab);
+  {
+    std::lock_guard<std::mutex> lock(mtx);
+    const auto it = cache.find(key);
+    if (it != cache.end()) {
+      sh.perm = it->second.perm;
+      sh.perm_up = it->second.perm_up;
+      sh.pent = it->second.pent;
+      return;
+    }
+  }
+  build_down_tables_uncached(sh);
+  std::lock_guard<std::mutex> lock(mtx);
+  if (cache.size() < 64) cache[key] = Tables{sh.perm, sh.perm_up, sh.pent};
+}
+
+static void build_down_tables_uncached (Shape& sh) {
   const std::vector<unsigned short>& dtab = sh.dtab;
   auto off9 = [&] (int p) { return dtab[p] & 0x7fff; };
   auto pair9 = [&] (int p) { return (dtab[p] >> 15) != 0; };
