@@ -88,36 +88,65 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def cpu_reference_step(ncells, config_id, nt_sample, nrep, warm):
+def host_cores():
+    """Host threads this process may use (its affinity mask, else the CPU count)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def digest_np(a):
+    """Wrap-around (mod 2^64) sum of the raw 64-bit patterns: order-independent, so ranks'
+    digests of disjoint cell ranges add up to the digest of the whole array."""
+    import numpy as np
+    with np.errstate(over="ignore"):
+        return int(np.ascontiguousarray(a).view(np.uint64).sum(dtype=np.uint64))
+
+
+def cpu_reference_step(ncells, config_id, nt_sample, nrep, warm, digests=None):
     """Time the reference's own QLT::run + CAAS::run (oracle/_ref, all host threads) on a
-    tracer batch of the workload. Returns (per-step seconds list, info dict)."""
+    tracer batch of the workload. Returns (per-step seconds list, info dict). If `digests`
+    is a dict it receives digest_np of the reference's outputs for that batch."""
     from oracle.oracle_py import Oracle, Ref, ref_available
     o = Oracle()
     rhom, lo, q, hi, prev = o.fill_headline(ncells, config_id, 0, nt_sample)
     pts = [CST]*nt_sample
     if ref_available(omp=True):
         r = Ref(omp=True)
-        cores = r.num_threads()
-        _, _, sq = r.qlt(ncells, ("bisect", False), pts, rhom, lo, q, hi, prev, nrep=warm + nrep)
+        # torchrun exports OMP_NUM_THREADS=1: ask for the host's cores explicitly.
+        cores = r.set_num_threads(host_cores())
+        oq, _, sq = r.qlt(ncells, ("bisect", False), pts, rhom, lo, q, hi, prev, nrep=warm + nrep)
         _, sc = r.caas(ncells, pts, rhom, lo, q, hi, prev, nrep=warm + nrep)
         kind = "reference"
         secs = [float(a + b) for a, b in zip(sq[warm:], sc[warm:])]
         split = {"qlt_s": float(min(sq[warm:])), "caas_s": float(min(sc[warm:]))}
+        if digests is not None:
+            # CAAS digest: the reference CAAS driven through its own BfbTreeAllReducer
+            # (tree-ordered sums, the b200 default mode; untimed). The timed CAAS above is
+            # the stock sequential-sum path.
+            oc, _ = r.caas(ncells, pts, rhom, lo, q, hi, prev, tree=("bisect", False))
+            digests["qlt"] = "%016x" % digest_np(oq)
+            digests["caas"] = "%016x" % digest_np(oc)
     else:
         # The plain-C restatement, OpenMP over tracers.
         tree = o.bisection_tree(ncells)
-        cores = os.cpu_count()
+        cores = host_cores()
+        os.environ["OMP_NUM_THREADS"] = str(cores)
         secs, split = [], {}
         for i in range(warm + nrep):
             t0 = time.perf_counter()
-            o.qlt(tree, pts, rhom, lo, q, hi, prev)
+            oq = o.qlt(tree, pts, rhom, lo, q, hi, prev)
             t1 = time.perf_counter()
-            o.caas(ncells, pts, lo, q, hi, prev, tree=tree)
+            oc = o.caas(ncells, pts, lo, q, hi, prev, tree=tree)
             t2 = time.perf_counter()
             if i >= warm:
                 secs.append(t2 - t0)
                 split = {"qlt_s": t1 - t0, "caas_s": t2 - t1}
         kind = "port"
+        if digests is not None:
+            digests["qlt"] = "%016x" % digest_np(oq)
+            digests["caas"] = "%016x" % digest_np(oc)
     info = {"cores": cores, "kind": kind,
             "sample": "%d cells x %d of the workload's tracers (one tracer batch; tracers are "
                       "independent problems), QLT::run + CAAS::run only, %d warm-up + %d reps, "
@@ -133,7 +162,8 @@ def run_reference_arm(args):
         return
     ncells, nt, cid = workload_dims(args.workload)
     nts = min(REF_SAMPLE_NT, nt)
-    secs, info = cpu_reference_step(ncells, cid, nts, args.steps, args.warmup)
+    digests = {}
+    secs, info = cpu_reference_step(ncells, cid, nts, args.steps, args.warmup, digests)
     ms = 1e3*sum(secs)/len(secs)
     value = 2.0*ncells*nts/(ms*1e-3)
     info["value"] = value
@@ -147,6 +177,11 @@ def run_reference_arm(args):
         "cpu_baseline": info,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # Parity record: compare with the b200 arm's "sample_digest" (same tracers, any N).
+        "sample_digest": dict(digests, tracers=nts,
+                              how="mod-2^64 sum of the raw 64-bit output words of the first "
+                                  "%d tracers; caas = reference CAAS + its BfbTreeAllReducer"
+                                  % nts),
     }
     print(json.dumps(line))
 
@@ -198,7 +233,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"    # keep NCCL's version banner off stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -272,6 +306,23 @@ def main():
     ms_step, ms_qlt, ms_caas = (float(x) for x in t.cpu())
     updates = float(ncells)*nt
     value = 2.0*updates/(ms_step*1e-3)
+
+    # ---- parity record: digests of the outputs of the last timed step (all tracers, and
+    # the first REF_SAMPLE_NT tracers = the reference arm's batch), summed over the ranks'
+    # disjoint cell ranges. Identical at every N and equal to the reference arm's
+    # sample_digest iff the results are bit-identical.
+    nts = min(REF_SAMPLE_NT, nt)
+    dig = []
+    for c in (qlt, caas):
+        o = c.get_Qm()
+        dig += [o.view(torch.int64).sum(), o[:nts].contiguous().view(torch.int64).sum()]
+        del o
+    dig = torch.stack(dig)
+    if world > 1:
+        dist.all_reduce(dig, op=dist.ReduceOp.SUM)
+    dig = ["%016x" % (int(v) & 0xffffffffffffffff) for v in dig.cpu()]
+    output_digest = {"qlt": dig[0], "caas": dig[2]}
+    sample_digest = {"qlt": dig[1], "caas": dig[3], "tracers": nts}
 
     # ---- per-launch breakdown (untimed extra step)
     kernels = None
@@ -382,10 +433,13 @@ def main():
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        nts = min(REF_SAMPLE_NT, nt)
-        secs, cpu = cpu_reference_step(ncells, cid, nts, 3, 1)
+        ref_dig = {}
+        secs, cpu = cpu_reference_step(ncells, cid, nts, 3, 1, ref_dig)
         cpu["value"] = 2.0*ncells*nts/(sum(secs)/len(secs))
         cpu["unit"] = UNIT
+        cpu["sample_digest"] = ref_dig
+        sample_digest["matches_cpu_reference"] = (ref_dig.get("qlt") == sample_digest["qlt"] and
+                                                  ref_dig.get("caas") == sample_digest["caas"])
 
     if rank == 0:
         line = {
@@ -397,6 +451,7 @@ def main():
             "qlt": {"value": updates/(ms_qlt*1e-3), "ms_per_run": ms_qlt},
             "caas": {"value": updates/(ms_caas*1e-3), "ms_per_run": ms_caas},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "output_digest": output_digest, "sample_digest": sample_digest,
             "gpu_launches": launches, "clocks": clocks, "kernels_ms": kernels,
             "small_problem": small,
             "exchange": (None if world == 1 else

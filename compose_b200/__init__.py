@@ -287,8 +287,11 @@ class CDR:
                                                         _ptr(self._xrecv)))
 
         def gather(ctx, send, recv, count, stream):
+            # Enqueue the collective on the CDR's own stream (the pack / unpack kernels
+            # either side of it run there), whatever torch's current stream is.
             try:
-                dist.all_gather_into_tensor(self._xrecv, self._xsend, group=group)
+                with torch.cuda.stream(torch.cuda.ExternalStream(int(stream or 0))):
+                    dist.all_gather_into_tensor(self._xrecv, self._xsend, group=group)
                 return 0
             except Exception:   # surfaced as a CedrError by run()
                 import traceback

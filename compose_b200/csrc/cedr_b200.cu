@@ -239,13 +239,21 @@ size_t sweep_smem_bytes (const cedr_b200_cdr& c, int tier) {
 }
 
 // Raise (never lower) the dynamic shared memory limit of sweep_kernel<CLS, MODE>.
+// (cudaFuncSetAttribute is per device: the cache is keyed by the current device.)
+int current_device () {
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  return dev;
+}
+
 template <int CLS, int MODE> void sweep_smem_configure (const size_t smem) {
-  static size_t configured = 48*1024;
-  if (smem > configured) {
+  static std::unordered_map<int, size_t> configured;
+  size_t& have = configured.emplace(current_device(), 48*1024).first->second;
+  if (smem > have) {
     CUDA_CHECK(cudaFuncSetAttribute(sweep_kernel<CLS, MODE>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
-    configured = smem;
+    have = smem;
   }
 }
 
@@ -375,6 +383,7 @@ fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
   if (const char* e = std::getenv("CEDR_B200_GROUP")) a.group = std::max(1, std::atoi(e));
   a.n7buf = c.d_n7.p;
   a.rq = c.d_frq.p;
+  a.caas_rows = c.caas_need_conserve ? 4 : 3;
   if (c.split && cls != CLS_CAAS) {
     a.split = c.split;
     a.rec_out = c.d_xrec.p;
@@ -397,8 +406,9 @@ void launch_fast (cedr_b200_cdr& c, K kernel, const fast::FastArgs& a, size_t sm
                   int threads = fast::kThreads) {
   if (a.ntr == 0) return;
   // Raise (never lower) the kernel's dynamic shared memory limit, once per size.
-  static std::unordered_map<const void*, size_t> configured;
-  size_t& have = configured[reinterpret_cast<const void*>(kernel)];
+  static std::map<std::pair<int, const void*>, size_t> configured;
+  size_t& have = configured[std::make_pair(current_device(),
+                                           reinterpret_cast<const void*>(kernel))];
   if (smem > have) {
     CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(std::max<size_t>(smem, 48*1024))));
@@ -1119,6 +1129,7 @@ void finish_setup (cedr_b200_cdr& c) {
 }
 
 void fill_1d_tree (cedr_b200_cdr& c, int ncells, bool imbalanced) {
+  cedr_b200_throw_if(c.nranks < 1 || c.nranks > ncells, "#GIDs < #ranks is not supported.");
   make_bisection_tree(ncells, imbalanced, c.tree_kids, c.tree_cellidx);
   c.tree_root = 0;
   c.tree_rank.assign(c.tree_cellidx.size(), 0);

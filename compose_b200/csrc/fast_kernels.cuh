@@ -127,6 +127,9 @@ struct FastArgs {
   // takes the narrowest levels of the dependent chain out of the block kernels. S is 0, 2
   // or 3.
   int split;
+  // CAAS: rows allotted per tracer in `in` (4 if any tracer conserves, else 3: there is no
+  // Qm_prev row to stage, cedr_caas.cpp:86-100).
+  int caas_rows;
 };
 
 #ifdef CEDR_B200_PHASE_CLOCKS
@@ -194,14 +197,16 @@ up_kernel (const FastArgs a) {
     mbar_fence_init();
   }
   __syncthreads();
+  // Rows to stage: a CAAS without conserving tracers has no Qm_prev row.
+  const int nstage = (R::caas && a.caas_rows == 3) ? 3 : nrows;
   auto issue = [&] (const int i) {
     const int t = a.tracers[g0 + i];
     const double* src = a.in + static_cast<long long>(a.trcr_row[t])*a.in_ld + src0;
     double* dst = stage + (i & 1)*nrows*a.sbuf;
-    mbar_expect_tx(&mbar[i & 1], nrows*bytes);
+    mbar_expect_tx(&mbar[i & 1], nstage*bytes);
 #pragma unroll
     for (int f = 0; f < nrows; ++f)
-      tma_load(dst + f*a.sbuf, src + f*a.in_ld, bytes, &mbar[i & 1]);
+      if (f < nstage) tma_load(dst + f*a.sbuf, src + f*a.in_ld, bytes, &mbar[i & 1]);
   };
   if (tid == 0) {
     issue(0);

@@ -4,7 +4,7 @@
  * by QLT (cedr/cedr_qlt.{hpp,cpp}) and CAAS (cedr/cedr_caas.{hpp,cpp}). Each
  * entry point names the reference interface it replaces; `file:line` are
  * relative to the reference's cedr/ directory. The C++ mirror of the
- * reference's classes (compose_b200/cxx/) and the Python front end
+ * reference's classes (include/cedr_b200.hpp) and the Python front end
  * (compose_b200/__init__.py) are thin layers over exactly these symbols.
  *
  * Conventions

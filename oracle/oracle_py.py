@@ -237,6 +237,11 @@ class Ref:
     def num_threads(self):
         return self.lib.cedr_ref_num_threads()
 
+    def set_num_threads(self, n):
+        """omp_set_num_threads (torchrun exports OMP_NUM_THREADS=1); returns the count."""
+        self.lib.cedr_ref_set_num_threads.argtypes = [C.c_int]
+        return self.lib.cedr_ref_set_num_threads(int(n))
+
     def _err(self, rc, what):
         if rc:
             raise RuntimeError("%s failed (%d): %s" %

@@ -21,6 +21,9 @@
 #include "cedr_bfb_tree_allreduce.hpp"
 #include "cedr_tree.hpp"
 
+#ifdef _OPENMP
+# include <omp.h>
+#endif
 #include <chrono>
 #include <cstdint>
 #include <sstream>
@@ -97,6 +100,17 @@ extern "C" {
 const char* cedr_ref_last_error () { return g_err.c_str(); }
 
 int cedr_ref_num_threads () {
+  return Kokkos::DefaultHostExecutionSpace::concurrency();
+}
+
+// torchrun exports OMP_NUM_THREADS=1 to every rank; bench.py's reference arm asks for
+// the host's cores explicitly. Returns the thread count in effect afterwards.
+int cedr_ref_set_num_threads (int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void) n;
+#endif
   return Kokkos::DefaultHostExecutionSpace::concurrency();
 }
 
