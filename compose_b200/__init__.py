@@ -89,6 +89,11 @@ SYMBOLS = [
     ("cedr_b200_debug_phase_clocks", C.c_int, [_H, C.POINTER(C.c_ulonglong)]),
     ("cedr_b200_set_fused", C.c_int, [_H, C.c_int, C.c_int]),
     ("cedr_b200_uses_fused", C.c_int, [_H, _ip]),
+    ("cedr_b200_set_ring", C.c_int, [_H, C.c_int]),
+    ("cedr_b200_uses_ring", C.c_int, [_H, _ip]),
+    ("cedr_b200_ring_info", C.c_int, [_H, _ip]),
+    ("cedr_b200_ring_trace", C.c_int, [_H, C.POINTER(C.c_ulonglong), C.c_size_t,
+                                       C.POINTER(C.c_size_t)]),
     ("cedr_b200_set_profiling", C.c_int, [_H, C.c_int]),
     ("cedr_b200_get_launch_times", C.c_int, [_H, C.c_int, C.POINTER(C.c_float), _ip, _ip,
                                              _ip]),
@@ -372,6 +377,31 @@ class CDR:
         v = C.c_int(0)
         _check(self._lib.cedr_b200_uses_fused(self._h, C.byref(v)))
         return bool(v.value)
+
+    def set_ring(self, on=True):
+        _check(self._lib.cedr_b200_set_ring(self._h, int(bool(on))))
+
+    def uses_ring(self):
+        v = C.c_int(0)
+        _check(self._lib.cedr_b200_uses_ring(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def ring_info(self):
+        v = (C.c_int*8)()
+        _check(self._lib.cedr_b200_ring_info(self._h, v))
+        keys = ("grid", "S", "npn", "TB", "nslots", "np", "sw", "smem")
+        return dict(zip(keys, list(v)))
+
+    def ring_trace(self):
+        """Debug (CEDR_B200_RING_TRACE=1): numpy uint64 stamps of the last ring launch."""
+        import numpy as np
+        n = C.c_size_t(0)
+        _check(self._lib.cedr_b200_ring_trace(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, np.uint64)
+        if n.value:
+            _check(self._lib.cedr_b200_ring_trace(
+                self._h, out.ctypes.data_as(C.POINTER(C.c_ulonglong)), n.value, C.byref(n)))
+        return out
 
     def debug_phase_clocks(self):
         out = (C.c_ulonglong*16)()

@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "fast_kernels.cuh"
 #include "fused_kernels.cuh"
+#include "ring_kernels.cuh"
 #include "tree_plan.h"
 
 namespace {
@@ -175,6 +176,27 @@ struct cedr_b200_cdr {
   DevBuf<BlockDev> d_xblock;
   DevBuf<dev::NodeConst> d_xnc;
   DevBuf<double> d_xrhom, d_xrec, d_xsol;
+  // Persistent single-read kernel (ring_kernels.cuh), the default run() where it applies.
+  bool ring_enabled = true;   // cedr_b200_set_ring
+  bool ring_ok = false;
+  struct Ring {
+    int grid = 0, S = 0, npn = 0, npairs_max = 0, TB = 1, plen = 0, nslots = 0, npslots = 0;
+    int np = 3, sw = 1;
+    int M = 0, mni = 0, mnlev = 0;
+    long long ld = 0;         // padded sub-root count
+    size_t smem = 0;
+    DevBuf<ring::PieceDev> pieces;
+    DevBuf<ushort4> d7tab;
+    DevBuf<int2> d7c;
+    DevBuf<uint2> pairtab;
+    DevBuf<int> topc, lvlptr, kid0, kid1, micro_c, micro_h, msrc;
+    DevBuf<dev::NodeWQ> mwq;
+    DevBuf<dev::NodeRh> mrh;
+    DevBuf<double> rec, sol;
+    DevBuf<unsigned> sync;    // [2 nt]: arrivals, flags
+    DevBuf<unsigned long long> trace;   // debug (CEDR_B200_RING_TRACE)
+    size_t trace_n = 0;
+  } ring;
   DevBuf<unsigned> d_sync;    // [2 nt]: arrival counters, flags
   DevBuf<int> d_status;
   std::vector<DevBuf<BlockDev> > d_blocks;   // per tier
@@ -536,6 +558,342 @@ void launch_fused (cedr_b200_cdr& c, int cls) {
   ++c.last_launches;
 }
 
+// ---- persistent single-read kernel (ring_kernels.cuh)
+
+bool ring_class (int cls) { return cls == CLS_ST || cls == CLS_CST || cls == CLS_CAAS; }
+
+const void* ring_kernel_ptr (int cls, int np, int sw) {
+#define CEDR_RK(C, N, W) reinterpret_cast<const void*>(ring::run_kernel<C, N, W>)
+#define CEDR_RK_CLS(C)                                                  \
+  (np == 2 ? (sw == 1 ? CEDR_RK(C, 2, 1) : CEDR_RK(C, 2, 2))            \
+           : (sw == 1 ? CEDR_RK(C, 3, 1) : CEDR_RK(C, 3, 2)))
+  switch (cls) {
+  case CLS_ST: return CEDR_RK_CLS(CLS_ST);
+  case CLS_CST: return CEDR_RK_CLS(CLS_CST);
+  default: return CEDR_RK_CLS(CLS_CAAS);
+  }
+#undef CEDR_RK_CLS
+#undef CEDR_RK
+}
+
+int env_int (const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+
+// Decide whether run() can be the ring kernel and build its tables; called from
+// finish_setup. One piece per CTA: consecutive depth-S subtrees of the tier-0 blocks.
+void ring_setup (cedr_b200_cdr& c) {
+  c.ring_ok = false;
+  cedr_b200_cdr::Ring& R = c.ring;
+  if ( ! c.ring_enabled || ! c.fast_ok || c.is_bfb || std::getenv("CEDR_B200_NO_RING")) return;
+  if (c.nranks > 1) return;
+  if (c.is_caas && c.caas_sum_mode != CEDR_B200_CAAS_SUM_TREE) return;
+  if (c.plan.tiers.size() != 2 || c.plan.tiers[1].blocks.size() != 1) return;
+  const int nt = static_cast<int>(c.trcr_prob.size());
+  if (nt == 0) return;
+  if ( ! c.is_caas && c.cls_tracers[CLS_ST].empty() && c.cls_tracers[CLS_CST].empty()) return;
+  int dev = 0, coop = 0, nsm = 0, smem_max = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if ( ! coop) return;
+  nsm = env_int("CEDR_B200_RING_GRID", nsm);
+  const std::vector<Block>& blocks = c.plan.tiers[0].blocks;
+  const int nb = static_cast<int>(blocks.size());
+  // The leaves of consecutive blocks must be consecutive local cells.
+  for (int b = 0; b + 1 < nb; ++b)
+    if (c.leaf_lci[blocks[b + 1].leaf0] != c.leaf_lci[blocks[b].leaf0] + blocks[b].nl) return;
+  // S: the shallowest cut that keeps the SMs busy (sub-blocks per CTA x CTAs against the
+  // sub-blocks there are), with at most 128 depth-7 nodes per piece. Deeper cuts cost more
+  // records and a larger tree above the sub-roots.
+  int S = -1, G = 0, per = 0;
+  {
+    double eff[8] = {0}, best = 0;
+    for (int s = 3; s <= 7; ++s) {
+      const long long n1 = static_cast<long long>(nb) << s;
+      const int g = static_cast<int>(std::min<long long>(nsm, n1));
+      const int pr = static_cast<int>((n1 + g - 1)/g);
+      if ((pr << (7 - s)) > ring::kGroup) continue;
+      eff[s] = static_cast<double>(n1)/(static_cast<double>(pr)*nsm);
+      best = std::max(best, eff[s]);
+    }
+    for (int s = 3; s <= 7 && S < 0; ++s)
+      if (eff[s] > 0 && eff[s] >= best - 0.03) {
+        const long long n1 = static_cast<long long>(nb) << s;
+        S = s;
+        G = static_cast<int>(std::min<long long>(nsm, n1));
+        per = static_cast<int>((n1 + G - 1)/G);
+      }
+  }
+  if (const char* e = std::getenv("CEDR_B200_RING_S")) {
+    const int s = std::atoi(e);
+    const long long n1 = static_cast<long long>(nb) << s;
+    if (s >= 3 && s <= 7) {
+      S = s; G = static_cast<int>(std::min<long long>(nsm, n1));
+      per = static_cast<int>((n1 + G - 1)/G);
+      if ((per << (7 - s)) > ring::kGroup) return;
+    }
+  }
+  if (S < 0) return;
+  const int N1 = nb << S, nhp = 1 << (7 - S);
+  R.S = S;
+  R.grid = G;
+  R.npn = per*nhp;
+  R.ld = round_up(N1, 16);
+  R.np = std::max(2, std::min(3, env_int("CEDR_B200_RING_NP", c.is_caas ? 2 : 3)));
+  R.sw = std::max(1, std::min(2, env_int("CEDR_B200_RING_SW", 1)));
+
+  // ---- pieces
+  std::vector<ring::PieceDev> pieces(G);
+  std::vector<ushort4> d7tab;
+  std::vector<int2> d7c;
+  std::vector<uint2> pairtab;
+  std::vector<int> topc;
+  int maxnl = 0;
+  R.npairs_max = 1;
+  for (int g = 0, sub = 0; g < G; ++g) {
+    // The first N1 % G pieces take `per` sub-blocks, the others per - 1 (all `per` if even).
+    const int rem = N1 % G;
+    const int ns = (rem == 0 || g < rem) ? per : per - 1;
+    ring::PieceDev P;
+    std::memset(&P, 0, sizeof(P));
+    P.nsub = ns;
+    P.sub0 = sub;
+    P.nd7 = ns*nhp;
+    P.d7_off = static_cast<int>(d7tab.size());
+    P.pair_off = static_cast<int>(pairtab.size());
+    P.top_off = static_cast<int>(topc.size());
+    int leaf0 = -1, leaf_end = -1;
+    for (int i = 0; i < ns; ++i, ++sub) {
+      const int b = sub >> S, ps = sub & ((1 << S) - 1);
+      const Block& blk = blocks[b];
+      const Shape& sh = c.plan.shapes[blk.shape];
+      const int lci0 = c.leaf_lci[blk.leaf0];
+      for (int k = 0; k < nhp; ++k) {
+        const int n7 = ps*nhp + k;            // depth-7 node of the block
+        const int nloc = i*nhp + k;           // ... of the piece
+        unsigned short e[4];
+        for (int q = 0; q < 4; ++q) {
+          const unsigned short de = sh.dtab[4*n7 + q];
+          const int o = lci0 + (de & 0x7fff);
+          const bool pair = (de >> 15) != 0;
+          if (leaf0 < 0) leaf0 = o;
+          leaf_end = o + (pair ? 2 : 1);
+          const int rel = o - leaf0;
+          if (rel > 0x7ffe) return;           // does not fit the 15-bit offsets
+          e[q] = static_cast<unsigned short>(rel | (pair ? 0x8000 : 0));
+          if (pair) {
+            const int r = static_cast<int>(std::lower_bound(sh.ptab.begin(), sh.ptab.end(),
+                                                            4*n7 + q) - sh.ptab.begin());
+            uint2 pe;
+            pe.x = static_cast<unsigned>(rel) | (static_cast<unsigned>(q) << 16) |
+              (static_cast<unsigned>(nloc) << 18);
+            pe.y = static_cast<unsigned>(blk.ibase + 511 + r);
+            pairtab.push_back(pe);
+          }
+        }
+        d7tab.push_back(make_ushort4(e[0], e[1], e[2], e[3]));
+        d7c.push_back(make_int2(blk.ibase + 127 + n7, blk.ibase + 255 + 2*n7));
+      }
+      // Constants of the sub-block's nodes of depths S..6: heap order within the sub-block.
+      for (int h = 0; h < nhp; ++h) {
+        if (h == nhp - 1) { topc.push_back(-1); break; }
+        int l = 0;
+        while ((2 << l) - 1 <= h) ++l;
+        const int pp = h - ((1 << l) - 1);
+        topc.push_back(blk.ibase + (1 << (S + l)) - 1 + ps*(1 << l) + pp);
+      }
+    }
+    P.leaf0 = leaf0;
+    P.nl = leaf_end - leaf0;
+    P.npairs = static_cast<int>(pairtab.size()) - P.pair_off;
+    maxnl = std::max(maxnl, P.nl);
+    R.npairs_max = std::max(R.npairs_max, P.npairs);
+    pieces[g] = P;
+  }
+  R.plen = (maxnl + 2 + 1) & ~1;
+
+  // ---- tracers per unit and ring depth, from the shared-memory budget
+  const bool has_prev = c.is_caas ? c.caas_need_conserve : ! c.cls_tracers[CLS_CST].empty();
+  const int M = nb << (S - 3);
+  int TB = std::max(1, std::min(std::min(ring::kMaxTB, nt), ring::kGroup/R.npn));
+  TB = std::max(1, std::min(TB, env_int("CEDR_B200_RING_TB", TB)));
+  const size_t budget = static_cast<size_t>(smem_max) - 1024;
+  for (;; TB = std::max(1, TB/2)) {
+    const int nps = has_prev ? std::max(2, env_int("CEDR_B200_RING_PSLOTS", 3)) : 0;
+    const ring::SmemLayout l0 = ring::smem_layout(TB, R.plen, 0, nps, R.np, M, R.npn,
+                                                  R.npairs_max, c.is_caas);
+    const size_t per_slot = sizeof(double)*l0.slot_doubles + 4*sizeof(uint64_t);
+    int ns = l0.total < budget ? static_cast<int>((budget - l0.total)/per_slot) : 0;
+    ns = std::min(ns, ring::kMaxSlots);
+    ns = std::min(ns, env_int("CEDR_B200_RING_SLOTS", ns));
+    if (ns >= R.np + 1) {
+      R.TB = TB; R.nslots = ns; R.npslots = nps;
+      R.smem = ring::smem_layout(TB, R.plen, ns, nps, R.np, M, R.npn, R.npairs_max,
+                                 c.is_caas).total;
+      break;
+    }
+    if (TB == 1) return;
+  }
+
+  // ---- the tree over the micro-roots: the blocks' nodes above depth S-3 (perfect, Ep
+  // micro-roots per block), then the tier-1 block with the block roots as its leaves.
+  {
+    const int Sp = S - 3, Ep = 1 << Sp, nx = (Ep - 1)*nb;
+    const Block& b1 = c.plan.tiers[1].blocks[0];
+    const Shape& s1 = c.plan.shapes[b1.shape];
+    if (s1.nl != nb) return;
+    std::vector<int> hstart(Sp + 2, 0);       // first internal index of height h
+    for (int h = 1; h <= Sp; ++h) hstart[h + 1] = hstart[h] + nb*(1 << (Sp - h));
+    auto xnode = [&] (int b, int d, int p) { return M + hstart[Sp - d] + b*(1 << d) + p; };
+    const int ni = nx + s1.ni;
+    std::vector<int> kid0(ni), kid1(ni), lvlptr(1, 0), msrc(ni);
+    for (int h = 1; h <= Sp; ++h) {
+      const int d = Sp - h;
+      for (int b = 0; b < nb; ++b)
+        for (int p = 0; p < (1 << d); ++p) {
+          const int me = xnode(b, d, p) - M;
+          if (d == Sp - 1) { kid0[me] = b*Ep + 2*p; kid1[me] = b*Ep + 2*p + 1; }
+          else { kid0[me] = xnode(b, d + 1, 2*p); kid1[me] = xnode(b, d + 1, 2*p + 1); }
+          msrc[me] = blocks[b].ibase + (1 << d) - 1 + p;
+        }
+      lvlptr.push_back(hstart[h + 1]);
+    }
+    auto map1 = [&] (int id) {
+      return id < nb ? (Sp > 0 ? xnode(id, 0, 0) : id) : M + nx + (id - nb);
+    };
+    for (int j = 0; j < s1.ni; ++j) {
+      kid0[nx + j] = map1(s1.kid0[j]);
+      kid1[nx + j] = map1(s1.kid1[j]);
+      msrc[nx + j] = -1 - (b1.ibase + j);
+    }
+    for (int l = 1; l <= s1.nlev; ++l) lvlptr.push_back(nx + s1.lvlptr[l]);
+    std::vector<int> micro_c(M), micro_h(M);
+    for (int m = 0; m < M; ++m) {
+      const int b = m >> Sp, pm = m & (Ep - 1);
+      micro_h[m] = Ep - 1 + pm;
+      micro_c[m] = blocks[b].ibase + micro_h[m];
+    }
+    R.M = M;
+    R.mni = ni;
+    R.mnlev = static_cast<int>(lvlptr.size()) - 1;
+    R.lvlptr.upload(lvlptr);
+    R.kid0.upload(kid0);
+    R.kid1.upload(kid1);
+    R.msrc.upload(msrc);
+    R.micro_c.upload(micro_c);
+    R.micro_h.upload(micro_h);
+    R.mwq.alloc(std::max(1, ni));
+    R.mrh.alloc(std::max(1, ni));
+  }
+  R.pieces.upload(pieces);
+  R.d7tab.upload(d7tab);
+  R.d7c.upload(d7c);
+  if (pairtab.empty()) pairtab.push_back(make_uint2(0, 0));
+  R.pairtab.upload(pairtab);
+  R.topc.upload(topc);
+  R.rec.alloc(static_cast<size_t>(4)*nt*R.ld);
+  R.sol.alloc(static_cast<size_t>(nt)*R.ld);
+  R.sync.alloc(2*static_cast<size_t>(nt));
+  if ( ! c.d_status.p) {
+    c.d_status.alloc(1);
+    CUDA_CHECK(cudaMemsetAsync(c.d_status.p, 0, sizeof(int), c.stream));
+  }
+  // All CTAs must be co-resident (they wait on each other): one per SM.
+  for (int cls : {CLS_ST, CLS_CST, CLS_CAAS}) {
+    if (c.is_caas != (cls == CLS_CAAS)) continue;
+    const void* fn = ring_kernel_ptr(cls, R.np, R.sw);
+    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(R.smem)));
+    int per_sm = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      &per_sm, fn, ring::block_threads(R.np, R.sw), R.smem));
+    int nsm_real = 0;
+    CUDA_CHECK(cudaDeviceGetAttribute(&nsm_real, cudaDevAttrMultiProcessorCount, dev));
+    if (per_sm*nsm_real < R.grid) return;
+  }
+  c.ring_ok = true;
+}
+
+// Constants of the nodes above the micro-roots, after the rhom sweep of this run().
+void ring_gather (cedr_b200_cdr& c) {
+  cedr_b200_cdr::Ring& R = c.ring;
+  if (R.mni == 0) return;
+  LaunchTimer lt(c, CEDR_B200_TAG_RHOM, 1);
+  ring::gather_kernel<<<(R.mni + 255)/256, 256, 0, c.stream>>>(
+    R.msrc.p, R.mni, c.d_fwq.p, c.d_frh.p, c.d_nc.p, R.mwq.p, R.mrh.p);
+  CUDA_CHECK(cudaGetLastError());
+  ++c.last_launches;
+}
+
+void launch_ring (cedr_b200_cdr& c, int cls) {
+  const int ntr = static_cast<int>(c.cls_tracers[cls].size());
+  if (ntr == 0) return;
+  cedr_b200_cdr::Ring& R = c.ring;
+  ring::Args a;
+  std::memset(&a, 0, sizeof(a));
+  a.pieces = R.pieces.p;
+  a.d7tab = R.d7tab.p;
+  a.d7c = R.d7c.p;
+  a.pairtab = R.pairtab.p;
+  a.topc = R.topc.p;
+  a.wq = c.d_fwq.p;
+  a.rh = c.d_frh.p;
+  a.in = c.in;
+  a.in_ld = c.ld;
+  a.trcr_row = c.d_trcr_row.p;
+  a.trcr_prob = c.d_trcr_prob.p;
+  a.out = c.out;
+  a.out_ld = c.ld;
+  a.rec = R.rec.p;
+  a.rec_ld = R.ld;
+  a.sol = R.sol.p;
+  a.sol_ld = R.ld;
+  a.scal = c.d_caas_scal.p;
+  a.tracers = c.d_cls_tracers[cls].p;
+  a.ntr = ntr;
+  a.S = R.S;
+  a.npn = R.npn;
+  a.npairs_max = R.npairs_max;
+  a.TB = R.TB;
+  a.plen = R.plen;
+  a.nslots = R.nslots;
+  a.npslots = R.npslots;
+  a.prefer_mass_con = c.prefer_mass_con;
+  a.caas_rows = c.caas_need_conserve ? 4 : 3;
+  a.cnt = R.sync.p;
+  a.flag = R.sync.p + ntr;
+  a.status = c.d_status.p;
+  a.spin_limit = static_cast<unsigned long long>(env_int("CEDR_B200_RING_TIMEOUT_MS", 4000))*1000000ull;
+  a.top.M = R.M;
+  a.top.ni = R.mni;
+  a.top.nlev = R.mnlev;
+  a.top.lvlptr = R.lvlptr.p;
+  a.top.kid0 = R.kid0.p;
+  a.top.kid1 = R.kid1.p;
+  a.top.mwq = R.mwq.p;
+  a.top.mrh = R.mrh.p;
+  a.top.micro_c = R.micro_c.p;
+  a.top.micro_h = R.micro_h.p;
+  CUDA_CHECK(cudaMemsetAsync(R.sync.p, 0, 2*static_cast<size_t>(ntr)*sizeof(unsigned),
+                             c.stream));
+  if (std::getenv("CEDR_B200_RING_TRACE")) {
+    const size_t U = (static_cast<size_t>(ntr) + R.TB - 1)/R.TB;
+    R.trace_n = static_cast<size_t>(R.grid)*U*8 + 2*static_cast<size_t>(ntr);
+    if (R.trace.n < R.trace_n) R.trace.alloc(R.trace_n);
+    CUDA_CHECK(cudaMemsetAsync(R.trace.p, 0, R.trace_n*sizeof(unsigned long long), c.stream));
+    a.trace = R.trace.p;
+  }
+  void* params[] = {&a};
+  const void* fn = ring_kernel_ptr(cls, R.np, R.sw);
+  LaunchTimer lt(c, CEDR_B200_TAG_FUSED, 0);
+  CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(R.grid), dim3(ring::block_threads(R.np, R.sw)),
+                                         params, R.smem, c.stream));
+  ++c.last_launches;
+}
+
 // rhom sweep of tiers [k0, k1).
 void run_rhom (cedr_b200_cdr& c, int k0, int k1) {
   const int ntiers = static_cast<int>(c.plan.tiers.size());
@@ -849,7 +1207,7 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
   // Classes on the fast kernels hand their blocks' sub-roots to the expanded tier.
   auto via_x = [&] (int cls) {
     return c.split && c.x_tier && c.fast_ok && fast_class(cls, MODE_DOWN) &&
-      ! (c.fused_ok && fused_class(cls));
+      ! (c.fused_ok && fused_class(cls)) && ! (c.ring_ok && ring_class(cls));
   };
   if (solo_ok(c)) {
     for (int cls = 0; cls < CLS_CAAS; ++cls)
@@ -863,6 +1221,7 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
   if (phase <= 0) {
     run_rhom(c, 0, multi ? 1 : ntiers);
     if ( ! multi) run_rhom_x(c);
+    if (c.ring_ok) ring_gather(c);
     if (multi) {
       for (int cls = 0; cls < CLS_CAAS; ++cls)
         if ( ! c.cls_tracers[cls].empty()) {
@@ -880,6 +1239,7 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
     }
     for (int cls = 0; cls < CLS_CAAS; ++cls) {
       if (c.cls_tracers[cls].empty()) continue;
+      if (c.ring_ok && ring_class(cls)) { launch_ring(c, cls); continue; }
       if (c.fused_ok && fused_class(cls)) { launch_fused(c, cls); continue; }
       if (via_x(cls)) {
         if ( ! multi) launch_up(c, cls, 0);
@@ -921,6 +1281,7 @@ void run_caas (cedr_b200_cdr& c, int phase) {
     ++c.last_launches;
     return;
   }
+  if (c.ring_ok) { launch_ring(c, CLS_CAAS); return; }
   if (c.fused_ok) { launch_fused(c, CLS_CAAS); return; }
   if (solo_ok(c)) { launch_solo(c, CLS_CAAS); return; }
   const int ntiers = static_cast<int>(c.plan.tiers.size());
@@ -1125,6 +1486,7 @@ void finish_setup (cedr_b200_cdr& c) {
     c.xrecv = c.xrecv_own.p;
   }
   fused_setup(c);
+  ring_setup(c);
   c.finished = true;
 }
 
@@ -1551,8 +1913,15 @@ int cedr_b200_synchronize (cedr_b200_cdr* c) {
     if (c->d_status.p) {
       int st = 0;
       CUDA_CHECK(cudaMemcpy(&st, c->d_status.p, sizeof(int), cudaMemcpyDeviceToHost));
-      if (st) throw std::runtime_error("cedr_b200: the fused run() kernel gave up waiting "
-                                       "for a tracer's root (results are invalid)");
+      if (st) {
+        // Report once; the next run() starts clean.
+        CUDA_CHECK(cudaMemset(c->d_status.p, 0, sizeof(int)));
+        if (st == 2)
+          throw std::runtime_error("cedr_b200: the peer-to-peer exchange gave up waiting for "
+                                   "another rank's block roots (results are invalid)");
+        throw std::runtime_error("cedr_b200: the persistent run() kernel gave up waiting for "
+                                 "a tracer's root (results are invalid)");
+      }
     }
   });
 }
@@ -1574,6 +1943,35 @@ int cedr_b200_set_fused (cedr_b200_cdr* c, int on, int depth) {
     cedr_b200_throw_if(c->finished, "set_fused must precede finish_setup");
     c->fused_enabled = on != 0;
     if (depth > 0) c->fused_depth = depth;
+  });
+}
+
+int cedr_b200_set_ring (cedr_b200_cdr* c, int on) {
+  return guarded([&] {
+    cedr_b200_throw_if(c->finished, "set_ring must precede finish_setup");
+    c->ring_enabled = on != 0;
+  });
+}
+
+int cedr_b200_uses_ring (const cedr_b200_cdr* c, int* on) {
+  return guarded([&] { *on = c->ring_ok; });
+}
+
+int cedr_b200_ring_info (const cedr_b200_cdr* c, int* info8) {
+  return guarded([&] {
+    const cedr_b200_cdr::Ring& R = c->ring;
+    const int v[8] = {R.grid, R.S, R.npn, R.TB, R.nslots, R.np, R.sw, static_cast<int>(R.smem)};
+    for (int i = 0; i < 8; ++i) info8[i] = c->ring_ok ? v[i] : 0;
+  });
+}
+
+int cedr_b200_ring_trace (cedr_b200_cdr* c, unsigned long long* host, size_t cap, size_t* n) {
+  return guarded([&] {
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *n = c->ring.trace_n;
+    if (host && c->ring.trace.p)
+      CUDA_CHECK(cudaMemcpy(host, c->ring.trace.p, std::min(cap, c->ring.trace_n)*sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost));
   });
 }
 

@@ -254,6 +254,21 @@ int cedr_b200_uses_fast_path(const cedr_b200_cdr* cdr, int* on);
  * (default 2). Results are bit-identical either way. */
 int cedr_b200_set_fused(cedr_b200_cdr* cdr, int on, int depth);
 int cedr_b200_uses_fused(const cedr_b200_cdr* cdr, int* on);
+/* The default run() for the shape-preserving QLT classes and CAAS where the fast shapes
+ * apply on one rank: ONE persistent cooperative kernel per problem class
+ * (ring_kernels.cuh) that replaces QLT::run's 2*nlev+1 launches (cedr_qlt.cpp:618-640) and
+ * CAAS::run's three (cedr_caas.cpp:258-270). Every CTA owns a fixed piece of the leaves;
+ * a tracer's piece stays in shared memory between the up- and the down-sweep, so the
+ * leaves cross HBM once. set_ring(0) before finish_setup forces the multi-launch path;
+ * uses_ring reports the choice; ring_info returns {grid, sub-root depth, depth-7 nodes
+ * per piece, tracers per unit, ring slots, L groups, S warps, dynamic smem bytes}.
+ * Results are bit-identical either way. */
+int cedr_b200_set_ring(cedr_b200_cdr* cdr, int on);
+int cedr_b200_uses_ring(const cedr_b200_cdr* cdr, int* on);
+int cedr_b200_ring_info(const cedr_b200_cdr* cdr, int* info8_host);
+/* Debug: per-unit, per-stage device timestamps of the last ring launch (only recorded when
+ * the environment variable CEDR_B200_RING_TRACE is set); see tools/ring_trace.py. */
+int cedr_b200_ring_trace(cedr_b200_cdr* cdr, unsigned long long* host, size_t cap, size_t* n);
 
 /* Per-launch device times of run(): with profiling on, every kernel launch of
  * run() is bracketed by CUDA events on the CDR's stream (measurement aid for
