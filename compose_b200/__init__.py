@@ -87,8 +87,6 @@ SYMBOLS = [
     ("cedr_b200_set_fast_path", C.c_int, [_H, C.c_int]),
     ("cedr_b200_uses_fast_path", C.c_int, [_H, _ip]),
     ("cedr_b200_debug_phase_clocks", C.c_int, [_H, C.POINTER(C.c_ulonglong)]),
-    ("cedr_b200_set_fused", C.c_int, [_H, C.c_int, C.c_int]),
-    ("cedr_b200_uses_fused", C.c_int, [_H, _ip]),
     ("cedr_b200_set_ring", C.c_int, [_H, C.c_int]),
     ("cedr_b200_uses_ring", C.c_int, [_H, _ip]),
     ("cedr_b200_ring_info", C.c_int, [_H, _ip]),
@@ -370,14 +368,6 @@ class CDR:
         _check(self._lib.cedr_b200_uses_fast_path(self._h, C.byref(v)))
         return bool(v.value)
 
-    def set_fused(self, on=True, depth=0):
-        _check(self._lib.cedr_b200_set_fused(self._h, int(bool(on)), int(depth)))
-
-    def uses_fused(self):
-        v = C.c_int(0)
-        _check(self._lib.cedr_b200_uses_fused(self._h, C.byref(v)))
-        return bool(v.value)
-
     def set_ring(self, on=True):
         _check(self._lib.cedr_b200_set_ring(self._h, int(bool(on))))
 
@@ -390,7 +380,9 @@ class CDR:
         v = (C.c_int*8)()
         _check(self._lib.cedr_b200_ring_info(self._h, v))
         keys = ("grid", "S", "npn", "TB", "nslots", "np", "sw", "smem")
-        return dict(zip(keys, list(v)))
+        d = dict(zip(keys, list(v)))
+        d["nuslots"], d["ndslots"] = divmod(d.pop("nslots"), 100)
+        return d
 
     def ring_trace(self):
         """Debug (CEDR_B200_RING_TRACE=1): numpy uint64 stamps of the last ring launch."""

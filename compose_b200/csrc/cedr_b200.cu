@@ -21,7 +21,6 @@
 
 #include "kernels.cuh"
 #include "fast_kernels.cuh"
-#include "fused_kernels.cuh"
 #include "ring_kernels.cuh"
 #include "tree_plan.h"
 
@@ -161,10 +160,6 @@ struct cedr_b200_cdr {
   DevBuf<double> d_frq;
   bool fast_enabled = true;   // cedr_b200_set_fast_path
   bool fast_ok = false;       // plan + buffers allow the fast tier-0 kernels
-  bool fused_enabled = false; // cedr_b200_set_fused (opt-in until it beats the multi-launch path)
-  bool fused_ok = false;      // plan + device allow the fused persistent kernel
-  int fused_depth = 2;        // tracers between UP(k) and DOWN(k)
-  int fused_capacity = 0;     // co-resident CTAs of the fused kernel on this device
   DevBuf<unsigned long long> d_phase_clk;   // debug (CEDR_B200_PHASE_CLOCKS builds)
   DevBuf<double> d_n7;        // depth-7 sums per own block x tracer (fast path)
   // Expanded tier above the fast blocks (FastArgs::split): its leaves are the 2^split
@@ -177,11 +172,12 @@ struct cedr_b200_cdr {
   DevBuf<dev::NodeConst> d_xnc;
   DevBuf<double> d_xrhom, d_xrec, d_xsol;
   // Persistent single-read kernel (ring_kernels.cuh), the default run() where it applies.
-  bool ring_enabled = true;   // cedr_b200_set_ring
+  bool ring_enabled = false;  // cedr_b200_set_ring (opt-in: slower than the multi-launch path today)
   bool ring_ok = false;
   struct Ring {
-    int grid = 0, S = 0, npn = 0, npairs_max = 0, TB = 1, plen = 0, nslots = 0, npslots = 0;
-    int np = 3, sw = 1;
+    int grid = 0, S = 0, npn = 0, npairs_max = 0, TB = 1, plen = 0, nuslots = 0, ndslots = 0;
+    int maxlag = 0, n7len = 0;
+    int np = 3, sw = 2;
     int M = 0, mni = 0, mnlev = 0;
     long long ld = 0;         // padded sub-root count
     size_t smem = 0;
@@ -192,12 +188,12 @@ struct cedr_b200_cdr {
     DevBuf<int> topc, lvlptr, kid0, kid1, micro_c, micro_h, msrc;
     DevBuf<dev::NodeWQ> mwq;
     DevBuf<dev::NodeRh> mrh;
-    DevBuf<double> rec, sol;
+    DevBuf<double> rec, sol, n7ring;
+    DevBuf<int2> ktab[NCLS];
     DevBuf<unsigned> sync;    // [2 nt]: arrivals, flags
     DevBuf<unsigned long long> trace;   // debug (CEDR_B200_RING_TRACE)
     size_t trace_n = 0;
   } ring;
-  DevBuf<unsigned> d_sync;    // [2 nt]: arrival counters, flags
   DevBuf<int> d_status;
   std::vector<DevBuf<BlockDev> > d_blocks;   // per tier
   DevBuf<dev::NodeConst> d_nc;
@@ -467,97 +463,6 @@ void launch_fast_down (cedr_b200_cdr& c, int cls) {
                 fast::kDown2Threads);
 }
 
-// ---- fused persistent kernel (fused_kernels.cuh)
-
-bool fused_class (int cls) { return cls == CLS_ST || cls == CLS_CST || cls == CLS_CAAS; }
-
-template <int CLS> int fused_capacity_of (const size_t smem) {
-  CUDA_CHECK(cudaFuncSetAttribute(fused::run_kernel<CLS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
-  int per_sm = 0, dev = 0, nsm = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused::run_kernel<CLS>,
-                                                           fused::kThreads, smem));
-  CUDA_CHECK(cudaGetDevice(&dev));
-  CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  return per_sm*nsm;
-}
-
-int fused_sbuf (const cedr_b200_cdr& c) { return (c.plan.tiers[0].max_nl + 2 + 1) & ~1; }
-
-// Decide whether run() can be the fused kernel; called from finish_setup.
-void fused_setup (cedr_b200_cdr& c) {
-  c.fused_ok = false;
-  if ( ! c.fused_enabled || ! c.fast_ok || std::getenv("CEDR_B200_NO_FUSED")) return;
-  if (c.nranks > 1) return;
-  if (c.is_caas && c.caas_sum_mode != CEDR_B200_CAAS_SUM_TREE) return;
-  if (c.plan.tiers.size() != 2 || c.plan.tiers[1].blocks.size() != 1) return;
-  const int sbuf = fused_sbuf(c);
-  const size_t nl1 = c.plan.tiers[1].nleaves;
-  if (4*(2*nl1 - 1) > fused::top_scratch_doubles(sbuf)) return;
-  int dev = 0, coop = 0;
-  CUDA_CHECK(cudaGetDevice(&dev));
-  CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-  if ( ! coop) return;
-  const size_t smem = fused::smem_bytes(sbuf);
-  int cap = c.is_caas ? fused_capacity_of<CLS_CAAS>(smem) :
-    std::min(fused_capacity_of<CLS_ST>(smem), fused_capacity_of<CLS_CST>(smem));
-  if (cap < static_cast<int>(c.plan.tiers[0].blocks.size())) return;
-  c.fused_capacity = cap;
-  if (const char* e = std::getenv("CEDR_B200_FUSED_DEPTH"))
-    c.fused_depth = std::max(1, std::atoi(e));
-  c.d_sync.alloc(2*std::max<size_t>(1, c.trcr_prob.size()));
-  c.d_status.alloc(1);
-  CUDA_CHECK(cudaMemsetAsync(c.d_status.p, 0, sizeof(int), c.stream));
-  c.fused_ok = true;
-}
-
-
-void launch_fused (cedr_b200_cdr& c, int cls) {
-  const int ntr = static_cast<int>(c.cls_tracers[cls].size());
-  if (ntr == 0) return;
-  fused::Args a;
-  std::memset(&a, 0, sizeof(a));
-  a.blocks = c.d_blocks[0].p;
-  a.nblocks = static_cast<int>(c.plan.tiers[0].blocks.size());
-  a.dtab = c.d_dtab.p;
-  a.ptab = c.d_ptab.p;
-  a.wq = c.d_fwq.p;
-  a.rh = c.d_frh.p;
-  a.in = c.in;
-  a.in_ld = c.ld;
-  a.trcr_row = c.d_trcr_row.p;
-  a.trcr_prob = c.d_trcr_prob.p;
-  a.rec = c.d_rec[1].p;
-  a.rec_ld = c.tier_ld[1];
-  a.sol = c.d_sol[1].p;
-  a.sol_ld = c.tier_ld[1];
-  a.out = c.out;
-  a.out_ld = c.ld;
-  a.tracers = c.d_cls_tracers[cls].p;
-  a.ntr = ntr;
-  a.sbuf = fused_sbuf(c);
-  a.prefer_mass_con = c.prefer_mass_con;
-  a.depth = c.fused_depth;
-  a.cnt = c.d_sync.p;
-  a.flag = c.d_sync.p + ntr;
-  a.status = c.d_status.p;
-  a.caas_scal = c.d_caas_scal.p;
-  a.top = base_args(c, cls, 1);
-  const int nlanes = std::max(1, std::min(c.fused_capacity/a.nblocks, ntr));
-  const dim3 grid(static_cast<unsigned>(a.nblocks)*nlanes), block(fused::kThreads);
-  const size_t smem = fused::smem_bytes(a.sbuf);
-  CUDA_CHECK(cudaMemsetAsync(c.d_sync.p, 0, 2*static_cast<size_t>(ntr)*sizeof(unsigned),
-                             c.stream));
-  void* params[] = {&a};
-  const void* fn = cls == CLS_ST ? reinterpret_cast<const void*>(fused::run_kernel<CLS_ST>) :
-    cls == CLS_CST ? reinterpret_cast<const void*>(fused::run_kernel<CLS_CST>) :
-    reinterpret_cast<const void*>(fused::run_kernel<CLS_CAAS>);
-  LaunchTimer lt(c, CEDR_B200_TAG_FUSED, 0);
-  CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, block, params, smem, c.stream));
-  ++c.last_launches;
-}
-
 // ---- persistent single-read kernel (ring_kernels.cuh)
 
 bool ring_class (int cls) { return cls == CLS_ST || cls == CLS_CST || cls == CLS_CAAS; }
@@ -565,8 +470,8 @@ bool ring_class (int cls) { return cls == CLS_ST || cls == CLS_CST || cls == CLS
 const void* ring_kernel_ptr (int cls, int np, int sw) {
 #define CEDR_RK(C, N, W) reinterpret_cast<const void*>(ring::run_kernel<C, N, W>)
 #define CEDR_RK_CLS(C)                                                  \
-  (np == 2 ? (sw == 1 ? CEDR_RK(C, 2, 1) : CEDR_RK(C, 2, 2))            \
-           : (sw == 1 ? CEDR_RK(C, 3, 1) : CEDR_RK(C, 3, 2)))
+  (np == 2 ? (sw == 2 ? CEDR_RK(C, 2, 2) : CEDR_RK(C, 2, 4))            \
+           : (sw == 2 ? CEDR_RK(C, 3, 2) : CEDR_RK(C, 3, 4)))
   switch (cls) {
   case CLS_ST: return CEDR_RK_CLS(CLS_ST);
   case CLS_CST: return CEDR_RK_CLS(CLS_CST);
@@ -642,8 +547,8 @@ void ring_setup (cedr_b200_cdr& c) {
   R.grid = G;
   R.npn = per*nhp;
   R.ld = round_up(N1, 16);
-  R.np = std::max(2, std::min(3, env_int("CEDR_B200_RING_NP", c.is_caas ? 2 : 3)));
-  R.sw = std::max(1, std::min(2, env_int("CEDR_B200_RING_SW", 1)));
+  R.np = std::max(2, std::min(3, env_int("CEDR_B200_RING_NP", c.is_caas ? 3 : 2)));
+  R.sw = env_int("CEDR_B200_RING_SW", 2) >= 4 ? 4 : 2;
 
   // ---- pieces
   std::vector<ring::PieceDev> pieces(G);
@@ -715,27 +620,57 @@ void ring_setup (cedr_b200_cdr& c) {
   }
   R.plen = (maxnl + 2 + 1) & ~1;
 
-  // ---- tracers per unit and ring depth, from the shared-memory budget
-  const bool has_prev = c.is_caas ? c.caas_need_conserve : ! c.cls_tracers[CLS_CST].empty();
+  // ---- the tree over the micro-roots is sized first (it sits in shared memory)
   const int M = nb << (S - 3);
+  const int mni_est = ((1 << (S - 3)) - 1)*nb + c.plan.shapes[c.plan.tiers[1].blocks[0].shape].ni;
+  const int mnlev_est = (S - 3) + c.plan.shapes[c.plan.tiers[1].blocks[0].shape].nlev;
+  if (M + mni_est > 0xffff) return;
+
+  // ---- tracers per unit and ring depths, from the shared-memory budget
   int TB = std::max(1, std::min(std::min(ring::kMaxTB, nt), ring::kGroup/R.npn));
   TB = std::max(1, std::min(TB, env_int("CEDR_B200_RING_TB", TB)));
   const size_t budget = static_cast<size_t>(smem_max) - 1024;
   for (;; TB = std::max(1, TB/2)) {
-    const int nps = has_prev ? std::max(2, env_int("CEDR_B200_RING_PSLOTS", 3)) : 0;
-    const ring::SmemLayout l0 = ring::smem_layout(TB, R.plen, 0, nps, R.np, M, R.npn,
-                                                  R.npairs_max, c.is_caas);
-    const size_t per_slot = sizeof(double)*l0.slot_doubles + 4*sizeof(uint64_t);
-    int ns = l0.total < budget ? static_cast<int>((budget - l0.total)/per_slot) : 0;
-    ns = std::min(ns, ring::kMaxSlots);
-    ns = std::min(ns, env_int("CEDR_B200_RING_SLOTS", ns));
-    if (ns >= R.np + 1) {
-      R.TB = TB; R.nslots = ns; R.npslots = nps;
-      R.smem = ring::smem_layout(TB, R.plen, ns, nps, R.np, M, R.npn, R.npairs_max,
-                                 c.is_caas).total;
+    const ring::SmemLayout l0 = ring::smem_layout(TB, R.plen, 0, 0, R.np, M, mni_est, mnlev_est,
+                                                  R.npn, R.npairs_max, c.is_caas);
+    const size_t per_u = sizeof(double)*l0.uslot_doubles + 3*sizeof(uint64_t);
+    const size_t per_d = sizeof(double)*l0.dslot_doubles + 4*sizeof(uint64_t);
+    // The UP ring holds a unit from its load to its arrival, the DOWN ring from its re-load
+    // through the solves to its store: about 1 : 2.
+    int nu = 0, nd = 0;
+    if (l0.total < budget) {
+      const size_t avail = budget - l0.total;
+      nu = static_cast<int>(std::max<size_t>(2, avail/3/per_u));
+      nu = std::min(nu, env_int("CEDR_B200_RING_USLOTS", std::min(nu, 6)));
+      nd = avail > nu*per_u ? static_cast<int>((avail - nu*per_u)/per_d) : 0;
+      nd = std::min(nd, ring::kMaxSlots);
+      nd = std::min(nd, env_int("CEDR_B200_RING_DSLOTS", nd));
+      // (whatever the DOWN ring's cap left over goes to the UP ring)
+      if (avail > nd*per_d) nu = std::max(nu, std::min<int>(env_int("CEDR_B200_RING_USLOTS", ring::kMaxSlots),
+                                                       std::min<int>(ring::kMaxSlots, (avail - nd*per_d)/per_u)));
+    }
+    // A slot always serves the same pipe (slot = unit % depth): depths are multiples of
+    // the pipe count, so that every waiter sees the phases of its barriers in order.
+    nu = nu/R.np*R.np;
+    nd = nd/R.np*R.np;
+    if (nu >= R.np && nd >= R.np) {
+      R.TB = TB; R.nuslots = nu; R.ndslots = nd;
+      R.smem = ring::smem_layout(TB, R.plen, nu, nd, R.np, M, mni_est, mnlev_est, R.npn,
+                                 R.npairs_max, c.is_caas).total;
       break;
     }
     if (TB == 1) return;
+  }
+  // The UP pass may run ahead of the DOWN pass by what L2 holds comfortably (the leaves of
+  // the units in between are re-read from there).
+  {
+    const double unit_bytes = 32.0*c.nlcl*R.TB;
+    const double l2_window = 1e6*env_int("CEDR_B200_RING_L2_MB", 48);
+    R.maxlag = static_cast<int>(std::max(4.0, std::min(64.0, l2_window/unit_bytes)));
+    R.maxlag = env_int("CEDR_B200_RING_MAXLAG", R.maxlag);
+    // (the kernel's window over the tracer table spans the units in flight)
+    R.maxlag = std::max(1, std::min(R.maxlag, (ring::kWin - 96)/R.TB - R.nuslots - R.ndslots - 4));
+    R.n7len = R.maxlag + R.ndslots + 1;
   }
 
   // ---- the tree over the micro-roots: the blocks' nodes above depth S-3 (perfect, Ep
@@ -749,6 +684,7 @@ void ring_setup (cedr_b200_cdr& c) {
     for (int h = 1; h <= Sp; ++h) hstart[h + 1] = hstart[h] + nb*(1 << (Sp - h));
     auto xnode = [&] (int b, int d, int p) { return M + hstart[Sp - d] + b*(1 << d) + p; };
     const int ni = nx + s1.ni;
+    if (ni != mni_est) return;
     std::vector<int> kid0(ni), kid1(ni), lvlptr(1, 0), msrc(ni);
     for (int h = 1; h <= Sp; ++h) {
       const int d = Sp - h;
@@ -796,7 +732,17 @@ void ring_setup (cedr_b200_cdr& c) {
   R.topc.upload(topc);
   R.rec.alloc(static_cast<size_t>(4)*nt*R.ld);
   R.sol.alloc(static_cast<size_t>(nt)*R.ld);
+  if ( ! c.is_caas) {
+    R.n7ring.alloc(static_cast<size_t>(R.n7len)*R.grid*3*ring::kGroup);
+    CUDA_CHECK(cudaMemsetAsync(R.n7ring.p, 0, R.n7ring.n*sizeof(double), c.stream));
+  }
   R.sync.alloc(2*static_cast<size_t>(nt));
+  for (int cls : {CLS_ST, CLS_CST, CLS_CAAS}) {
+    std::vector<int2> kt;
+    for (int t : c.cls_tracers[cls])
+      kt.push_back(make_int2(t, c.trcr_row[t] | ((c.trcr_prob[t] & 1) << 30)));
+    R.ktab[cls].upload(kt);
+  }
   if ( ! c.d_status.p) {
     c.d_status.alloc(1);
     CUDA_CHECK(cudaMemsetAsync(c.d_status.p, 0, sizeof(int), c.stream));
@@ -853,14 +799,18 @@ void launch_ring (cedr_b200_cdr& c, int cls) {
   a.sol_ld = R.ld;
   a.scal = c.d_caas_scal.p;
   a.tracers = c.d_cls_tracers[cls].p;
+  a.ktab = R.ktab[cls].p;
   a.ntr = ntr;
   a.S = R.S;
   a.npn = R.npn;
   a.npairs_max = R.npairs_max;
   a.TB = R.TB;
   a.plen = R.plen;
-  a.nslots = R.nslots;
-  a.npslots = R.npslots;
+  a.nuslots = R.nuslots;
+  a.ndslots = R.ndslots;
+  a.maxlag = R.maxlag;
+  a.n7ring = R.n7ring.p;
+  a.n7len = R.n7len;
   a.prefer_mass_con = c.prefer_mass_con;
   a.caas_rows = c.caas_need_conserve ? 4 : 3;
   a.cnt = R.sync.p;
@@ -881,10 +831,11 @@ void launch_ring (cedr_b200_cdr& c, int cls) {
                              c.stream));
   if (std::getenv("CEDR_B200_RING_TRACE")) {
     const size_t U = (static_cast<size_t>(ntr) + R.TB - 1)/R.TB;
-    R.trace_n = static_cast<size_t>(R.grid)*U*8 + 2*static_cast<size_t>(ntr);
+    R.trace_n = static_cast<size_t>(R.grid)*U*8 + 2*static_cast<size_t>(ntr) + 64;
     if (R.trace.n < R.trace_n) R.trace.alloc(R.trace_n);
     CUDA_CHECK(cudaMemsetAsync(R.trace.p, 0, R.trace_n*sizeof(unsigned long long), c.stream));
     a.trace = R.trace.p;
+    a.clk = R.trace.p + R.trace_n - 64;
   }
   void* params[] = {&a};
   const void* fn = ring_kernel_ptr(cls, R.np, R.sw);
@@ -1207,7 +1158,7 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
   // Classes on the fast kernels hand their blocks' sub-roots to the expanded tier.
   auto via_x = [&] (int cls) {
     return c.split && c.x_tier && c.fast_ok && fast_class(cls, MODE_DOWN) &&
-      ! (c.fused_ok && fused_class(cls)) && ! (c.ring_ok && ring_class(cls));
+      ! (c.ring_ok && ring_class(cls));
   };
   if (solo_ok(c)) {
     for (int cls = 0; cls < CLS_CAAS; ++cls)
@@ -1240,7 +1191,6 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
     for (int cls = 0; cls < CLS_CAAS; ++cls) {
       if (c.cls_tracers[cls].empty()) continue;
       if (c.ring_ok && ring_class(cls)) { launch_ring(c, cls); continue; }
-      if (c.fused_ok && fused_class(cls)) { launch_fused(c, cls); continue; }
       if (via_x(cls)) {
         if ( ! multi) launch_up(c, cls, 0);
         launch_top_x(c, cls);
@@ -1282,7 +1232,6 @@ void run_caas (cedr_b200_cdr& c, int phase) {
     return;
   }
   if (c.ring_ok) { launch_ring(c, CLS_CAAS); return; }
-  if (c.fused_ok) { launch_fused(c, CLS_CAAS); return; }
   if (solo_ok(c)) { launch_solo(c, CLS_CAAS); return; }
   const int ntiers = static_cast<int>(c.plan.tiers.size());
   const int top = ntiers - 1;
@@ -1485,7 +1434,6 @@ void finish_setup (cedr_b200_cdr& c) {
     c.xsend = c.xsend_own.p;
     c.xrecv = c.xrecv_own.p;
   }
-  fused_setup(c);
   ring_setup(c);
   c.finished = true;
 }
@@ -1604,7 +1552,7 @@ void bfb_finish (cedr_b200_cdr& c, int nfield) {
   cedr_b200_throw_if(nfield < 1, "nfield must be >= 1");
   c.is_bfb = true;
   c.fast_enabled = false;      // the generic sweeps carry the one-word records
-  c.fused_enabled = false;
+  c.ring_enabled = false;
   for (int j = 0; j < nfield; ++j) {
     c.trcr_prob.push_back(0);
     c.trcr_cls.push_back(CLS_BFB);
@@ -1938,14 +1886,6 @@ int cedr_b200_debug_phase_clocks (cedr_b200_cdr* c, unsigned long long* out16) {
   });
 }
 
-int cedr_b200_set_fused (cedr_b200_cdr* c, int on, int depth) {
-  return guarded([&] {
-    cedr_b200_throw_if(c->finished, "set_fused must precede finish_setup");
-    c->fused_enabled = on != 0;
-    if (depth > 0) c->fused_depth = depth;
-  });
-}
-
 int cedr_b200_set_ring (cedr_b200_cdr* c, int on) {
   return guarded([&] {
     cedr_b200_throw_if(c->finished, "set_ring must precede finish_setup");
@@ -1960,7 +1900,8 @@ int cedr_b200_uses_ring (const cedr_b200_cdr* c, int* on) {
 int cedr_b200_ring_info (const cedr_b200_cdr* c, int* info8) {
   return guarded([&] {
     const cedr_b200_cdr::Ring& R = c->ring;
-    const int v[8] = {R.grid, R.S, R.npn, R.TB, R.nslots, R.np, R.sw, static_cast<int>(R.smem)};
+    const int v[8] = {R.grid, R.S, R.npn, R.TB, R.nuslots*100 + R.ndslots, R.np, R.sw,
+                      static_cast<int>(R.smem)};
     for (int i = 0; i < 8; ++i) info8[i] = c->ring_ok ? v[i] : 0;
   });
 }
@@ -1973,10 +1914,6 @@ int cedr_b200_ring_trace (cedr_b200_cdr* c, unsigned long long* host, size_t cap
       CUDA_CHECK(cudaMemcpy(host, c->ring.trace.p, std::min(cap, c->ring.trace_n)*sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost));
   });
-}
-
-int cedr_b200_uses_fused (const cedr_b200_cdr* c, int* on) {
-  return guarded([&] { *on = c->fused_ok; });
 }
 
 int cedr_b200_set_allgather (cedr_b200_cdr* c, cedr_b200_allgather_fn fn, void* ctx) {

@@ -246,23 +246,15 @@ int cedr_b200_last_run_launches(const cedr_b200_cdr* cdr, int* n);
  * the choice after finish_setup. */
 int cedr_b200_set_fast_path(cedr_b200_cdr* cdr, int on);
 int cedr_b200_uses_fast_path(const cedr_b200_cdr* cdr, int* on);
-/* When the fast shapes apply and the block roots form a single tier-1 block, run() is
- * ONE persistent cooperative kernel per problem class (fused_kernels.cuh): up-sweep,
- * tier-1 sweep and down-sweep pipelined over tracers, the down-sweep re-reading the
- * leaves from L2. set_fused(0, 0) before finish_setup forces the multi-launch path;
- * depth > 0 sets the number of tracers between a block's up- and down-sweep
- * (default 2). Results are bit-identical either way. */
-int cedr_b200_set_fused(cedr_b200_cdr* cdr, int on, int depth);
-int cedr_b200_uses_fused(const cedr_b200_cdr* cdr, int* on);
-/* The default run() for the shape-preserving QLT classes and CAAS where the fast shapes
- * apply on one rank: ONE persistent cooperative kernel per problem class
- * (ring_kernels.cuh) that replaces QLT::run's 2*nlev+1 launches (cedr_qlt.cpp:618-640) and
- * CAAS::run's three (cedr_caas.cpp:258-270). Every CTA owns a fixed piece of the leaves;
- * a tracer's piece stays in shared memory between the up- and the down-sweep, so the
- * leaves cross HBM once. set_ring(0) before finish_setup forces the multi-launch path;
- * uses_ring reports the choice; ring_info returns {grid, sub-root depth, depth-7 nodes
- * per piece, tracers per unit, ring slots, L groups, S warps, dynamic smem bytes}.
- * Results are bit-identical either way. */
+/* Opt-in (set_ring(1) before finish_setup) for the shape-preserving QLT classes and CAAS
+ * where the fast shapes apply on one rank: run() as ONE persistent cooperative kernel per
+ * problem class (ring_kernels.cuh) in place of QLT::run's 2*nlev+1 launches
+ * (cedr_qlt.cpp:618-640) and CAAS::run's three (cedr_caas.cpp:258-270). Every CTA owns a
+ * fixed piece of the leaves; the down-sweep re-reads them from L2 a few tracers behind the
+ * up-sweep, so the leaves cross HBM once. Bit-identical to the multi-launch path, which
+ * stays the default because it is faster today. uses_ring reports
+ * the choice; ring_info returns {grid, sub-root depth, depth-7 nodes per piece, tracers
+ * per unit, 100 x UP slots + DOWN slots, L groups, S warps, dynamic smem bytes}. */
 int cedr_b200_set_ring(cedr_b200_cdr* cdr, int on);
 int cedr_b200_uses_ring(const cedr_b200_cdr* cdr, int* on);
 int cedr_b200_ring_info(const cedr_b200_cdr* cdr, int* info8_host);

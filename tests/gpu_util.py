@@ -6,15 +6,15 @@ import numpy as np
 
 def run_qlt_gpu(ncells, ptypes, rhom, qm_min, qm, qm_max, qm_prev, tree=None,
                 imbalanced=False, prefer=False, max_block_leaves=None, nrun=1,
-                external_buffers=False, fused=None, depth=0):
+                external_buffers=False, ring=None):
     import torch
     import compose_b200 as cb
     q = cb.QLT(ncells, tree=tree, imbalanced=imbalanced,
                prefer_numerical_mass_conservation_to_numerical_bounds=prefer)
     if max_block_leaves:
         q.set_max_block_leaves(max_block_leaves)
-    if fused is not None:
-        q.set_fused(fused, depth)
+    if ring is not None:
+        q.set_ring(ring)
     for p in ptypes:
         q.declare_tracer(int(p))
     q.end_tracer_declarations()
@@ -33,7 +33,7 @@ def run_qlt_gpu(ncells, ptypes, rhom, qm_min, qm, qm_max, qm_prev, tree=None,
         q.set_Qm(*d)
         q.run()
         out = q.get_Qm()
-    q.synchronize()     # also raises if the fused kernel's watchdog fired
+    q.synchronize()     # also raises if the persistent kernel's watchdog fired
     torch.cuda.synchronize()
     res = np.empty((len(ptypes), ncells))
     res[:, gcis] = out.cpu().numpy()
@@ -41,14 +41,14 @@ def run_qlt_gpu(ncells, ptypes, rhom, qm_min, qm, qm_max, qm_prev, tree=None,
 
 
 def run_caas_gpu(ncells, ptypes, rhom, qm_min, qm, qm_max, qm_prev, max_block_leaves=None,
-                 external_buffers=False, fused=None, depth=0):
+                 external_buffers=False, ring=None, exact_buffers=False):
     import torch
     import compose_b200 as cb
     c = cb.CAAS(ncells)
     if max_block_leaves:
         c.set_max_block_leaves(max_block_leaves)
-    if fused is not None:
-        c.set_fused(fused, depth)
+    if ring is not None:
+        c.set_ring(ring)
     for p in ptypes:
         c.declare_tracer(int(p))
     c.end_tracer_declarations()

@@ -207,54 +207,55 @@ def test_errors_mirror_reference():
 
 @pytest.mark.parametrize("ncells", [5400, 8*513, 8*768, 8192, 2*1023, 3*700 + 1])
 @pytest.mark.parametrize("prefer", [False, True])
-@pytest.mark.parametrize("fused,depth", [(False, 0), (True, 1), (True, 2), (True, 3)])
-def test_fast_path_blocks_bitwise(oracle, ncells, prefer, fused, depth):
+@pytest.mark.parametrize("ring", [False, True])
+def test_fast_path_blocks_bitwise(oracle, ncells, prefer, ring):
     """Tier-0 blocks of 513..1024 leaves run the fast kernels (TMA + register
-    micro-subtrees) for the st/cst classes; same bits as the oracle and as the generic
-    kernels, for every block size class (few pairs .. all pairs)."""
-    import compose_b200 as cb
+    micro-subtrees) for the st/cst classes -- as separate launches (default) or as the
+    persistent ring kernel -- with the same bits as the oracle, for every block size class
+    (few pairs .. all pairs)."""
     from gpu_util import run_qlt_gpu
     ts, v = R.generate(ncells, seed=3*ncells + prefer)
     pts = [t.problem_type for t in ts]
     tree = oracle.bisection_tree(ncells)
     ref = oracle.qlt(tree, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev, prefer)
     got, q = run_qlt_gpu(ncells, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev,
-                         prefer=prefer, nrun=2, fused=fused, depth=depth)
+                         prefer=prefer, nrun=2, ring=ring)
     assert q.uses_fast_path()
-    assert q.uses_fused() == fused
+    assert q.uses_ring() == ring
     assert np.array_equal(got, ref)
     assert R.check(ts, v, got, prefer) == []
 
 
-@pytest.mark.parametrize("ncells,nt,depth", [(86400, 24, 2), (86400, 9, 1), (5400, 700, 2),
-                                             (5400, 333, 4), (8*768, 150, 3)])
-def test_fused_pipeline_many_tracers_bitwise(oracle, ncells, nt, depth):
-    """The fused persistent kernel with several tracers per CTA lane (the up/down
-    pipeline, the per-tracer arrival counters and the in-kernel tier-1 sweep all in play)
-    for QLT `cst` and CAAS, against the oracle and against the multi-launch path."""
+@pytest.mark.parametrize("ncells,nt", [(86400, 24), (86400, 9), (5400, 700), (5400, 333),
+                                       (8*768, 150), (2*1023, 41), (49152, 17)])
+def test_ring_kernel_many_tracers_bitwise(oracle, ncells, nt):
+    """The persistent ring kernel (one cooperative launch per class: pieces per CTA, units
+    of several tracers, the UP and DOWN passes, per-tracer arrival counters and flags, the
+    in-kernel sweep above the sub-roots) for QLT `cst` and CAAS, against the oracle and
+    against the multi-launch path."""
     from compose_b200 import workloads as W
     from gpu_util import run_qlt_gpu, run_caas_gpu
     rhom, lo, q, hi, prev = W.headline(ncells, nt, 3)
     pts = [7]*nt
     tree = oracle.bisection_tree(ncells)
     ref = oracle.qlt(tree, pts, rhom, lo, q, hi, prev)
-    got, c = run_qlt_gpu(ncells, pts, rhom, lo, q, hi, prev, nrun=2, fused=True, depth=depth)
-    assert c.uses_fused()
-    assert c.last_run_launches() <= 4
+    got, c = run_qlt_gpu(ncells, pts, rhom, lo, q, hi, prev, nrun=2, ring=True)
+    assert c.uses_ring()
+    assert c.last_run_launches() <= 5
     assert np.array_equal(got, ref)
     ref = oracle.caas(ncells, pts, lo, q, hi, prev, tree=tree)
-    got, c = run_caas_gpu(ncells, pts, rhom, lo, q, hi, prev, fused=True, depth=depth)
-    assert c.uses_fused() and c.last_run_launches() == 1
+    got, c = run_caas_gpu(ncells, pts, rhom, lo, q, hi, prev, ring=True)
+    assert c.uses_ring() and c.last_run_launches() == 1
     assert np.array_equal(got, ref)
-    got2, c2 = run_caas_gpu(ncells, pts, rhom, lo, q, hi, prev, fused=False)
-    assert not c2.uses_fused()
+    got2, c2 = run_caas_gpu(ncells, pts, rhom, lo, q, hi, prev, ring=False)
+    assert not c2.uses_ring()
     assert np.array_equal(got, got2)
 
 
-def test_fused_mixed_classes_and_noop_inputs(oracle):
-    """st and cst tracers go through the fused kernel, the other four classes through
-    the multi-launch kernels, in one run(); and inputs already in bounds with
-    Qm == Qm_prev must come back bit-for-bit (the quick exit, cedr_qlt_inl.hpp:145-160)."""
+def test_ring_mixed_classes_and_noop_inputs(oracle):
+    """st and cst tracers go through the ring kernel, the other four classes through the
+    multi-launch kernels, in one run(); and inputs already in bounds with Qm == Qm_prev must
+    come back bit-for-bit (the quick exit, cedr_qlt_inl.hpp:145-160)."""
     from compose_b200 import workloads as W
     from gpu_util import run_qlt_gpu
     ncells = 5400
@@ -262,13 +263,47 @@ def test_fused_mixed_classes_and_noop_inputs(oracle):
     pts = [t.problem_type for t in ts]
     tree = oracle.bisection_tree(ncells)
     ref = oracle.qlt(tree, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev)
-    got, c = run_qlt_gpu(ncells, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev, fused=True)
-    assert c.uses_fused()
+    got, c = run_qlt_gpu(ncells, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev, ring=True)
+    assert c.uses_ring()
     assert np.array_equal(got, ref)
     nt = 40
     rhom, lo, q, hi, prev = W.headline(ncells, nt, 5)
-    got, c = run_qlt_gpu(ncells, [7]*nt, rhom, lo, prev, hi, prev, fused=True)
+    got, c = run_qlt_gpu(ncells, [7]*nt, rhom, lo, prev, hi, prev, ring=True)
     assert np.array_equal(got, prev)
+
+
+@pytest.mark.parametrize("ring", [False, True])
+@pytest.mark.parametrize("ncells", [5400, 8*768])
+def test_caas_without_conserving_tracers_exact_buffers(oracle, ncells, ring):
+    """A CAAS whose tracers all lack `conserve` allots three rows per tracer
+    (cedr_caas.cpp:86-100): the fast kernels must not stage a fourth. The caller's buffers
+    are sized exactly to get_buffers_sizes() at the very end of an allocation."""
+    import torch
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    nt = 7
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, 4)
+    pts = [cb.SHAPEPRESERVE]*nt
+    ref = oracle.caas(ncells, pts, lo, q, hi, prev, tree=oracle.bisection_tree(ncells))
+    c = cb.CAAS(ncells)
+    c.set_ring(ring)
+    for p in pts:
+        c.declare_tracer(p)
+    c.end_tracer_declarations()
+    b1, b2 = c.get_buffers_sizes()
+    assert b1 == (1 + 3*nt)*((ncells + 15)//16*16)
+    # The buffer is the tail of a larger allocation: any read past it leaves the allocation.
+    pool = torch.zeros(b1 + 4096, dtype=torch.float64, device="cuda")
+    buf = pool[4096:]
+    c.set_buffers(buf, torch.zeros(1, dtype=torch.float64, device="cuda"))
+    c.finish_setup()
+    assert c.uses_fast_path() and c.uses_ring() == ring
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    c.set_rhom(dev(rhom))
+    c.set_Qm(dev(q), dev(lo), dev(hi), None)
+    c.run()
+    c.synchronize()
+    assert np.array_equal(c.get_Qm().cpu().numpy(), ref)
 
 
 def test_fast_and_generic_paths_agree_on_headline_inputs(oracle):
@@ -637,3 +672,72 @@ def test_qlt_block_granular_rank_map_bitwise(oracle):
     for q, g in zip(cdrs, gcis):
         res[:, g] = q.get_Qm().cpu().numpy()
     assert np.array_equal(res, ref)
+
+
+# ---------------------------------------------------------------- full sizes vs the oracle
+
+@pytest.mark.parametrize("workload,nt", [("ne120x128x40", 64), ("ne256x128x10", 8)])
+def test_default_path_full_size_bitwise_vs_oracle(oracle, workload, nt):
+    """The DEFAULT single-rank path at the cell counts of BASELINE.json's configs 3 and 4
+    (86,400 and 393,216 cells), on a slice of the workload's own tracers, bit for bit
+    against the oracle (QLT, and CAAS with tree-ordered sums). Tracers are independent
+    problems, so a slice of them is checked exactly as the whole would be."""
+    import torch
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    ncells, _, cid = W.CONFIGS[workload]
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, cid)
+    pts = [7]*nt
+    tree = oracle.bisection_tree(ncells)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    d = [dev(x) for x in (rhom, lo, q, hi, prev)]
+    for kind in ("qlt", "caas"):
+        c = cb.QLT(ncells) if kind == "qlt" else cb.CAAS(ncells)
+        for p in pts:
+            c.declare_tracer(p)
+        c.end_tracer_declarations()
+        c.finish_setup()
+        assert c.uses_fast_path() and not c.uses_ring()
+        c.set_rhom(d[0])
+        c.set_Qm(d[2], d[1], d[3], d[4])
+        c.run()
+        c.synchronize()
+        got = c.get_Qm().cpu().numpy()
+        ref = (oracle.qlt(tree, pts, rhom, lo, q, hi, prev) if kind == "qlt"
+               else oracle.caas(ncells, pts, lo, q, hi, prev, tree=tree))
+        assert np.array_equal(got, ref), kind
+
+
+def test_against_the_reference_itself_when_present(oracle):
+    """Straight against the UNMODIFIED reference (oracle/_ref, built where /root/reference
+    exists and shipped to the GPU box), not through the C restatement: QLT bit for bit;
+    CAAS bit for bit against the reference CAAS driven through its own BfbTreeAllReducer
+    (tree-ordered sums), and its default sequential sums against our
+    CAAS_SUM_SEQUENTIAL mode."""
+    from oracle.oracle_py import Ref, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref is not built on this box")
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    from gpu_util import run_qlt_gpu, run_caas_gpu
+    r = Ref()
+    for ncells, nt in ((5400, 24), (86400, 6)):
+        rhom, lo, q, hi, prev = W.headline(ncells, nt, 2)
+        pts = [7]*nt
+        ref, _, _ = r.qlt(ncells, ("bisect", False), pts, rhom, lo, q, hi, prev)
+        got, _ = run_qlt_gpu(ncells, pts, rhom, lo, q, hi, prev)
+        assert np.array_equal(got, ref)
+        ref, _ = r.caas(ncells, pts, rhom, lo, q, hi, prev, tree=("bisect", False))
+        got, _ = run_caas_gpu(ncells, pts, rhom, lo, q, hi, prev)
+        assert np.array_equal(got, ref)
+    # the randomized six-class set, balanced and imbalanced trees, both options
+    for imb in (False, True):
+        for prefer in (False, True):
+            ncells = 1000
+            ts, v = R.generate(ncells, seed=17 + imb + 2*prefer)
+            pts = [t.problem_type for t in ts]
+            ref, _, _ = r.qlt(ncells, ("bisect", imb), pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max,
+                              v.Qm_prev, prefer_mass_con=prefer)
+            got, _ = run_qlt_gpu(ncells, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev,
+                                 imbalanced=imb, prefer=prefer)
+            assert np.array_equal(got, ref)

@@ -103,9 +103,16 @@ if __name__ == "__main__":
     ap.add_argument("--time", default=None)
     ap.add_argument("--nt", type=int, default=0)
     ap.add_argument("--skip-check", action="store_true")
+    ap.add_argument("--case", action="append", default=[],
+                    help="kind,ncells,nt (repeatable): check only these")
     a = ap.parse_args()
     ok = True
-    if not a.skip_check:
+    if a.case:
+        for cs in a.case:
+            kind, nc, nt = cs.split(",")
+            ok &= check(kind, int(nc), int(nt))
+        print("ALL OK" if ok else "SOME FAILED")
+    elif not a.skip_check:
         for kind in ("caas", "qlt"):
             for ncells, nt in ((5400, 3), (5400, 40), (86400, 7), (86400, 40), (2*1023, 5)):
                 ok &= check(kind, ncells, nt)

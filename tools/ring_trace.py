@@ -35,9 +35,12 @@ print("run: %.3f ms" % e0.elapsed_time(e1), c.ring_info())
 info = c.ring_info()
 tr = c.ring_trace().astype(np.int64)
 G, TB = info["grid"], info["TB"]
+if not TB: raise SystemExit("ring kernel not used")
 U = (nt + TB - 1)//TB
 units = tr[:G*U*8].reshape(G, U, 8)
-strace = tr[G*U*8:].reshape(nt, 2)
+strace = tr[G*U*8:G*U*8 + 2*nt].reshape(nt, 2)
+clk = tr[G*U*8 + 2*nt:].reshape(32, 2)
+tr = tr[:G*U*8 + 2*nt]
 t0 = units[units > 0].min()
 names = ["load", "UPstart", "UPend", "T-UPend", "DNstart", "T-DNend", "L-DNend", "store"]
 mid = slice(U//4, 3*U//4)
@@ -71,3 +74,13 @@ if TB == 1:
     print("%-36s %s" % ("S done -> first DOWN start", stat(first_dn[k] - strace[k, 1])))
     arr = units[:, mid, 3].astype(np.float64)
     print("%-36s %s" % ("arrival skew over CTAs (max-min)", stat(arr.max(axis=0) - arr.min(axis=0))))
+
+names = {0: "L decision poll", 1: "L decision barrier", 2: "L UP smem loads+sums", 3: "L UP n7/shuffles/records",
+         4: "L UP arrive", 5: "L DOWN compute (QLT: d7..d9)", 6: "L DOWN fence+arrive", 7: "L loop top",
+         16: "L DOWN barrier", 17: "L DOWN pairs", 8: "T arrival (fence+red)", 9: "T-DOWN loads",
+         10: "T-DOWN sums", 11: "T-DOWN solves", 18: "T idle/poll", 12: "S flag release", 13: "S loads + micro sums",
+         14: "S tree over micro-roots", 15: "S micro solves", 20: "P store", 21: "P reload", 22: "P load", 23: "P idle"}
+print("phase clocks, CTA 0 (cycles per occurrence, occurrences):")
+for i in sorted(names):
+    if clk[i, 1]:
+        print("  %-32s %9.0f  x %d" % (names[i], clk[i, 0]/clk[i, 1], clk[i, 1]))
