@@ -293,8 +293,12 @@ class CDR:
             # Enqueue the collective on the CDR's own stream (the pack / unpack kernels
             # either side of it run there), whatever torch's current stream is.
             try:
-                with torch.cuda.stream(torch.cuda.ExternalStream(int(stream or 0))):
+                sp = int(stream or 0)
+                if sp == torch.cuda.current_stream().cuda_stream:
                     dist.all_gather_into_tensor(self._xrecv, self._xsend, group=group)
+                else:
+                    with torch.cuda.stream(torch.cuda.ExternalStream(sp)):
+                        dist.all_gather_into_tensor(self._xrecv, self._xsend, group=group)
                 return 0
             except Exception:   # surfaced as a CedrError by run()
                 import traceback

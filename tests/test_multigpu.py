@@ -24,7 +24,7 @@ def _ngpus():
         return 0
 
 
-def _worker(rank, world, port, ncells, nt, p2p, q):
+def _worker(rank, world, port, ncells, nt, p2p, q, side_stream=False):
     import torch
     import torch.distributed as dist
     import compose_b200 as cb
@@ -56,15 +56,23 @@ def _worker(rank, world, port, ncells, nt, p2p, q):
                 c.declare_tracer(p)
             c.end_tracer_declarations()
             c.enable_distributed(world)
-            c.finish_setup()
+            # side_stream: the CDR is bound to a non-default stream (finish_setup binds
+            # torch's current one) and driven from the default stream afterwards: the
+            # all-gather callback must enqueue on the CDR's stream, not on torch's current.
+            side = torch.cuda.Stream() if side_stream else None
+            with torch.cuda.stream(side) if side else torch.cuda.stream(torch.cuda.current_stream()):
+                c.finish_setup()
             if p2p:
                 c.enable_p2p(world)
-            c.set_rhom(dev(rhom))
+            d = [dev(x) for x in (rhom, qq, lo, hi, prev)]
+            torch.cuda.synchronize()
+            c.set_rhom(d[0])
             for rep in range(3):
-                c.set_Qm(dev(qq), dev(lo), dev(hi), dev(prev))
+                c.set_Qm(d[1], d[2], d[3], d[4])
                 c.run()
-                got = c.get_Qm().cpu().numpy()
+                out = c.get_Qm()
                 c.synchronize()
+                got = out.cpu().numpy()
                 ok = ok and np.array_equal(got, ref[:, sl])
         q.put((rank, ok))
     finally:
@@ -72,14 +80,14 @@ def _worker(rank, world, port, ncells, nt, p2p, q):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("p2p", [False, True])
-def test_two_gpus_bitwise(p2p):
+@pytest.mark.parametrize("p2p,side_stream", [(False, False), (True, False), (False, True)])
+def test_two_gpus_bitwise(p2p, side_stream):
     import torch.multiprocessing as mp
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 1000) + int(p2p)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 5400, 24, p2p, q))
+    port = 29600 + (os.getpid() % 1000) + int(p2p) + 2*int(side_stream)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 5400, 24, p2p, q, side_stream))
              for r in range(world)]
     for p in procs:
         p.start()
