@@ -16,7 +16,7 @@ import ctypes as C
 import os
 
 CONSERVE, SHAPEPRESERVE, CONSISTENT, NONNEGATIVE = 1, 2, 4, 8
-CAAS_SUM_TREE, CAAS_SUM_SEQUENTIAL = 0, 1
+CAAS_SUM_TREE, CAAS_SUM_SEQUENTIAL, CAAS_SUM_USER = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # CEDR_B200_LIB: a differently built copy of the library (kernel A/B experiments).
@@ -28,6 +28,7 @@ _lp = C.POINTER(C.c_int64)
 _vp = C.c_void_p
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, _vp, C.c_size_t, _vp)
+USER_REDUCER_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp)
 
 
 class DeviceOp(C.Structure):
@@ -49,6 +50,7 @@ SYMBOLS = [
                                           C.c_int]),
     ("cedr_b200_caas_create", C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.c_int64,
                                         C.c_int64, C.c_int, C.c_int]),
+    ("cedr_b200_caas_set_user_reducer", C.c_int, [_H, USER_REDUCER_FN, _vp, C.c_int]),
     ("cedr_b200_bfb_create", C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.c_int, _ip, _lp,
                                        _ip, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("cedr_b200_bfb_allreduce", C.c_int, [_H, _vp, _vp, C.c_int, C.c_int]),
@@ -485,15 +487,51 @@ class BfbTreeAllReducer(CDR):
 
 
 class CAAS(CDR):
-    """cedr::caas::CAAS (cedr_caas.hpp:15-118)."""
+    """cedr::caas::CAAS (cedr_caas.hpp:15-118).
+
+    user_reducer: the reference's UserAllReducer (cedr_caas.hpp:27-49) as a callable
+    ``f(send, recv, nlocal, nfld)`` on cuda float64 tensors -- send viewed as
+    [nfld, nlocal] (nlocal fastest), recv [nfld] to fill with the sums; n_accum is its
+    n_accum_in_place(). With a reducer this rank's cells may be any set."""
 
     def __init__(self, nlclcells, sum_mode=CAAS_SUM_TREE, cell0=0, ncells_global=None,
-                 rank=0, nranks=1):
+                 rank=0, nranks=1, user_reducer=None, n_accum=1):
         super().__init__()
         ng = nlclcells if ncells_global is None else ncells_global
+        if user_reducer is not None:
+            sum_mode = CAAS_SUM_USER
         _check(self._lib.cedr_b200_caas_create(C.byref(self._h), int(nlclcells),
                                                int(sum_mode), int(cell0), int(ng),
                                                int(rank), int(nranks)))
+        if user_reducer is not None:
+            import torch
+
+            def tramp(ctx, send, recv, nlocal, nfld, stream):
+                try:
+                    s = _wrap_device(send, nlocal*nfld).view(nfld, nlocal)
+                    r = _wrap_device(recv, nfld)
+                    user_reducer(s, r, nlocal, nfld)
+                    torch.cuda.synchronize()
+                    return 0
+                except Exception:   # surfaced as a CedrError by run()
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            self._ucb = USER_REDUCER_FN(tramp)
+            _check(self._lib.cedr_b200_caas_set_user_reducer(self._h, self._ucb, None,
+                                                             int(n_accum)))
+
+
+def _wrap_device(ptr, n):
+    """A cuda float64 tensor over n doubles at device address `ptr` (no copy)."""
+    import torch
+
+    class _Arr:
+        pass
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+                                  "version": 2}
+    return torch.as_tensor(a, device="cuda")
 
 
 def fill_headline(ncells, nt, config_id, lda=None, cell0=0, nlclcells=None):

@@ -119,6 +119,12 @@ struct cedr_b200_cdr {
   bool prefer_mass_con = false;
   int caas_sum_mode = CEDR_B200_CAAS_SUM_TREE;
   bool caas_need_conserve = false;
+  // CAAS::UserAllReducer (CEDR_B200_CAAS_SUM_USER)
+  cedr_b200_user_reducer_fn user_reducer = nullptr;
+  void* user_reducer_ctx = nullptr;
+  int user_naccum = 1;
+  double* usend = nullptr;      // (nlocal, 4 nt), then recv (4 nt): in buf2 if the caller set it
+  double* urecv = nullptr;
 
   // Tree (QLT: the caller's; CAAS: bisection over the cells, for the ordered sums).
   int ncells = 0;           // global
@@ -150,7 +156,7 @@ struct cedr_b200_cdr {
   bool user_buffers = false;
   double* in = nullptr;
   double* out = nullptr;
-  DevBuf<double> in_own, out_own;
+  DevBuf<double> in_own, out_own, usend_own;
   DevBuf<int> d_trcr_row, d_trcr_prob, d_cls_tracers[NCLS];
   DevBuf<int> d_lvlptr, d_kid0, d_kid1;
   DevBuf<unsigned short> d_dtab, d_ptab, d_fpos, d_perm;
@@ -1209,6 +1215,38 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
 
 // CAAS::run, cedr_caas.cpp:258-270; phases as for run_qlt.
 void run_caas (cedr_b200_cdr& c, int phase) {
+  if (c.caas_sum_mode == CEDR_B200_CAAS_SUM_USER) {
+    // CAAS::run with a UserAllReducer, cedr_caas.cpp:258-270.
+    cedr_b200_throw_if( ! c.user_reducer, "CEDR_B200_CAAS_SUM_USER but no reducer was set "
+                       "(cedr_b200_caas_set_user_reducer)");
+    if (phase == 1) return;
+    const int nt = static_cast<int>(c.trcr_prob.size());
+    const int nlocal = c.nlcl/c.user_naccum;
+    {
+      LaunchTimer lt(c, CEDR_B200_TAG_UP, 0);
+      caas_user_partials_kernel<<<grid_for(static_cast<long long>(nlocal)*nt), kThreads, 0,
+                                  c.stream>>>(c.in, c.ld, nlocal, c.user_naccum,
+                                              c.d_trcr_row.p, c.d_trcr_prob.p, nt, c.usend);
+      CUDA_CHECK(cudaGetLastError());
+      ++c.last_launches;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    const int e = c.user_reducer(c.user_reducer_ctx, c.usend, c.urecv, nlocal, 4*nt, c.stream);
+    cedr_b200_throw_if(e != 0, "the UserAllReducer failed with code " << e);
+    {
+      LaunchTimer lt(c, CEDR_B200_TAG_TOP, 0);
+      caas_scal_from_recv_kernel<<<(nt + 127)/128, 128, 0, c.stream>>>(c.urecv, nt,
+                                                                     c.d_caas_scal.p);
+      CUDA_CHECK(cudaGetLastError());
+      ++c.last_launches;
+    }
+    LaunchTimer lt(c, CEDR_B200_TAG_CAAS_ADJUST, 0);
+    caas_adjust_kernel<<<grid_for(static_cast<long long>(c.nlcl)*nt), kThreads, 0, c.stream>>>(
+      c.in, c.ld, c.nlcl, c.d_trcr_row.p, c.d_caas_scal.p, nt);
+    CUDA_CHECK(cudaGetLastError());
+    ++c.last_launches;
+    return;
+  }
   const bool multi = c.nranks > 1;
   if (c.caas_sum_mode == CEDR_B200_CAAS_SUM_SEQUENTIAL) {
     cedr_b200_throw_if(multi, "CEDR_B200_CAAS_SUM_SEQUENTIAL is a one-rank mode (the order of "
@@ -1337,6 +1375,9 @@ void get_buffers_sizes (cedr_b200_cdr& c, size_t& b1, size_t& b2) {
   cedr_b200_throw_if(c.declaring, "end_tracer_declarations must be called first.");
   b1 = static_cast<size_t>(c.nrows)*c.ld;
   b2 = c.is_caas ? 0 : c.trcr_prob.size()*static_cast<size_t>(c.ld);
+  // CAAS with a UserAllReducer: send (nlocal, 4 nt) then recv (4 nt), cedr_caas.cpp:75-90.
+  if (c.is_caas && c.caas_sum_mode == CEDR_B200_CAAS_SUM_USER)
+    b2 = 4*c.trcr_prob.size()*(static_cast<size_t>(c.nlcl/c.user_naccum) + 1);
 }
 
 void finish_setup (cedr_b200_cdr& c) {
@@ -1352,6 +1393,13 @@ void finish_setup (cedr_b200_cdr& c) {
     // Rows are padded to ld; keep the padding defined.
     CUDA_CHECK(cudaMemsetAsync(c.in, 0, b1*sizeof(double), c.stream));
     if (b2) CUDA_CHECK(cudaMemsetAsync(c.out, 0, b2*sizeof(double), c.stream));
+  }
+  if (c.is_caas && c.caas_sum_mode == CEDR_B200_CAAS_SUM_USER) {
+    cedr_b200_throw_if( ! c.user_reducer, "CEDR_B200_CAAS_SUM_USER but no reducer was set "
+                       "(cedr_b200_caas_set_user_reducer)");
+    if (c.user_buffers && c.out) c.usend = c.out;
+    else { c.usend_own.alloc(b2); c.usend = c.usend_own.p; }
+    c.urecv = c.usend + 4*c.trcr_prob.size()*static_cast<size_t>(c.nlcl/c.user_naccum);
   }
   if (c.is_caas) c.out = c.in;
   const int nt = static_cast<int>(c.trcr_prob.size());
@@ -1518,6 +1566,13 @@ int cedr_b200_caas_create (cedr_b200_cdr** out, int nlclcells, int sum_mode,
     cedr_b200_throw_if(! out, "null output pointer");
     require_device();
     cedr_b200_throw_if(nlclcells == 0, "CAAS does not support 0 cells on a rank.");
+    if (sum_mode == CEDR_B200_CAAS_SUM_USER) {
+      // The reducer owns the cross-rank sum: any cells, no exchange of ours.
+      cell0 = 0;
+      ncells_global = nlclcells;
+      rank = 0;
+      nranks = 1;
+    }
     cedr_b200_throw_if(nranks == 1 && (cell0 != 0 || ncells_global != nlclcells),
                        "one rank: cell0 must be 0 and ncells_global == nlclcells");
     cedr_b200_throw_if(cell0 < 0 || cell0 + nlclcells > ncells_global ||
@@ -1615,6 +1670,21 @@ int cedr_b200_bfb_allreduce (cedr_b200_cdr* c, const double* send, double* recv,
     if (phase != 0)
       CUDA_CHECK(cudaMemcpyAsync(recv, c->d_qglob.p, sizeof(double)*nf,
                                  cudaMemcpyDeviceToDevice, c->stream));
+  });
+}
+
+int cedr_b200_caas_set_user_reducer (cedr_b200_cdr* c, cedr_b200_user_reducer_fn fn, void* ctx,
+                                     int n_accum_in_place) {
+  return guarded([&] {
+    cedr_b200_throw_if( ! c->is_caas || c->caas_sum_mode != CEDR_B200_CAAS_SUM_USER,
+                       "set_user_reducer needs a CAAS created with CEDR_B200_CAAS_SUM_USER");
+    cedr_b200_throw_if( ! c->declaring, "set_user_reducer must precede end_tracer_declarations");
+    cedr_b200_throw_if( ! fn, "null reducer");
+    cedr_b200_throw_if(n_accum_in_place < 1 || c->nlcl % n_accum_in_place != 0,
+                       "n_accum_in_place must be >= 1 and divide nlclcells");
+    c->user_reducer = fn;
+    c->user_reducer_ctx = ctx;
+    c->user_naccum = n_accum_in_place;
   });
 }
 

@@ -549,6 +549,62 @@ caas_seq_sums_kernel (const double* data, const long long ld, const int ncells,
   scal[2*t+1] = fac;
 }
 
+// CAAS with the caller's UserAllReducer (CEDR_B200_CAAS_SUM_USER): reduce_locally's
+// user-reducer branch (cedr_caas.cpp:140-168). One thread per (tracer k, block bi of
+// n_accum cells): clips the block's cells in place and accumulates, each sum starting at
+// 0 and adding cell after cell as the reference's lambdas do, the four partial sums
+//   send[nlocal*k + bi] (clip), [nlocal*(nt + k) + bi] (term),
+//   send[nlocal*(2 nt + k) + bi] (min), [nlocal*(3 nt + k) + bi] (max).
+__global__ void __launch_bounds__(256)
+caas_user_partials_kernel (double* data, const long long ld, const int nlocal,
+                           const int n_accum, const int* trcr_row, const int* trcr_prob,
+                           const int nt, double* send) {
+  const long long n = static_cast<long long>(nlocal)*nt;
+  for (long long j = blockIdx.x*static_cast<long long>(blockDim.x) + threadIdx.x; j < n;
+       j += static_cast<long long>(gridDim.x)*blockDim.x) {
+    const int k = static_cast<int>(j / nlocal), bi = static_cast<int>(j % nlocal);
+    double* row = data + static_cast<long long>(trcr_row[k])*ld;
+    const bool conserve = trcr_prob[k] & 1;
+    double a_clip = 0, a_term = 0, a_min = 0, a_max = 0;
+    for (int ai = 0; ai < n_accum; ++ai) {
+      const long long i = static_cast<long long>(n_accum)*bi + ai;
+      const double lo = row[i], q = row[ld + i], hi = row[2*ld + i];
+      const double term = conserve ? row[3*ld + i] : q;
+      const double clip = dev::rmin(hi, dev::rmax(lo, q));
+      row[ld + i] = clip;
+      a_clip += clip;
+      a_term += term;
+      a_min += lo;
+      a_max += hi;
+    }
+    const long long nl = nlocal;
+    send[nl*k + bi] = a_clip;
+    send[nl*(nt + k) + bi] = a_term;
+    send[nl*(2LL*nt + k) + bi] = a_min;
+    send[nl*(3LL*nt + k) + bi] = a_max;
+  }
+}
+
+// The scalar part of finish_locally (cedr_caas.cpp:211-227) from the reducer's output
+// recv = [sum clip (nt) | sum term (nt) | sum min (nt) | sum max (nt)].
+__global__ void __launch_bounds__(128)
+caas_scal_from_recv_kernel (const double* recv, const int nt, double* scal) {
+  const int t = blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= nt) return;
+  const double clip_sum = recv[t], term_sum = recv[nt + t];
+  const double m = term_sum - clip_sum;
+  double mode = 0, fac = 0;
+  if (m < 0) {
+    fac = clip_sum - recv[2*nt + t];
+    if (fac > 0) { fac = m/fac; mode = -1; }
+  } else if (m > 0) {
+    fac = recv[3*nt + t] - clip_sum;
+    if (fac > 0) { fac = m/fac; mode = 1; }
+  }
+  scal[2*t] = mode;
+  scal[2*t + 1] = fac;
+}
+
 // Bulk DeviceOp::set_Qm (cedr_qlt_inl.hpp:21-58, cedr_caas_inl.hpp:21-34) from
 // SoA caller arrays a[t*lda + lci].
 // BfbTreeAllReducer leaf fill: send is (nfield fastest, nlocal) unless transpose, then

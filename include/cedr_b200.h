@@ -49,7 +49,12 @@ enum {
    * computes on a host backend (team size 1, cedr_kokkos.hpp:118). One rank; a
    * compatibility mode (one thread per tracer), bit-identical to the reference's
    * default CAAS. */
-  CEDR_B200_CAAS_SUM_SEQUENTIAL = 1
+  CEDR_B200_CAAS_SUM_SEQUENTIAL = 1,
+  /* By the caller's UserAllReducer (cedr_caas.hpp:27-49, cedr_caas.cpp:140-168, 262-266):
+   * CAAS hands it nlclcells / n_accum_in_place partial sums per field and uses the 4 nt
+   * sums it returns. The reducer owns the cross-rank reduction, so this rank's cells may be
+   * any set (cell0 / ncells_global are not used). See cedr_b200_caas_set_user_reducer. */
+  CEDR_B200_CAAS_SUM_USER = 2
 };
 
 typedef struct cedr_b200_cdr cedr_b200_cdr;
@@ -88,6 +93,21 @@ int cedr_b200_qlt_create_1d(cedr_b200_cdr** cdr, int ncells, int imbalanced,
 int cedr_b200_caas_create(cedr_b200_cdr** cdr, int nlclcells, int sum_mode,
                           int64_t cell0, int64_t ncells_global, int rank,
                           int nranks);
+
+/* CAAS::UserAllReducer::operator() (cedr_caas.hpp:31-39): an MPI_Allreduce-like call.
+ * send is (nlocal fastest, nfld), recv is (nfld), both DEVICE pointers as on the
+ * reference's GPU builds; the operation is always a sum (the reference passes MPI_SUM,
+ * cedr_caas.cpp:262-266). `stream` is the CDR's CUDA stream: it has been synchronised
+ * before the call, and whatever the reducer enqueues must be complete or ordered on
+ * `stream` when it returns. The implementation may modify send. Return 0 on success. */
+typedef int (*cedr_b200_user_reducer_fn)(void* ctx, double* send, double* recv, int nlocal,
+                                         int nfld, void* stream);
+/* The `r` argument of CAAS<ES>::CAAS (cedr_caas.cpp:37-48); `n_accum_in_place` is
+ * UserAllReducer::n_accum_in_place() (cedr_caas.hpp:41-48) and must divide nlclcells (the
+ * reference silently drops the remainder cells, cedr_caas.cpp:139). Only for a CAAS created
+ * with CEDR_B200_CAAS_SUM_USER; call before end_tracer_declarations. */
+int cedr_b200_caas_set_user_reducer(cedr_b200_cdr* cdr, cedr_b200_user_reducer_fn fn,
+                                    void* ctx, int n_accum_in_place);
 
 /* ~CDR */
 int cedr_b200_destroy(cedr_b200_cdr* cdr);

@@ -50,6 +50,16 @@
 # define CEDR_B200_HD inline
 #endif
 
+// UserAllReducer::operator() takes an MPI_Op (cedr_caas.hpp:39); without an MPI in the build
+// a stand-in is declared (CAAS only ever passes MPI_SUM, cedr_caas.cpp:262-266).
+#if ! defined(MPI_VERSION) && ! defined(CEDR_B200_HAVE_MPI_OP)
+# define CEDR_B200_HAVE_MPI_OP
+typedef int MPI_Op;
+# ifndef MPI_SUM
+static const MPI_Op MPI_SUM = 0;
+# endif
+#endif
+
 namespace cedr {
 typedef int Int;
 typedef long Long;
@@ -388,27 +398,47 @@ public:
   typedef std::shared_ptr<Me> Ptr;
   typedef CDR::DeviceOp DeviceOp;
 
-  // The reference's plug-in point for decomposition-invariant sums
-  // (cedr_caas.hpp:27-49). Here the tree-ordered (BfbTreeAllReducer-equivalent) sum is
-  // built in and is the default; the type is kept so caller code still compiles.
+  // The caller's own all-reduce (cedr_caas.hpp:27-49): an MPI_Allreduce-like call that CAAS
+  // makes once per run() with nlclcells / n_accum_in_place() partial sums per field
+  // (cedr_caas.cpp:140-168, 262-266). sendbuf(nlocal, nfld) and rcvbuf(nfld) are DEVICE
+  // pointers, as on the reference's GPU builds; the CDR's stream has been synchronised, and
+  // the result must be complete (or ordered on the CDR's stream) on return.
   struct UserAllReducer {
     typedef std::shared_ptr<const UserAllReducer> Ptr;
     virtual ~UserAllReducer () {}
+    virtual int operator() (const mpi::Parallel& p, Real* sendbuf, Real* rcvbuf, int nlocal,
+                            int nfld, MPI_Op op) const = 0;
     virtual int n_accum_in_place () const { return 1; }
   };
 
-  // One rank: CAAS(p, nlclcells). Several ranks: this rank's cells are
-  // [cell0, cell0 + nlclcells) of ncells_global, in the global cell order the
-  // tree-ordered sums run over.
+  // CAAS(p, nlclcells, r), cedr_caas.hpp:51-52. With a reducer `r` this rank's cells may be
+  // any set (the reducer owns the cross-rank sum). Without one the built-in tree-ordered
+  // sum runs (what the reference computes when `r` is backed by its BfbTreeAllReducer);
+  // on several ranks this rank's cells are then [cell0, cell0 + nlclcells) of
+  // ncells_global, in the global cell order the tree-ordered sums run over.
   CAAS (const mpi::Parallel::Ptr& p, const Int nlclcells,
-        const typename UserAllReducer::Ptr& /*r*/ = nullptr,
+        const typename UserAllReducer::Ptr& r = nullptr,
         Memory memory = Memory::device, const Long cell0 = 0, const Long ncells_global = -1,
-        const int sum_mode = CEDR_B200_CAAS_SUM_TREE) {
+        const int sum_mode = CEDR_B200_CAAS_SUM_TREE) : user_reducer_(r) {
     cedr_b200_cdr* h = nullptr;
-    impl::check(cedr_b200_caas_create(&h, nlclcells, sum_mode, cell0,
-                                      ncells_global < 0 ? nlclcells : ncells_global,
+    impl::check(cedr_b200_caas_create(&h, nlclcells, r ? CEDR_B200_CAAS_SUM_USER : sum_mode,
+                                      cell0, ncells_global < 0 ? nlclcells : ncells_global,
                                       p ? p->rank() : 0, p ? p->size() : 1));
     adopt(h, p, memory);
+    if (r) {
+      par_ = p ? p : mpi::make_parallel();
+      impl::check(cedr_b200_caas_set_user_reducer(h, &Me::reduce_trampoline, this,
+                                                  r->n_accum_in_place()));
+    }
+  }
+
+private:
+  typename UserAllReducer::Ptr user_reducer_;
+  mpi::Parallel::Ptr par_;
+  static int reduce_trampoline (void* ctx, double* send, double* recv, int nlocal, int nfld,
+                                void* /*stream*/) {
+    const Me* me = static_cast<const Me*>(ctx);
+    return (*me->user_reducer_)(*me->par_, send, recv, nlocal, nfld, MPI_SUM);
   }
 };
 } // namespace caas

@@ -213,6 +213,38 @@ int main () {
     }
   }
 
+  { // A caller-supplied UserAllReducer (cedr_caas.hpp:27-49), here one that delegates to
+    // the public BfbTreeAllReducer with transpose = true -- the (nlocal, nfld) layout CAAS
+    // sends (cedr_caas.cpp:153-154, cedr_bfb_tree_allreduce.cpp:95-97): must reproduce the
+    // built-in tree-ordered sums, i.e. the oracle, bit for bit.
+    struct TreeReducer : public CAAST::UserAllReducer {
+      mutable std::shared_ptr<BfbTreeAllReducer<> > r;
+      mpi::Parallel::Ptr par;
+      int ncells, calls = 0;
+      TreeReducer (const mpi::Parallel::Ptr& p, int n) : par(p), ncells(n) {}
+      int operator() (const mpi::Parallel&, Real* send, Real* recv, int nlocal, int nfld,
+                      MPI_Op op) const override {
+        if (op != MPI_SUM || nlocal != ncells) return 1;
+        if ( ! r)
+          r = std::make_shared<BfbTreeAllReducer<> >(
+            par, tree::make_tree_over_1d_mesh(par, ncells, false), ncells, nfld);
+        r->allreduce(send, recv, true);
+        ++const_cast<TreeReducer*>(this)->calls;
+        return 0;
+      }
+    };
+    for (const int n : {11, 1350}) {
+      const Problem p(n, {cst, ProblemType::shapepreserve, cst, st});
+      const std::vector<double> ref = oracle_caas(p);
+      std::vector<long long> id(n);
+      for (int i = 0; i < n; ++i) id[i] = i;
+      auto red = std::make_shared<TreeReducer>(par, n);
+      CAAST c(par, n, red);
+      REQUIRE(same_bits(run_device(c, p, id), ref));
+      REQUIRE(red->calls >= 1);
+    }
+  }
+
   { // cedr::local on the device == the oracle's restatement of the reference, bitwise.
     const int np = 4096;
     unsigned long long seed = 12345;

@@ -741,3 +741,105 @@ def test_against_the_reference_itself_when_present(oracle):
             got, _ = run_qlt_gpu(ncells, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev,
                                  imbalanced=imb, prefer=prefer)
             assert np.array_equal(got, ref)
+
+
+# ---------------------------------------------------------------- CAAS UserAllReducer
+
+def _numpy_caas(pts, lo, q, hi, prev, sums):
+    """CAAS::run (cedr_caas.cpp:129-253) in numpy given the four per-tracer global sums
+    `sums(values[nt, n]) -> [nt]` in whatever order the reducer under test uses."""
+    pts = np.asarray(pts)
+    clip = np.minimum(hi, np.maximum(lo, q))
+    term = np.where((pts & 1)[:, None] != 0, prev, q)
+    s_clip, s_term, s_min, s_max = sums(clip), sums(term), sums(lo), sums(hi)
+    out = clip.copy()
+    m = s_term - s_clip
+    for t in range(len(pts)):
+        if m[t] < 0:
+            fac = s_clip[t] - s_min[t]
+            if fac > 0:
+                fac = m[t]/fac
+                out[t] = np.maximum(lo[t], clip[t] + fac*(clip[t] - lo[t]))
+        elif m[t] > 0:
+            fac = s_max[t] - s_clip[t]
+            if fac > 0:
+                fac = m[t]/fac
+                out[t] = np.minimum(hi[t], clip[t] + fac*(hi[t] - clip[t]))
+    return out
+
+
+@pytest.mark.parametrize("ncells,n_accum", [(11, 1), (1350, 1), (1350, 3), (5400, 8)])
+def test_caas_user_reducer_sequential(oracle, ncells, n_accum):
+    """A UserAllReducer that sums its nlocal partials one after the other on the host, as
+    the reference's own TestAllReducer does (cedr_caas.cpp:276-300): with n_accum = 1 that
+    is the reference's default summation order (bitwise the oracle's sequential mode and
+    our CAAS_SUM_SEQUENTIAL); with n_accum > 1 the partials are block sums, checked
+    against a numpy CAAS that sums in the same order."""
+    import torch
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    nt = 6
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, 7)
+    pts = [7, 3, 2, 7, 6, 3]
+    calls = []
+
+    def reducer(send, recv, nlocal, nfld):
+        calls.append((nlocal, nfld))
+        h = send.cpu().numpy()
+        recv.copy_(torch.from_numpy(np.add.accumulate(h, axis=1)[:, -1].copy()).cuda())
+
+    c = cb.CAAS(ncells, user_reducer=reducer, n_accum=n_accum)
+    for p in pts:
+        c.declare_tracer(p)
+    c.end_tracer_declarations()
+    b1, b2 = c.get_buffers_sizes()
+    assert b2 == 4*nt*(ncells//n_accum + 1)       # send + recv, cedr_caas.cpp:75-90
+    c.finish_setup()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    c.set_rhom(dev(rhom))
+    c.set_Qm(dev(q), dev(lo), dev(hi), dev(prev))
+    c.run()
+    c.synchronize()
+    got = c.get_Qm().cpu().numpy()
+    assert calls == [(ncells//n_accum, 4*nt)]
+
+    def sums(v):
+        blocks = np.add.accumulate(v.reshape(nt, ncells//n_accum, n_accum), axis=2)[:, :, -1]
+        return np.add.accumulate(blocks, axis=1)[:, -1]
+    assert np.array_equal(got, _numpy_caas(pts, lo, q, hi, prev, sums))
+    if n_accum == 1:
+        assert np.array_equal(got, oracle.caas(ncells, pts, lo, q, hi, prev, tree=None))
+
+
+def test_caas_user_reducer_backed_by_bfb_tree_allreducer(oracle):
+    """the public BfbTreeAllReducer as the CAAS UserAllReducer (transpose =
+    True is CAAS's (nlocal, nfld) send layout, cedr_caas.cpp:153-154): same bits as the
+    built-in tree-ordered sums and as the oracle."""
+    import torch
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    from gpu_util import run_caas_gpu
+    ncells, nt = 5400, 9
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, 8)
+    pts = [7, 3]*4 + [7]
+    bfb = cb.BfbTreeAllReducer(ncells, 4*nt)
+
+    def reducer(send, recv, nlocal, nfld):
+        assert (nlocal, nfld) == (ncells, 4*nt)
+        bfb.allreduce(send.reshape(-1), recv, transpose=True)
+
+    c = cb.CAAS(ncells, user_reducer=reducer)
+    for p in pts:
+        c.declare_tracer(p)
+    c.end_tracer_declarations()
+    c.finish_setup()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    c.set_rhom(dev(rhom))
+    c.set_Qm(dev(q), dev(lo), dev(hi), dev(prev))
+    c.run()
+    c.synchronize()
+    got = c.get_Qm().cpu().numpy()
+    ref = oracle.caas(ncells, pts, lo, q, hi, prev, tree=oracle.bisection_tree(ncells))
+    assert np.array_equal(got, ref)
+    got2, _ = run_caas_gpu(ncells, pts, rhom, lo, q, hi, prev)
+    assert np.array_equal(got, got2)
