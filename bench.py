@@ -335,6 +335,45 @@ def main():
         for c in (qlt, caas):
             c.set_profiling(False)
 
+    # ---- the caller's whole device-resident step: scatter + run + gather
+    # through set_Qm / get_Qm against run() on bound arrays (no copies), QLT then CAAS.
+    caller_step = None
+    if nl % 2 == 0:
+        def timed(fn, reps=3):
+            fn()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1)/reps
+        outq = torch.empty_like(q)
+        qc = q.clone()
+
+        def copy_step():
+            qlt.set_Qm(q, lo, hi, prev)
+            qlt.run()
+            qlt.get_Qm(out=outq)
+            caas.set_Qm(q, lo, hi, prev)
+            caas.run()
+            caas.get_Qm(out=outq)
+        ms_copy = timed(copy_step)
+        qlt.bind_arrays(q, lo, hi, prev, out=outq)
+        caas.bind_arrays(qc, lo, hi, prev)
+
+        def bound_step():
+            qlt.run()
+            caas.run()      # in place on qc: later repetitions redistribute a solved field
+        ms_bound = timed(bound_step)
+        qlt.bind_arrays(None, None, None)
+        caas.bind_arrays(None, None, None)
+        caller_step = {"set_run_get_ms": ms_copy, "bound_run_ms": ms_bound,
+                       "run_ms": ms_step,
+                       "note": "device-resident caller arrays; bound = cedr_b200_bind_arrays "
+                               "(run() reads the caller's SoA arrays, no set_Qm/get_Qm kernels)"}
+        del outq, qc
+
     # ---- roofline of the dominant reconstructor pass (QLT run()): algorithmic bytes
     # (40 B x the updates one run() processes on this GPU) over the CUDA-event duration
     # of the run's launches; traffic = DRAM bytes of the same launches from the committed
@@ -453,7 +492,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "output_digest": output_digest, "sample_digest": sample_digest,
             "gpu_launches": launches, "clocks": clocks, "kernels_ms": kernels,
-            "small_problem": small,
+            "small_problem": small, "caller_step": caller_step,
             "exchange": (None if world == 1 else
                          "p2p (NVLink stores + epoch flags)" if p2p_used and all(p2p_used)
                          else "nccl all-gather"),

@@ -73,6 +73,7 @@ SYMBOLS = [
     ("cedr_b200_set_Qm_bulk", C.c_int, [_H, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp,
                                         _vp]),
     ("cedr_b200_get_Qm_bulk", C.c_int, [_H, C.c_int, C.c_int, C.c_int64, _vp]),
+    ("cedr_b200_bind_arrays", C.c_int, [_H, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     ("cedr_b200_set_stream", C.c_int, [_H, _vp]),
     ("cedr_b200_synchronize", C.c_int, [_H]),
     ("cedr_b200_set_allgather", C.c_int, [_H, ALLGATHER_FN, _vp]),
@@ -269,6 +270,22 @@ class CDR:
                                  x.shape == qm.shape and _row_stride(x) == lda)
         _check(self._lib.cedr_b200_set_Qm_bulk(self._h, int(t0), int(nt), int(lda), _ptr(qm),
                                                _ptr(qm_min), _ptr(qm_max), _ptr(qm_prev)))
+
+    def bind_arrays(self, qm, qm_min, qm_max, qm_prev=None, out=None):
+        """Zero-copy set_Qm/get_Qm: run() reads these SoA cuda float64 [nt, lda] arrays in
+        place and writes QLT's results to `out` (CAAS updates qm in place). bind_arrays(None,
+        None, None) unbinds. The tensors must outlive the binding."""
+        if qm is None:
+            self._bound = None
+            _check(self._lib.cedr_b200_bind_arrays(self._h, 0, None, None, None, None, None))
+            return
+        lda = _row_stride(qm)
+        for x in (qm, qm_min, qm_max, qm_prev, out):
+            assert x is None or (x.is_cuda and x.element_size() == 8 and
+                                 x.shape == qm.shape and _row_stride(x) == lda)
+        self._bound = (qm, qm_min, qm_max, qm_prev, out)
+        _check(self._lib.cedr_b200_bind_arrays(self._h, int(lda), _ptr(qm_min), _ptr(qm),
+                                               _ptr(qm_max), _ptr(qm_prev), _ptr(out)))
 
     def run(self):
         _check(self._lib.cedr_b200_run(self._h))

@@ -119,6 +119,17 @@ struct cedr_b200_cdr {
   bool prefer_mass_con = false;
   int caas_sum_mode = CEDR_B200_CAAS_SUM_TREE;
   bool caas_need_conserve = false;
+  // Caller arrays bound in place of the `in` / `out` rows (cedr_b200_bind_arrays).
+  struct Bound {
+    bool on = false;
+    long long lda = 0;
+    const double* qm_min = nullptr;
+    double* qm = nullptr;
+    const double* qm_max = nullptr;
+    const double* qm_prev = nullptr;
+    double* qm_out = nullptr;
+  } bound;
+  DevBuf<int> d_ident;          // 0, 1, 2, ...: tracer -> row of a bound array
   // CAAS::UserAllReducer (CEDR_B200_CAAS_SUM_USER)
   cedr_b200_user_reducer_fn user_reducer = nullptr;
   void* user_reducer_ctx = nullptr;
@@ -329,6 +340,33 @@ int nblocks_dev (const cedr_b200_cdr& c, int tier) {
     static_cast<int>(c.plan.tiers[tier].blocks.size());
 }
 
+// Where the leaf rows of class `cls` are: the CDR's own buffer (row offsets of the class,
+// cedr_qlt_inl.hpp:21-58, cedr_caas_inl.hpp:21-34) or the caller's bound arrays.
+RowMap row_map (const cedr_b200_cdr& c, int cls) {
+  RowMap rm;
+  std::memset(&rm, 0, sizeof(rm));
+  if (c.bound.on) {
+    rm.p[0] = c.bound.qm_min;
+    rm.p[1] = c.bound.qm;
+    rm.p[2] = c.bound.qm_max;
+    rm.p[3] = c.bound.qm_prev;
+    rm.ld = c.bound.lda;
+    rm.trow = c.d_ident.p;
+    return rm;
+  }
+  rm.ld = c.ld;
+  rm.trow = c.d_trcr_row.p;
+  if (cls == CLS_NN || cls == CLS_CNN || cls == CLS_BFB) {
+    rm.p[1] = c.in;
+    if (cls == CLS_CNN) rm.p[3] = c.in + c.ld;
+  } else {
+    for (int f = 0; f < 3; ++f) rm.p[f] = c.in + f*c.ld;
+    const bool prev = cls == CLS_CAAS ? c.caas_need_conserve : (cls == CLS_CST || cls == CLS_CT);
+    if (prev) rm.p[3] = c.in + 3*c.ld;
+  }
+  return rm;
+}
+
 SweepArgs base_args (cedr_b200_cdr& c, int cls, int tier) {
   SweepArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -342,8 +380,9 @@ SweepArgs base_args (cedr_b200_cdr& c, int cls, int tier) {
   if (tier == 0) {
     a.in = c.in;
     a.in_ld = c.ld;
-    a.out = c.out;
-    a.out_ld = c.ld;
+    a.rows = row_map(c, cls);
+    a.out = c.bound.on && ! c.is_caas ? c.bound.qm_out : c.out;
+    a.out_ld = c.bound.on && ! c.is_caas ? c.bound.lda : c.ld;
   } else {
     a.in = c.d_rec[tier].p;
     a.in_ld = c.tier_ld[tier];
@@ -387,14 +426,15 @@ fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
   a.rh = c.d_frh.p;
   a.in = c.in;
   a.in_ld = c.ld;
+  a.rows = row_map(c, cls);
   a.trcr_row = c.d_trcr_row.p;
   a.trcr_prob = c.d_trcr_prob.p;
   a.rec_out = c.d_rec[1].p;
   a.rec_ld = c.tier_ld[1];
   a.sol_in = c.d_sol[1].p;
   a.sol_in_ld = c.tier_ld[1];
-  a.out = c.out;
-  a.out_ld = c.ld;
+  a.out = c.bound.on && ! c.is_caas ? c.bound.qm_out : c.out;
+  a.out_ld = c.bound.on && ! c.is_caas ? c.bound.lda : c.ld;
   a.tracers = c.d_cls_tracers[cls].p;
   a.ntr = static_cast<int>(c.cls_tracers[cls].size());
   a.sbuf = (c.plan.tiers[0].max_nl + 2 + 1) & ~1;
@@ -1164,7 +1204,7 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
   // Classes on the fast kernels hand their blocks' sub-roots to the expanded tier.
   auto via_x = [&] (int cls) {
     return c.split && c.x_tier && c.fast_ok && fast_class(cls, MODE_DOWN) &&
-      ! (c.ring_ok && ring_class(cls));
+      ! (c.ring_ok && ring_class(cls) && ! c.bound.on);
   };
   if (solo_ok(c)) {
     for (int cls = 0; cls < CLS_CAAS; ++cls)
@@ -1196,7 +1236,7 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
     }
     for (int cls = 0; cls < CLS_CAAS; ++cls) {
       if (c.cls_tracers[cls].empty()) continue;
-      if (c.ring_ok && ring_class(cls)) { launch_ring(c, cls); continue; }
+      if (c.ring_ok && ring_class(cls) && ! c.bound.on) { launch_ring(c, cls); continue; }
       if (via_x(cls)) {
         if ( ! multi) launch_up(c, cls, 0);
         launch_top_x(c, cls);
@@ -1225,8 +1265,8 @@ void run_caas (cedr_b200_cdr& c, int phase) {
     {
       LaunchTimer lt(c, CEDR_B200_TAG_UP, 0);
       caas_user_partials_kernel<<<grid_for(static_cast<long long>(nlocal)*nt), kThreads, 0,
-                                  c.stream>>>(c.in, c.ld, nlocal, c.user_naccum,
-                                              c.d_trcr_row.p, c.d_trcr_prob.p, nt, c.usend);
+                                  c.stream>>>(row_map(c, CLS_CAAS), nlocal, c.user_naccum,
+                                              c.d_trcr_prob.p, nt, c.usend);
       CUDA_CHECK(cudaGetLastError());
       ++c.last_launches;
     }
@@ -1242,7 +1282,7 @@ void run_caas (cedr_b200_cdr& c, int phase) {
     }
     LaunchTimer lt(c, CEDR_B200_TAG_CAAS_ADJUST, 0);
     caas_adjust_kernel<<<grid_for(static_cast<long long>(c.nlcl)*nt), kThreads, 0, c.stream>>>(
-      c.in, c.ld, c.nlcl, c.d_trcr_row.p, c.d_caas_scal.p, nt);
+      row_map(c, CLS_CAAS), c.nlcl, c.d_caas_scal.p, nt);
     CUDA_CHECK(cudaGetLastError());
     ++c.last_launches;
     return;
@@ -1256,20 +1296,19 @@ void run_caas (cedr_b200_cdr& c, int phase) {
     {
       LaunchTimer lt(c, CEDR_B200_TAG_UP, 0);
       caas_seq_sums_kernel<<<(nt + 127)/128, 128, 0, c.stream>>>(
-        c.in, c.ld, c.nlcl, c.d_trcr_row.p, c.d_trcr_prob.p, nt, c.d_caas_scal.p);
+        row_map(c, CLS_CAAS), c.nlcl, c.d_trcr_prob.p, nt, c.d_caas_scal.p);
       CUDA_CHECK(cudaGetLastError());
       ++c.last_launches;
     }
     const long long n = static_cast<long long>(c.nlcl)*nt;
     LaunchTimer lt(c, CEDR_B200_TAG_CAAS_ADJUST, 0);
-    caas_adjust_kernel<<<grid_for(n), kThreads, 0, c.stream>>>(c.in, c.ld, c.nlcl,
-                                                             c.d_trcr_row.p,
+    caas_adjust_kernel<<<grid_for(n), kThreads, 0, c.stream>>>(row_map(c, CLS_CAAS), c.nlcl,
                                                              c.d_caas_scal.p, nt);
     CUDA_CHECK(cudaGetLastError());
     ++c.last_launches;
     return;
   }
-  if (c.ring_ok) { launch_ring(c, CLS_CAAS); return; }
+  if (c.ring_ok && ! c.bound.on) { launch_ring(c, CLS_CAAS); return; }
   if (solo_ok(c)) { launch_solo(c, CLS_CAAS); return; }
   const int ntiers = static_cast<int>(c.plan.tiers.size());
   const int top = ntiers - 1;
@@ -1286,7 +1325,7 @@ void run_caas (cedr_b200_cdr& c, int phase) {
   const long long n = static_cast<long long>(c.nlcl)*nt;
   const int grid = static_cast<int>(std::min<long long>((n + kThreads - 1)/kThreads, 148*32));
   LaunchTimer lt(c, CEDR_B200_TAG_CAAS_ADJUST, 0);
-  caas_adjust_kernel<<<grid, kThreads, 0, c.stream>>>(c.in, c.ld, c.nlcl, c.d_trcr_row.p,
+  caas_adjust_kernel<<<grid, kThreads, 0, c.stream>>>(row_map(c, CLS_CAAS), c.nlcl,
                                                       c.d_caas_scal.p, nt);
   CUDA_CHECK(cudaGetLastError());
   ++c.last_launches;
@@ -1889,6 +1928,8 @@ int cedr_b200_set_Qm_bulk (cedr_b200_cdr* c, int t0, int nt, int64_t lda,
     cedr_b200_throw_if(t0 < 0 || nt < 0 ||
                        t0 + nt > static_cast<int>(c->trcr_prob.size()),
                        "tracer range out of bounds");
+    cedr_b200_throw_if(c->bound.on, "arrays are bound (cedr_b200_bind_arrays): write them "
+                       "directly instead of set_Qm");
     if (nt == 0) return;
     bool need_prev = c->is_caas && c->caas_need_conserve;
     for (int t = t0; t < t0 + nt; ++t) need_prev |= (c->trcr_prob[t] & 1) != 0;
@@ -1910,6 +1951,8 @@ int cedr_b200_get_Qm_bulk (cedr_b200_cdr* c, int t0, int nt, int64_t lda, double
     cedr_b200_throw_if(t0 < 0 || nt < 0 ||
                        t0 + nt > static_cast<int>(c->trcr_prob.size()),
                        "tracer range out of bounds");
+    cedr_b200_throw_if(c->bound.on, "arrays are bound (cedr_b200_bind_arrays): the results "
+                       "are in the bound output array");
     if (nt == 0) return;
     const long long n = static_cast<long long>(c->nlcl)*nt;
     const int grid = static_cast<int>(std::min<long long>((n + kThreads - 1)/kThreads,
@@ -1918,6 +1961,52 @@ int cedr_b200_get_Qm_bulk (cedr_b200_cdr* c, int t0, int nt, int64_t lda, double
       c->is_caas ? c->in : c->out, c->ld, c->nlcl, c->d_trcr_row.p, c->is_caas, t0,
       nt, lda, qm);
     CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+int cedr_b200_bind_arrays (cedr_b200_cdr* c, int64_t lda, const double* qm_min, double* qm,
+                            const double* qm_max, const double* qm_prev, double* qm_out) {
+  return guarded([&] {
+    cedr_b200_throw_if( ! c->finished, "finish_setup must be called first.");
+    if ( ! qm) {          // unbind
+      c->bound = cedr_b200_cdr::Bound();
+      return;
+    }
+    cedr_b200_throw_if(c->is_bfb, "bind_arrays is for QLT and CAAS");
+    cedr_b200_throw_if( ! qm_min || ! qm_max, "Qm_min and Qm_max are required");
+    cedr_b200_throw_if(lda < c->nlcl, "lda must be >= nlclcells");
+    bool need_prev = c->is_caas && c->caas_need_conserve;
+    for (size_t t = 0; t < c->trcr_prob.size(); ++t) {
+      const int cls = c->trcr_cls[t];
+      // Consistent-only tracers store q bounds (Qm bounds / rhom, cedr_qlt_inl.hpp:36-45)
+      // and nonnegative ones have no bound rows: those need set_Qm's transformation.
+      cedr_b200_throw_if( ! (cls == CLS_ST || cls == CLS_CST || cls == CLS_CAAS),
+                         "bind_arrays needs shape-preserving tracers (tracer " << t << ")");
+      need_prev |= (c->trcr_prob[t] & 1) != 0;
+    }
+    cedr_b200_throw_if(need_prev && ! qm_prev, "Qm_prev was not provided to set_Q.");
+    cedr_b200_throw_if( ! c->is_caas && ! qm_out, "QLT needs an output array");
+    cedr_b200_throw_if( ! c->is_caas && (qm_out == qm || qm_out == qm_min || qm_out == qm_max),
+                       "QLT's output must not alias its inputs (the down-sweep re-reads them)");
+    if (c->fast_ok) {
+      // The fast kernels move rows with 16-byte TMA bulk copies.
+      auto al = [] (const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+      cedr_b200_throw_if(lda % 2 != 0 || ! al(qm_min) || ! al(qm) || ! al(qm_max) ||
+                         (qm_prev && ! al(qm_prev)) || (qm_out && ! al(qm_out)),
+                         "bound arrays must be 16-byte aligned with an even lda");
+    }
+    if (c->d_ident.n < c->trcr_prob.size()) {
+      std::vector<int> id(c->trcr_prob.size());
+      for (size_t i = 0; i < id.size(); ++i) id[i] = static_cast<int>(i);
+      c->d_ident.upload(id);
+    }
+    c->bound.on = true;
+    c->bound.lda = lda;
+    c->bound.qm_min = qm_min;
+    c->bound.qm = qm;
+    c->bound.qm_max = qm_max;
+    c->bound.qm_prev = qm_prev;
+    c->bound.qm_out = qm_out;
   });
 }
 

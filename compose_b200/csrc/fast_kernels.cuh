@@ -100,8 +100,9 @@ struct FastArgs {
   const unsigned* pent;
   const NodeWQ* wq;             // per block: kHeapNodes + npairs entries, fast order
   const NodeRh* rh;
-  const double* in;             // tier-0 rows
+  const double* in;             // tier-0 rows (the CDR's own buffer)
   long long in_ld;
+  RowMap rows;                  // where the tracers' leaf rows are (own buffer or bound arrays)
   const int* trcr_row;
   const int* trcr_prob;
   double* rec_out;              // UP: [(4 t + f) rec_ld + block]
@@ -201,12 +202,16 @@ up_kernel (const FastArgs a) {
   const int nstage = (R::caas && a.caas_rows == 3) ? 3 : nrows;
   auto issue = [&] (const int i) {
     const int t = a.tracers[g0 + i];
-    const double* src = a.in + static_cast<long long>(a.trcr_row[t])*a.in_ld + src0;
     double* dst = stage + (i & 1)*nrows*a.sbuf;
     mbar_expect_tx(&mbar[i & 1], nstage*bytes);
 #pragma unroll
     for (int f = 0; f < nrows; ++f)
-      if (f < nstage) tma_load(dst + f*a.sbuf, src + f*a.in_ld, bytes, &mbar[i & 1]);
+      if (f < nstage) {
+        // Staged row f holds role (min, Qm, max, prev)[f]; the nonnegative classes stage
+        // Qm[, prev] only.
+        const int role = bounds ? f : (f == 0 ? 1 : 3);
+        tma_load(dst + f*a.sbuf, a.rows.row(role, t) + src0, bytes, &mbar[i & 1]);
+      }
   };
   if (tid == 0) {
     issue(0);
@@ -647,12 +652,12 @@ down2_kernel (const FastArgs a) {
 
   auto issue = [&] (const int i) {
     const int t = a.tracers[g0 + i];
-    const double* src = a.in + static_cast<long long>(a.trcr_row[t])*a.in_ld + src0;
     double* dst = stage + (i & 1)*3*sbuf;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&mbar[i & 1], 3*bytes);
 #pragma unroll
-    for (int f = 0; f < 3; ++f) tma_load(dst + f*sbuf, src + f*a.in_ld, bytes, &mbar[i & 1]);
+    for (int f = 0; f < 3; ++f)
+      tma_load(dst + f*sbuf, a.rows.row(f, t) + src0, bytes, &mbar[i & 1]);
   };
   if (tid == 0) {
     issue(0);

@@ -45,6 +45,20 @@ enum { CLS_ST = 0, CLS_CST = 1, CLS_T = 2, CLS_CT = 3, CLS_NN = 4, CLS_CNN = 5,
        CLS_BFB = 7, NCLS = 8 };
 enum { MODE_UP = 0, MODE_TOP = 1, MODE_DOWN = 2 };
 
+// Where a tracer's leaf rows live: row `role` (0 min, 1 Qm, 2 max, 3 prev) of tracer t is
+// p[role] + trow[t]*ld. For the CDR's own buffer p[role] = in + (row offset of the role in
+// the tracer's class)*ld and trow = trcr_row; for arrays bound by the caller
+// (cedr_b200_bind_arrays) p[role] is the caller's array, trow[t] = t and ld its leading
+// dimension. p[role] is null for roles the class does not have.
+struct RowMap {
+  const double* p[4];
+  long long ld;
+  const int* trow;
+  __host__ __device__ const double* row (const int role, const int t) const {
+    return p[role] + static_cast<long long>(trow[t])*ld;
+  }
+};
+
 struct SweepArgs {
   const BlockDev* blocks;
   int nblocks;
@@ -59,6 +73,7 @@ struct SweepArgs {
   const double* in;
   long long in_ld;
   int tier0;
+  RowMap rows;          // tier 0
   const int* trcr_row;
   const int* trcr_prob;
   // UP: block-root records for the next tier, [(4*t + f)*rec_ld + block].
@@ -105,12 +120,10 @@ sweep_block (const SweepArgs& a, const int b, const int t, double* const sm,
   { // Leaves.
     const double* p0, * p1, * p2, * p3;
     if (a.tier0) {
-      const double* base = a.in + (long long) a.trcr_row[t]*a.in_ld + B.leaf0;
-      if (nonneg) {
-        p1 = base; p3 = base + a.in_ld; p0 = p2 = nullptr;
-      } else {
-        p0 = base; p1 = base + a.in_ld; p2 = base + 2*a.in_ld; p3 = base + 3*a.in_ld;
-      }
+      p1 = a.rows.row(1, t) + B.leaf0;
+      p3 = (need_prev || (caas && a.rows.p[3])) ? a.rows.row(3, t) + B.leaf0 : nullptr;
+      p0 = p2 = nullptr;
+      if ( ! nonneg) { p0 = a.rows.row(0, t) + B.leaf0; p2 = a.rows.row(2, t) + B.leaf0; }
     } else {
       const double* base = a.in + (long long) t*4*a.in_ld + B.leaf0;
       p0 = base; p1 = base + a.in_ld; p2 = base + 2*a.in_ld; p3 = base + 3*a.in_ld;
@@ -286,13 +299,15 @@ solo_kernel (const SweepArgs a) {
     __syncthreads();
     // CAAS::finish_locally (cedr_caas.cpp:211-253) on this tracer's cells.
     const double mode = a.caas_scal[2*t], fac = a.caas_scal[2*t+1];
-    double* const row = const_cast<double*>(a.in) + (long long) a.trcr_row[t]*a.in_ld + B.leaf0;
+    const double* const rlo = a.rows.row(0, t) + B.leaf0;
+    const double* const rhi = a.rows.row(2, t) + B.leaf0;
+    double* const rq = const_cast<double*>(a.rows.row(1, t)) + B.leaf0;
     for (int i = tid; i < B.nl; i += nth) {
-      const double lo = row[i], hi = row[2*a.in_ld + i];
-      double q = dev::rmin(hi, dev::rmax(lo, row[a.in_ld + i]));
+      const double lo = rlo[i], hi = rhi[i];
+      double q = dev::rmin(hi, dev::rmax(lo, rq[i]));
       if (mode < 0) { q += fac*(q - lo); q = dev::rmax(lo, q); }
       else if (mode > 0) { q += fac*(hi - q); q = dev::rmin(hi, q); }
-      row[a.in_ld + i] = q;
+      rq[i] = q;
     }
     return;
   }
@@ -493,15 +508,14 @@ unpack_kernel (const double* recv, const int nranks, const int nown_max, const i
 // clipped value the reference stores in place during reduce_locally
 // (cedr_caas.cpp:177).
 __global__ void __launch_bounds__(256)
-caas_adjust_kernel (double* data, const long long ld, const int ncells,
-                    const int* trcr_row, const double* scal, const int nt) {
+caas_adjust_kernel (const RowMap rows, const int ncells, const double* scal, const int nt) {
   const long long n = (long long) ncells*nt;
   for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
        k += (long long) gridDim.x*blockDim.x) {
     const int t = (int) (k / ncells), i = (int) (k % ncells);
-    double* row = data + (long long) trcr_row[t]*ld + i;
-    const double lo = row[0], hi = row[2*ld];
-    double q = dev::rmin(hi, dev::rmax(lo, row[ld]));
+    double* const rq = const_cast<double*>(rows.row(1, t)) + i;
+    const double lo = rows.row(0, t)[i], hi = rows.row(2, t)[i];
+    double q = dev::rmin(hi, dev::rmax(lo, rq[0]));
     const double mode = scal[2*t], fac = scal[2*t+1];
     if (mode < 0) {
       q += fac*(q - lo);
@@ -510,7 +524,7 @@ caas_adjust_kernel (double* data, const long long ld, const int ncells,
       q += fac*(hi - q);
       q = dev::rmin(hi, q);
     }
-    row[ld] = q;
+    rq[0] = q;
   }
 }
 
@@ -521,16 +535,19 @@ caas_adjust_kernel (double* data, const long long ld, const int ncells,
 // (a compatibility mode for one rank: bit parity with the reference's default CAAS, not
 // speed), then forms the redistribution scalars of finish_locally (cedr_caas.cpp:211-253).
 __global__ void __launch_bounds__(128)
-caas_seq_sums_kernel (const double* data, const long long ld, const int ncells,
-                      const int* trcr_row, const int* trcr_prob, const int nt, double* scal) {
+caas_seq_sums_kernel (const RowMap rows, const int ncells, const int* trcr_prob, const int nt,
+                      double* scal) {
   const int t = blockIdx.x*blockDim.x + threadIdx.x;
   if (t >= nt) return;
-  const double* row = data + (long long) trcr_row[t]*ld;
+  const double* const rlo = rows.row(0, t);
+  const double* const rq = rows.row(1, t);
+  const double* const rhi = rows.row(2, t);
   const bool conserve = trcr_prob[t] & 1;
+  const double* const rp = conserve ? rows.row(3, t) : rq;
   double clip_sum = 0, term_sum = 0, min_sum = 0, max_sum = 0;
   for (int i = 0; i < ncells; ++i) {
-    const double lo = row[i], q = row[ld + i], hi = row[2*ld + i];
-    const double term = conserve ? row[3*ld + i] : q;
+    const double lo = rlo[i], q = rq[i], hi = rhi[i];
+    const double term = rp[i];
     clip_sum += dev::rmin(hi, dev::rmax(lo, q));
     term_sum += term;
     min_sum += lo;
@@ -556,22 +573,24 @@ caas_seq_sums_kernel (const double* data, const long long ld, const int ncells,
 //   send[nlocal*k + bi] (clip), [nlocal*(nt + k) + bi] (term),
 //   send[nlocal*(2 nt + k) + bi] (min), [nlocal*(3 nt + k) + bi] (max).
 __global__ void __launch_bounds__(256)
-caas_user_partials_kernel (double* data, const long long ld, const int nlocal,
-                           const int n_accum, const int* trcr_row, const int* trcr_prob,
-                           const int nt, double* send) {
+caas_user_partials_kernel (const RowMap rows, const int nlocal, const int n_accum,
+                           const int* trcr_prob, const int nt, double* send) {
   const long long n = static_cast<long long>(nlocal)*nt;
   for (long long j = blockIdx.x*static_cast<long long>(blockDim.x) + threadIdx.x; j < n;
        j += static_cast<long long>(gridDim.x)*blockDim.x) {
     const int k = static_cast<int>(j / nlocal), bi = static_cast<int>(j % nlocal);
-    double* row = data + static_cast<long long>(trcr_row[k])*ld;
+    const double* const rlo = rows.row(0, k);
+    double* const rq = const_cast<double*>(rows.row(1, k));
+    const double* const rhi = rows.row(2, k);
     const bool conserve = trcr_prob[k] & 1;
+    const double* const rp = conserve ? rows.row(3, k) : rq;
     double a_clip = 0, a_term = 0, a_min = 0, a_max = 0;
     for (int ai = 0; ai < n_accum; ++ai) {
       const long long i = static_cast<long long>(n_accum)*bi + ai;
-      const double lo = row[i], q = row[ld + i], hi = row[2*ld + i];
-      const double term = conserve ? row[3*ld + i] : q;
+      const double lo = rlo[i], q = rq[i], hi = rhi[i];
+      const double term = rp[i];
       const double clip = dev::rmin(hi, dev::rmax(lo, q));
-      row[ld + i] = clip;
+      rq[i] = clip;
       a_clip += clip;
       a_term += term;
       a_min += lo;

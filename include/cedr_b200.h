@@ -176,6 +176,18 @@ int cedr_b200_get_Qm_bulk(cedr_b200_cdr* cdr, int t0, int nt, int64_t lda,
 
 /* ---- streams, multi-GPU exchange --------------------------------------- */
 
+/* Zero-copy DeviceOp::set_Qm / get_Qm (cedr_qlt_inl.hpp:21-66, cedr_caas_inl.hpp:21-42;
+ * the caller kernels of cedr_test_randomized_inl.hpp:32-58): instead of scattering its SoA
+ * arrays into the CDR's buffer and gathering the results back, the caller binds them and
+ * run() reads them in place -- a[t*lda + lci], tracer-major, local cell index fastest --
+ * and writes QLT's results to qm_out (CAAS works in place on qm, as the reference does on
+ * its buffer). All tracers must be shape-preserving (consistent-only tracers store scaled
+ * bounds, nonnegative ones have none: use set_Qm for those). Arrays must stay valid and,
+ * where the fast kernels apply, be 16-byte aligned with an even lda. qm == NULL unbinds.
+ * rhom is still set through set_rhom. */
+int cedr_b200_bind_arrays(cedr_b200_cdr* cdr, int64_t lda, const double* qm_min, double* qm,
+                          const double* qm_max, const double* qm_prev, double* qm_out);
+
 /* All work of this CDR is enqueued on `cuda_stream` (a cudaStream_t). */
 int cedr_b200_set_stream(cedr_b200_cdr* cdr, void* cuda_stream);
 int cedr_b200_synchronize(cedr_b200_cdr* cdr);

@@ -843,3 +843,83 @@ def test_caas_user_reducer_backed_by_bfb_tree_allreducer(oracle):
     assert np.array_equal(got, ref)
     got2, _ = run_caas_gpu(ncells, pts, rhom, lo, q, hi, prev)
     assert np.array_equal(got, got2)
+
+
+# ---------------------------------------------------------------- zero-copy binding (8f-1)
+
+@pytest.mark.parametrize("ncells", [111, 1000, 5400])
+def test_bound_arrays_equal_set_get(oracle, ncells):
+    """cedr_b200_bind_arrays: run() reads the caller's SoA arrays in place of set_Qm's copy
+    and writes QLT's results to the caller's output array (CAAS in place on Qm): same bits
+    as the set_Qm / run / get_Qm route and as the oracle, on the generic, the fast and
+    the single-launch paths."""
+    import torch
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    nt = 10
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, 9)
+    pts = [7, 6]*5
+    tree = oracle.bisection_tree(ncells)
+    lda = (ncells + 15)//16*16
+    def dev(a):
+        t = torch.zeros((nt, lda), dtype=torch.float64, device="cuda")
+        t[:, :ncells] = torch.from_numpy(np.ascontiguousarray(a))
+        return t
+    for kind in ("qlt", "caas"):
+        ref = (oracle.qlt(tree, pts, rhom, lo, q, hi, prev) if kind == "qlt"
+               else oracle.caas(ncells, [7, 3]*5, lo, q, hi, prev, tree=tree))
+        c = cb.QLT(ncells) if kind == "qlt" else cb.CAAS(ncells)
+        for p in (pts if kind == "qlt" else [7, 3]*5):
+            c.declare_tracer(p)
+        c.end_tracer_declarations()
+        c.finish_setup()
+        g = c.get_owned_glblcells() if kind == "qlt" else np.arange(ncells)
+        c.set_rhom(torch.from_numpy(np.ascontiguousarray(rhom[g])).cuda())
+        d = [dev(a[:, g]) for a in (q, lo, hi, prev)]
+        out = torch.zeros((nt, lda), dtype=torch.float64, device="cuda")
+        if kind == "qlt":
+            c.bind_arrays(d[0], d[1], d[2], d[3], out=out)
+        else:
+            c.bind_arrays(d[0], d[1], d[2], d[3])
+        with pytest.raises(cb.CedrError, match="arrays are bound"):
+            c.set_Qm(d[0], d[1], d[2], d[3])
+        c.run()
+        c.synchronize()
+        res = (out if kind == "qlt" else d[0])[:, :ncells].cpu().numpy()
+        got = np.empty_like(res)
+        got[:, g] = res
+        assert np.array_equal(got, ref), kind
+        # inputs other than CAAS's Qm are untouched
+        assert torch.equal(d[1][:, :ncells].cpu(), torch.from_numpy(np.ascontiguousarray(lo[:, g])))
+        # unbind: back to the CDR's own buffer
+        c.bind_arrays(None, None, None)
+        d2 = [dev(a[:, g]) for a in (q, lo, hi, prev)]
+        c.set_Qm(*d2)
+        c.run()
+        res = c.get_Qm().cpu().numpy()
+        got[:, g] = res
+        assert np.array_equal(got, ref), kind
+
+
+def test_bind_arrays_rejects_what_it_cannot_read_in_place():
+    import torch
+    import compose_b200 as cb
+    n = 64
+    z = lambda: torch.zeros((2, n), dtype=torch.float64, device="cuda")
+    q = cb.QLT(n)
+    q.declare_tracer(cb.CONSERVE | cb.CONSISTENT)     # consistent-only: scaled bounds
+    q.declare_tracer(7)
+    q.end_tracer_declarations()
+    q.finish_setup()
+    with pytest.raises(cb.CedrError, match="shape-preserving"):
+        q.bind_arrays(z(), z(), z(), z(), out=z())
+    q = cb.QLT(n)
+    q.declare_tracer(7)
+    q.declare_tracer(7)
+    q.end_tracer_declarations()
+    q.finish_setup()
+    a = z()
+    with pytest.raises(cb.CedrError, match="alias"):
+        q.bind_arrays(a, z(), z(), z(), out=a)
+    with pytest.raises(cb.CedrError, match="Qm_prev"):
+        q.bind_arrays(z(), z(), z(), None, out=z())
