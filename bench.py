@@ -468,6 +468,15 @@ def main():
             torch.cuda.synchronize()
             small[kind + "_us_per_run"] = 1e3*e0.elapsed_time(e1)/200
             small[kind + "_launches_per_run"] = c.last_run_launches()
+            # The whole transport step on the device (interpolation + set_Qm, run, get_Qm:
+            # cedr_b200_transport1d_cycle), 351 steps, launched one by one and replayed
+            # from a CUDA graph.
+            import numpy as np
+            y0 = np.linspace(0.1, 0.9, 112)
+            y0[-1] = y0[0]
+            for g in (False, True):
+                _, us = c.transport1d_cycle(351, y0, use_graph=g)
+                small["%s_t1d_step_us_%s" % (kind, "graph" if g else "launches")] = us
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None

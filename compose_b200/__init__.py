@@ -74,6 +74,10 @@ SYMBOLS = [
                                         _vp]),
     ("cedr_b200_get_Qm_bulk", C.c_int, [_H, C.c_int, C.c_int, C.c_int64, _vp]),
     ("cedr_b200_bind_arrays", C.c_int, [_H, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
+    ("cedr_b200_local_solve", C.c_int, [C.c_int, C.c_int, C.c_int] + [_vp]*8 +
+     [C.c_int64, C.c_int64, C.c_int, C.c_int, _vp]),
+    ("cedr_b200_transport1d_cycle", C.c_int, [_H, C.c_int, _dp, _dp, C.c_int,
+                                              C.POINTER(C.c_float)]),
     ("cedr_b200_set_stream", C.c_int, [_H, _vp]),
     ("cedr_b200_synchronize", C.c_int, [_H]),
     ("cedr_b200_set_allgather", C.c_int, [_H, ALLGATHER_FN, _vp]),
@@ -286,6 +290,18 @@ class CDR:
         self._bound = (qm, qm_min, qm_max, qm_prev, out)
         _check(self._lib.cedr_b200_bind_arrays(self._h, int(lda), _ptr(qm_min), _ptr(qm),
                                                _ptr(qm_max), _ptr(qm_prev), _ptr(out)))
+
+    def transport1d_cycle(self, nsteps, y0, use_graph=True):
+        """Problem1D::cycle (cedr_test_1d_transport.cpp:231-254) on the device for tracer 0.
+        y0: numpy [ncells + 1]. Returns (yf, device microseconds per step)."""
+        import numpy as np
+        y0 = np.ascontiguousarray(y0, dtype=np.float64)
+        yf = np.empty_like(y0)
+        ms = C.c_float(0)
+        _check(self._lib.cedr_b200_transport1d_cycle(
+            self._h, int(nsteps), y0.ctypes.data_as(_dp), yf.ctypes.data_as(_dp),
+            int(bool(use_graph)), C.byref(ms)))
+        return yf, 1e3*ms.value
 
     def run(self):
         _check(self._lib.cedr_b200_run(self._h))
@@ -566,6 +582,25 @@ def fill_headline(ncells, nt, config_id, lda=None, cell0=0, nlclcells=None):
                                              _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
                                              _ptr(arrs[3]), _stream_ptr()))
     return (rhom,) + tuple(arrs)
+
+
+LOCAL_QP, LOCAL_CAAS, LOCAL_NONNEG_LS, LOCAL_NONNEG_CAAS, LOCAL_QP_2D = range(5)
+
+
+def local_solve(method, b, y, xlo=None, xhi=None, w=None, a=None, max_its=0, clip=True):
+    """cedr::local solvers (cedr_local.hpp:23-58) for a batch of elements: SoA cuda float64
+    arrays [n, nprob] (element index fastest), b [nprob]. Returns (x [n, nprob], info)."""
+    import torch
+    n, nprob = y.shape
+    for t in (y, xlo, xhi, w, a):
+        assert t is None or (t.is_cuda and t.is_contiguous() and t.shape == y.shape)
+    x = torch.zeros_like(y)
+    info = torch.zeros(nprob, dtype=torch.int32, device="cuda")
+    _check(load_library().cedr_b200_local_solve(
+        int(method), int(nprob), int(n), _ptr(w), _ptr(a), _ptr(b), _ptr(xlo), _ptr(xhi),
+        _ptr(y), _ptr(x), _ptr(info), int(nprob), 1, int(max_its), int(bool(clip)),
+        _stream_ptr()))
+    return x, info
 
 
 def make_1d_tree(ncells, imbalanced=False):

@@ -17,7 +17,7 @@ HEADERS = [os.path.join(HERE, "csrc", f) for f in
            ("kernels.cuh", "node_solve.cuh", "fast_kernels.cuh", "ring_kernels.cuh",
             "tree_plan.h")] + \
           [os.path.join(ROOT, "include", f) for f in
-           ("cedr_b200.h", "cedr_b200_device_op.h")]
+           ("cedr_b200.h", "cedr_b200_device_op.h", "cedr_b200_local.hpp")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "fast_kernels.cuh"
 #include "ring_kernels.cuh"
+#include "cedr_b200_local.hpp"
 #include "tree_plan.h"
 
 namespace {
@@ -1548,6 +1549,37 @@ void require_device () {
 
 } // namespace
 
+namespace {
+// One thread per element, the element's values in registers (cedr_b200_local.hpp).
+template <int N>
+__global__ void __launch_bounds__(128)
+local_solve_kernel (const int method, const int nprob, const int n, const double* w,
+                    const double* a, const double* b, const double* xlo, const double* xhi,
+                    const double* y, double* x, int* info, const long long sv,
+                    const long long sp, const int max_its, const bool clip) {
+  namespace L = cedr::local;
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= nprob) return;
+  const long long o = p*sp;
+  const bool nonneg = method == CEDR_B200_LOCAL_NONNEG_LS || method == CEDR_B200_LOCAL_NONNEG_CAAS;
+  const double bp = b[p];
+  if (nonneg && bp < 0) { info[p] = -1; return; }    // x untouched, as in the reference
+  L::Registers<N> v;
+  v.gather(n, w ? w + o : nullptr, a ? a + o : nullptr, bp, nonneg ? nullptr : xlo + o,
+           nonneg ? nullptr : xhi + o, y + o, sv);
+  int r = 0;
+  switch (method) {
+  case CEDR_B200_LOCAL_QP: r = L::solve_qp(v, max_its); break;
+  case CEDR_B200_LOCAL_CAAS: L::clip_and_spread(v, clip); break;
+  case CEDR_B200_LOCAL_NONNEG_LS: r = L::solve_nonneg(v, L::Method::least_squares); break;
+  case CEDR_B200_LOCAL_NONNEG_CAAS: r = L::solve_nonneg(v, L::Method::caas); break;
+  case CEDR_B200_LOCAL_QP_2D: r = L::solve_qp2(v, clip, true); break;
+  }
+  v.scatter(x + o, sv);
+  info[p] = r;
+}
+} // namespace
+
 extern "C" {
 
 const char* cedr_b200_last_error (void) { return g_err.c_str(); }
@@ -1724,6 +1756,34 @@ int cedr_b200_caas_set_user_reducer (cedr_b200_cdr* c, cedr_b200_user_reducer_fn
     c->user_reducer = fn;
     c->user_reducer_ctx = ctx;
     c->user_naccum = n_accum_in_place;
+  });
+}
+
+int cedr_b200_local_solve (int method, int nprob, int n, const double* w, const double* a,
+                           const double* b, const double* xlo, const double* xhi,
+                           const double* y, double* x, int* info, int64_t sv, int64_t sp,
+                           int max_its, int clip, void* stream) {
+  return guarded([&] {
+    require_device();
+    cedr_b200_throw_if(method < CEDR_B200_LOCAL_QP || method > CEDR_B200_LOCAL_QP_2D,
+                       "unknown local method");
+    cedr_b200_throw_if(n < 1 || n > 16, "local solvers: 1 <= n <= 16 (cedr_local_inl.hpp:310)");
+    cedr_b200_throw_if(method == CEDR_B200_LOCAL_QP_2D && n != 2, "solve_1eq_bc_qp_2d: n is 2");
+    const bool nonneg = method == CEDR_B200_LOCAL_NONNEG_LS || method == CEDR_B200_LOCAL_NONNEG_CAAS;
+    cedr_b200_throw_if( ! b || ! y || ! x || ! info || ( ! nonneg && ( ! xlo || ! xhi)),
+                       "null array");
+    if (nprob <= 0) return;
+    if (max_its <= 0) max_its = 100;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = (nprob + 127)/128;
+#define CEDR_LOCAL_LAUNCH(N) local_solve_kernel<N><<<grid, 128, 0, st>>>(                  \
+      method, nprob, n, w, a, b, xlo, xhi, y, x, info, sv, sp, max_its, clip != 0)
+    if (n <= 2) CEDR_LOCAL_LAUNCH(2);
+    else if (n <= 4) CEDR_LOCAL_LAUNCH(4);
+    else if (n <= 8) CEDR_LOCAL_LAUNCH(8);
+    else CEDR_LOCAL_LAUNCH(16);
+#undef CEDR_LOCAL_LAUNCH
+    CUDA_CHECK(cudaGetLastError());
   });
 }
 
@@ -2007,6 +2067,127 @@ int cedr_b200_bind_arrays (cedr_b200_cdr* c, int64_t lda, const double* qm_min, 
     c->bound.qm_max = qm_max;
     c->bound.qm_prev = qm_prev;
     c->bound.qm_out = qm_out;
+  });
+}
+
+int cedr_b200_transport1d_cycle (cedr_b200_cdr* c, int nsteps, const double* y0_host,
+                                 double* yf_host, int use_graph, float* ms_per_step) {
+  return guarded([&] {
+    cedr_b200_throw_if( ! c->finished, "finish_setup must be called first.");
+    cedr_b200_throw_if(c->is_bfb || c->nranks != 1 || c->trcr_prob.empty() || nsteps < 1,
+                       "transport1d: one rank, at least one tracer and one step");
+    cedr_b200_throw_if(c->bound.on, "transport1d: unbind the arrays first");
+    const int n = c->ncells;
+    cedr_b200_throw_if(n < 4, "transport1d: at least 4 cells");
+    const int cls = c->trcr_cls[0];
+    cedr_b200_throw_if(cls == CLS_T || cls == CLS_CT,
+                       "transport1d: consistent-only tracers are not driven by this harness");
+    // Problem1D::init_mesh, uniform (cedr_test_1d_transport.cpp:143-169), and the static
+    // part of cycle / cubic_interp_periodic: departure points, their wrapped images and
+    // intervals (:14-18, :46-58, :238-241).
+    std::vector<double> xb(n + 1), xcp(n + 1), area(n), xp(n + 1);
+    std::vector<int> ti(n + 1), lci(n);
+    xb[0] = 0;
+    xb[n] = 1;
+    for (int i = 1; i < n; ++i) xb[i] = static_cast<double>(i)/n;
+    for (int i = 0; i < n; ++i) { xcp[i] = 0.5*(xb[i] + xb[i + 1]); area[i] = xb[i + 1] - xb[i]; }
+    xcp[n] = 1 + xcp[0];
+    const double xos = -1.0/nsteps;
+    for (int j = 0; j <= n; ++j) {
+      const double xi = xcp[j] + xos, xl = xcp[0], xr = xcp[n];
+      double x = xi;
+      if ( ! (x >= xl && x <= xr)) { const double w = xr - xl; x = xi - w*std::floor((xi - xl)/w); }
+      xp[j] = x;
+      int ip1 = static_cast<int>(std::upper_bound(xcp.begin(), xcp.end(), x) - xcp.begin());
+      if (ip1 == 0) ++ip1; else if (ip1 == n + 1) --ip1;
+      ti[j] = ip1 - 1;
+    }
+    for (int i = 0; i < n; ++i) {
+      const auto it = c->gci2lci.find(i);
+      cedr_b200_throw_if(c->is_caas ? false : it == c->gci2lci.end(),
+                         "transport1d: the CDR's cells must be 0..ncells-1");
+      lci[i] = c->is_caas ? i : it->second;
+    }
+    DevBuf<double> d_xcp, d_area, d_xp, d_y[2];
+    DevBuf<int> d_ti, d_lci;
+    d_xcp.upload(xcp); d_area.upload(area); d_xp.upload(xp); d_ti.upload(ti); d_lci.upload(lci);
+    d_y[0].alloc(n + 1); d_y[1].alloc(n + 1);
+    cudaStream_t own = nullptr, saved = c->stream;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamSynchronize(saved));
+    c->stream = own;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&] () {
+      c->stream = saved;
+      if (exec) cudaGraphExecDestroy(exec);
+      if (graph) cudaGraphDestroy(graph);
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+      cudaStreamDestroy(own);
+    };
+    try {
+      CUDA_CHECK(cudaMemcpyAsync(d_y[0].p, y0_host, sizeof(double)*(n + 1),
+                                 cudaMemcpyHostToDevice, own));
+      // rhom = the cell areas (cedr_test_1d_transport.cpp:283-289).
+      std::vector<double> rh(c->nlcl);
+      for (int i = 0; i < n; ++i) rh[lci[i]] = area[i];
+      CUDA_CHECK(cudaMemcpyAsync(c->in, rh.data(), sizeof(double)*c->nlcl,
+                                 cudaMemcpyHostToDevice, own));
+      CUDA_CHECK(cudaStreamSynchronize(own));
+      T1dArgs a;
+      std::memset(&a, 0, sizeof(a));
+      a.ncells = n;
+      a.xcp = d_xcp.p; a.area = d_area.p; a.tgt_i = d_ti.p; a.tgt_xp = d_xp.p; a.lci = d_lci.p;
+      a.in = c->in;
+      a.ld = c->ld;
+      a.row = c->trcr_row[0];
+      a.layout = (cls == CLS_NN || cls == CLS_CNN) ? 1 : 0;
+      cedr_b200_throw_if(a.layout == 0 && cls != CLS_CAAS && cls != CLS_CST,
+                         "transport1d: tracer 0 must conserve (Qm_prev is set every step)");
+      a.out = c->is_caas ? c->in + (static_cast<long long>(a.row) + 1)*c->ld : c->out;
+      const int grid = (n + 1 + 127)/128;
+      auto step = [&] (const int from) {
+        t1d_interp_set_kernel<<<grid, 128, 0, own>>>(a, d_y[from].p, d_y[1 - from].p);
+        CUDA_CHECK(cudaGetLastError());
+        run_any(*c, -1);
+        t1d_get_kernel<<<grid, 128, 0, own>>>(a, d_y[1 - from].p);
+        CUDA_CHECK(cudaGetLastError());
+      };
+      c->last_launches = 0;
+      c->ntimed = 0;
+      const bool prof = c->profiling;
+      c->profiling = false;
+      CUDA_CHECK(cudaEventCreate(&e0));
+      CUDA_CHECK(cudaEventCreate(&e1));
+      int done = 0;
+      if (use_graph && nsteps >= 2) {
+        // Two steps (y0 -> y1 -> y0) per graph launch: launch-bound work, replayed.
+        CUDA_CHECK(cudaStreamBeginCapture(own, cudaStreamCaptureModeThreadLocal));
+        step(0);
+        step(1);
+        CUDA_CHECK(cudaStreamEndCapture(own, &graph));
+        CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+        CUDA_CHECK(cudaEventRecord(e0, own));
+        for (; done + 2 <= nsteps; done += 2) CUDA_CHECK(cudaGraphLaunch(exec, own));
+      } else {
+        CUDA_CHECK(cudaEventRecord(e0, own));
+      }
+      for (; done < nsteps; ++done) step(done & 1);
+      CUDA_CHECK(cudaEventRecord(e1, own));
+      CUDA_CHECK(cudaStreamSynchronize(own));
+      c->profiling = prof;
+      float ms = 0;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+      if (ms_per_step) *ms_per_step = ms/nsteps;
+      CUDA_CHECK(cudaMemcpy(yf_host, d_y[nsteps & 1].p, sizeof(double)*(n + 1),
+                            cudaMemcpyDeviceToHost));
+    } catch (...) {
+      cleanup();
+      throw;
+    }
+    cleanup();
   });
 }
 

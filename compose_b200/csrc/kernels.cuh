@@ -680,6 +680,82 @@ get_qm_bulk_kernel (const double* src, const long long ld, const int ncells,
   }
 }
 
+// ---- the 1-D transport harness on the device (cedr_test_1d_transport.cpp:136-255): one
+// semi-Lagrangian step = periodic cubic interpolation at the departure points
+// (interp::cubic_interp_periodic, :38-85, with get_cubic, :24-36), the caller side of
+// run_cdr (:170-189: bounds from the domain of dependence, set_Qm) -- fused in one kernel
+// -- then CDR::run, then get_Qm / area (t1d_get_kernel). Tracer 0 of the CDR.
+struct T1dArgs {
+  int ncells;
+  const double* xcp;    // [ncells + 1] cell centres, the last one periodic image of the first
+  const double* area;   // [ncells]
+  const int* tgt_i;     // [ncells + 1] interval of each (wrapped) departure point
+  const double* tgt_xp; // [ncells + 1] the wrapped departure point
+  const int* lci;       // [ncells] cell -> local cell index of the CDR
+  double* in;           // the CDR's rows
+  long long ld;
+  int row;              // first row of tracer 0
+  int layout;           // 0: (min, Qm, max, prev) rows; 1: nonnegative (Qm, prev)
+  const double* out;    // results: QLT out row 0 / CAAS Qm row
+};
+
+__global__ void __launch_bounds__(128)
+t1d_interp_set_kernel (const T1dArgs a, const double* __restrict__ y, double* __restrict__ yi) {
+  const int j = blockIdx.x*blockDim.x + threadIdx.x;
+  const int nc = a.ncells;
+  if (j > nc) return;
+  const double* const x = a.xcp;
+  const int i = a.tgt_i[j], ip1 = i + 1;
+  auto slope = [&] (const int k) { return (y[k + 1] - y[k])/(x[k + 1] - x[k]); };
+  const double smid = slope(i);
+  double s1, s2;
+  if (i == 0) {
+    const double w = (x[nc] - x[nc - 1])/((x[1] - x[0]) + (x[nc] - x[nc - 1]));
+    s1 = (1 - w)*slope(nc - 1) + w*smid;
+  } else {
+    const double w = (x[i] - x[i - 1])/(x[ip1] - x[i - 1]);
+    s1 = (1 - w)*slope(i - 1) + w*smid;
+  }
+  if (i == nc - 1) {
+    const double w = (x[ip1] - x[i])/((x[ip1] - x[i]) + (x[1] - x[0]));
+    s2 = (1 - w)*smid + w*slope(0);
+  } else {
+    const double w = (x[ip1] - x[i])/(x[i + 2] - x[i]);
+    s2 = (1 - w)*smid + w*slope(ip1);
+  }
+  const double dx = x[ip1] - x[i], dx2 = dx*dx, dx3 = dx2*dx, den = -dx3;
+  const double c2 = s1, c3 = y[i];
+  const double b1 = y[ip1] - dx*c2 - c3, b2 = s2 - c2;
+  const double c0 = (2.0*b1 - dx*b2)/den, c1 = (-3.0*dx*b1 + dx2*b2)/den;
+  const double xij = a.tgt_xp[j] - x[i];
+  const double v = (((c0*xij + c1)*xij) + c2)*xij + c3;
+  yi[j] = v;
+  if (j == nc) return;
+  // run_cdr: bounds over the four cells of the domain of dependence.
+  double mn = y[(i - 1 + nc) % nc], mx = mn;
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    const double u = y[(i - 1 + k + nc) % nc];
+    mn = u < mn ? u : mn;
+    mx = mx < u ? u : mx;
+  }
+  const double ar = a.area[j];
+  double* const r = a.in + static_cast<long long>(a.row)*a.ld + a.lci[j];
+  if (a.layout == 0) {
+    r[0] = mn*ar; r[a.ld] = v*ar; r[2*a.ld] = mx*ar; r[3*a.ld] = y[j]*ar;
+  } else {
+    r[0] = v*ar; r[a.ld] = y[j]*ar;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+t1d_get_kernel (const T1dArgs a, double* __restrict__ yi) {
+  const int j = blockIdx.x*blockDim.x + threadIdx.x;
+  if (j > a.ncells) return;
+  const int c = j == a.ncells ? 0 : j;
+  yi[j] = a.out[a.lci[c]]/a.area[c];
+}
+
 // Synthetic workload of SURVEY.md 8(d): splitmix64, U = (z >> 11) * 2^-53.
 __device__ __forceinline__ double splitmix_u (const unsigned long long seed,
                                               const unsigned long long k) {

@@ -266,6 +266,42 @@ int cedr_b200_bfb_create(cedr_b200_cdr** reducer, int nleaf, int nnodes, int roo
 int cedr_b200_bfb_allreduce(cedr_b200_cdr* reducer, const double* send, double* recv,
                             int transpose, int phase);
 
+/* ---- element-local solvers, cedr_local.hpp:23-58 ------------------------ */
+
+/* cedr::local::solve_1eq_bc_qp / caas / solve_1eq_nonneg / solve_1eq_bc_qp_2d
+ * (cedr_local_inl.hpp:68-330) for a batch of `nprob` independent elements of `n` <= 16
+ * values each, one thread per element with the element held in registers
+ * (include/cedr_b200_local.hpp). Entry i of element p of every array is at
+ * [i*stride_var + p*stride_prob]: stride_var = nprob, stride_prob = 1 is the coalesced
+ * SoA layout; stride_var = 1, stride_prob = n is the reference's contiguous n-vectors.
+ * b is [nprob]; info [nprob] receives the reference's return codes (0 for CAAS). w may be
+ * NULL (all ones) where the method does not use it; xlo / xhi are ignored by the
+ * nonnegative methods. max_its <= 0 means the reference's default (100). */
+enum {
+  CEDR_B200_LOCAL_QP = 0,           /* solve_1eq_bc_qp */
+  CEDR_B200_LOCAL_CAAS = 1,         /* caas */
+  CEDR_B200_LOCAL_NONNEG_LS = 2,    /* solve_1eq_nonneg, Method::least_squares */
+  CEDR_B200_LOCAL_NONNEG_CAAS = 3,  /* solve_1eq_nonneg, Method::caas */
+  CEDR_B200_LOCAL_QP_2D = 4         /* solve_1eq_bc_qp_2d (n = 2) */
+};
+int cedr_b200_local_solve(int method, int nprob, int n, const double* w, const double* a,
+                          const double* b, const double* xlo, const double* xhi,
+                          const double* y, double* x, int* info, int64_t stride_var,
+                          int64_t stride_prob, int max_its, int clip, void* stream);
+
+/* ---- 1-D transport harness, cedr_test_1d_transport.cpp:136-255 ------------ */
+
+/* Problem1D::cycle(nsteps, y0, yf, cdr) on the device for tracer 0 of `cdr` (a QLT over
+ * the 1-D mesh tree of ncells cells, or a CAAS of ncells cells; uniform mesh): every step is
+ * the periodic cubic interpolation at the departure points fused with the caller side of
+ * run_cdr (bounds over the domain of dependence, set_Qm), CDR::run, and get_Qm / area --
+ * three launches. With use_graph the steps are captured once in a CUDA graph and replayed
+ * (the many-tiny-calls pattern of BASELINE.json's config 5). y0_host / yf_host hold
+ * ncells + 1 values (the last is the periodic image of the first). ms_per_step (may be
+ * NULL) receives the device time per step. rhom is set to the cell areas. */
+int cedr_b200_transport1d_cycle(cedr_b200_cdr* cdr, int nsteps, const double* y0_host,
+                                double* yf_host, int use_graph, float* ms_per_step);
+
 /* ---- introspection for tests / benches --------------------------------- */
 
 /* Number of kernels launched by the last run() on this CDR. */

@@ -1,13 +1,24 @@
-// cedr_b200_local.hpp -- the element-local solvers of COMPOSE's cedr::local
-// (cedr/cedr_local.hpp:23-58, cedr_local_inl.hpp) as __host__ __device__ inline functions:
-// what a HOMME-style caller runs per element right after CDR::run.
+// cedr_b200_local.hpp -- element-local solvers for the B200 CEDR path:
+// what a HOMME-style caller runs per element right after CDR::run,
 //
-//   min_x sum_i w_i (x_i - y_i)^2   s.t.  a'x = b,  xlo <= x <= xhi,   a, w > 0
+//   min_x sum_i w_i (x_i - y_i)^2   s.t.  a'x = b,  xlo <= x <= xhi,   a, w > 0.
 //
-// Same names, arguments and return codes as the reference. The operation order follows
-// the reference's exactly, so a caller compiled WITHOUT floating-point contraction
-// (nvcc -fmad=false; host: -ffp-contract=off) gets the reference's bits;
-// tests/cxx/test_cdr_mirror.cu checks that against the pinned oracle on the device.
+// The algorithms are those of COMPOSE's cedr::local (cedr/cedr_local.hpp:23-58,
+// cedr_local_inl.hpp; COMPOSE version 1.0, Copyright 2018 NTESS, BSD license -- see the
+// reference's LICENSE): a safeguarded Newton iteration on the dual variable, the closed form
+// for two variables, and clip-and-redistribute. Results are bit-identical to the reference
+// when the caller compiles without floating-point contraction (nvcc -fmad=false; host
+// -ffp-contract=off): every sum and product is formed in the reference's order.
+//
+// Organisation (not the reference's): the algorithms are templates over a STORAGE VIEW of
+// one element's problem, so the same code runs
+//   * on a `Registers<N>` view -- the element's n <= N values held by value, which on the
+//     device means in registers, gathered and scattered with arbitrary strides; this is what
+//     the batched kernels of the library use (cedr_b200_local_solve: one thread per
+//     element, SoA arrays with the element index fastest for coalesced access);
+//   * on a `Pointers` view -- the reference's calling convention (contiguous n-vectors), any n.
+//
+// The reference's names and signatures are kept as thin wrappers at the end of the file.
 #ifndef CEDR_B200_LOCAL_HPP
 #define CEDR_B200_LOCAL_HPP
 
@@ -25,214 +36,294 @@ namespace local {
 typedef int Int;
 typedef double Real;
 
-namespace impl {
-// cedr_kokkos.hpp:136-139: ternaries, not fmin/fmax.
-CEDR_B200_LOCAL_HD Real min (const Real a, const Real b) { return a < b ? a : b; }
-CEDR_B200_LOCAL_HD Real max (const Real a, const Real b) { return a > b ? a : b; }
+struct Method { enum Enum { least_squares, caas }; };
 
-// cedr_local_inl.hpp:13-18
-CEDR_B200_LOCAL_HD Real calc_r_tol (const Real b, const Real* a, const Real* y, const Int n) {
-  Real ab = std::fabs(b);
-  for (Int i = 0; i < n; ++i) ab = max(ab, std::fabs(a[i]*y[i]));
-  return 1e1*DBL_EPSILON*std::fabs(ab);
-}
+// ---------------------------------------------------------------- storage views
 
-// cedr_local_inl.hpp:23-41. 1: a corner solves the problem; -1: infeasible, x left at
-// the violated corner; 0: neither.
-CEDR_B200_LOCAL_HD Int check_lu (const Int n, const Real* a, const Real b, const Real* xlo,
-                                 const Real* xhi, const Real r_tol, Real* x) {
-  Real r = -b;
-  for (Int i = 0; i < n; ++i) { x[i] = xlo[i]; r += a[i]*x[i]; }
-  if (std::fabs(r) <= r_tol) return 1;
-  if (r > 0) return -1;
-  r = -b;
-  for (Int i = 0; i < n; ++i) { x[i] = xhi[i]; r += a[i]*x[i]; }
-  if (std::fabs(r) <= r_tol) return 1;
-  if (r < 0) return -1;
-  return 0;
-}
+// The reference's calling convention: caller-owned contiguous vectors.
+struct Pointers {
+  Int n;
+  const Real* w_;
+  const Real* a_;
+  const Real* lo_;
+  const Real* hi_;
+  const Real* y_;
+  Real* x_;
+  Real b;
+  CEDR_B200_LOCAL_HD Int size () const { return n; }
+  CEDR_B200_LOCAL_HD Real w (Int i) const { return w_[i]; }
+  CEDR_B200_LOCAL_HD Real a (Int i) const { return a_[i]; }
+  CEDR_B200_LOCAL_HD Real lo (Int i) const { return lo_[i]; }
+  CEDR_B200_LOCAL_HD Real hi (Int i) const { return hi_[i]; }
+  CEDR_B200_LOCAL_HD Real y (Int i) const { return y_[i]; }
+  CEDR_B200_LOCAL_HD Real& x (Int i) { return x_[i]; }
+};
 
-// cedr_local_inl.hpp:43-64: x(lambda) clipped to the bounds, the constraint residual and
-// its derivative.
-CEDR_B200_LOCAL_HD void calc_r (const Int n, const Real* w, const Real* a, const Real b,
-                                const Real* xlo, const Real* xhi, const Real* y,
-                                const Real lambda, Real* x, Real& r, Real& r_lambda) {
-  r = 0;
-  r_lambda = 0;
-  for (Int i = 0; i < n; ++i) {
-    const Real q = a[i]/w[i];
-    const Real x_trial = y[i] + lambda*q;
-    if (x_trial < xlo[i]) x[i] = xlo[i];
-    else if (x_trial > xhi[i]) x[i] = xhi[i];
-    else {
-      x[i] = x_trial;
-      r_lambda += a[i]*q;
+// One element held by value: with N a compile-time constant and the loops below fully
+// unrolled, the arrays live in registers on the device. Entries i >= n are ignored.
+template <int N> struct Registers {
+  Int n;
+  Real w_[N], a_[N], lo_[N], hi_[N], y_[N], x_[N];
+  Real b;
+  CEDR_B200_LOCAL_HD Int size () const { return n; }
+  CEDR_B200_LOCAL_HD Real w (Int i) const { return w_[i]; }
+  CEDR_B200_LOCAL_HD Real a (Int i) const { return a_[i]; }
+  CEDR_B200_LOCAL_HD Real lo (Int i) const { return lo_[i]; }
+  CEDR_B200_LOCAL_HD Real hi (Int i) const { return hi_[i]; }
+  CEDR_B200_LOCAL_HD Real y (Int i) const { return y_[i]; }
+  CEDR_B200_LOCAL_HD Real& x (Int i) { return x_[i]; }
+  // Entry i of the element at base[i*stride]. Null w / a mean all ones; null lo / hi are
+  // left for the caller to fill (the nonnegative problem derives them).
+  CEDR_B200_LOCAL_HD void gather (const Int n_, const Real* w, const Real* a, const Real b_,
+                                  const Real* lo, const Real* hi, const Real* y,
+                                  const long long stride) {
+    n = n_;
+    b = b_;
+#pragma unroll
+    for (Int i = 0; i < N; ++i) {
+      if (i >= n) break;
+      const long long o = i*stride;
+      w_[i] = w ? w[o] : 1.0;
+      a_[i] = a ? a[o] : 1.0;
+      if (lo) lo_[i] = lo[o];
+      if (hi) hi_[i] = hi[o];
+      y_[i] = y[o];
     }
-    r += a[i]*x[i];
   }
-  r -= b;
+  CEDR_B200_LOCAL_HD void scatter (Real* x, const long long stride) const {
+#pragma unroll
+    for (Int i = 0; i < N; ++i) {
+      if (i >= n) break;
+      x[i*stride] = x_[i];
+    }
+  }
+};
+
+// ---------------------------------------------------------------- the algorithms
+
+namespace impl {
+// cedr_kokkos.hpp:136-139: ternaries, not fmin / fmax (same NaN and signed-zero behaviour).
+CEDR_B200_LOCAL_HD Real lesser (const Real p, const Real q) { return p < q ? p : q; }
+CEDR_B200_LOCAL_HD Real greater (const Real p, const Real q) { return p > q ? p : q; }
+
+// cedr_local_inl.hpp:13-18: 10 eps max(|b|, max_i |a_i y_i|).
+template <typename V> CEDR_B200_LOCAL_HD Real residual_tolerance (const V& v) {
+  Real big = std::fabs(v.b);
+  for (Int i = 0; i < v.size(); ++i) big = greater(big, std::fabs(v.a(i)*v.y(i)));
+  return 1e1*DBL_EPSILON*std::fabs(big);
+}
+
+// cedr_local_inl.hpp:23-41: the constraint residual with every x at its lower, then its
+// upper bound. +1: that corner solves the problem; -1: infeasible (x stays at the violated
+// corner); 0: neither. x is left at the last corner tried.
+template <typename V> CEDR_B200_LOCAL_HD Int try_corners (V& v, const Real tol) {
+  for (Int side = 0; side < 2; ++side) {
+    Real r = -v.b;
+    for (Int i = 0; i < v.size(); ++i) {
+      v.x(i) = side == 0 ? v.lo(i) : v.hi(i);
+      r += v.a(i)*v.x(i);
+    }
+    if (std::fabs(r) <= tol) return 1;
+    if (side == 0 ? r > 0 : r < 0) return -1;
+  }
+  return 0;
 }
 } // namespace impl
 
-// cedr_local_inl.hpp:167-270: safeguarded Newton on the dual variable. Returns 0 if
-// x == y solves it, 1 if solved with x != y, -1 if infeasible, -2 if max_its was hit.
+// cedr_local_inl.hpp:167-270. Returns 1 if the problem was solved (also when a corner of the
+// box solves it), -1 if it is infeasible, -2 if max_its iterations did not suffice.
+//
+// The dual function r(lambda) = a'x(lambda) - b with x_i(lambda) = clamp(y_i + lambda
+// a_i/w_i) is piecewise linear and nondecreasing: Newton from inside the bracket
+// [lamlo, lamhi] outside of which every x_i sits on a bound, falling back to bisection when
+// a step leaves the bracket or (every other time) lands within 1e-3 of its ends.
+template <typename V>
+CEDR_B200_LOCAL_HD Int solve_qp (V& v, const Int max_its = 100) {
+  const Int n = v.size();
+  const Real tol = impl::residual_tolerance(v);
+  Int info = impl::try_corners(v, tol);
+  if (info != 0) return info;
+  for (Int i = 0; i < n; ++i)
+    if (v.x(i) != v.y(i)) { info = 1; v.x(i) = v.y(i); }
+
+  Real lamlo = 0, lamhi = 0;
+  for (Int i = 0; i < n; ++i) {
+    const Real s = v.w(i)/v.a(i);
+    const Real l = s*(v.lo(i) - v.y(i)), h = s*(v.hi(i) - v.y(i));
+    lamlo = i == 0 ? l : impl::lesser(lamlo, l);
+    lamhi = i == 0 ? h : impl::greater(lamhi, h);
+  }
+  const Real lamlo0 = lamlo, lamhi0 = lamhi;
+  Real lambda = (lamlo <= 0 && lamhi >= 0) ? 0 : lamlo;
+
+  bool bisected_last = false;
+  Int nbisect = 0;
+  for (Int it = 0; it < max_its; ++it) {
+    // x(lambda), r(lambda) and its slope over the coordinates strictly inside their bounds
+    // (cedr_local_inl.hpp:43-64).
+    Real r = 0, slope = 0;
+    for (Int i = 0; i < n; ++i) {
+      const Real q = v.a(i)/v.w(i);
+      const Real xt = v.y(i) + lambda*q;
+      if (xt < v.lo(i)) v.x(i) = v.lo(i);
+      else if (xt > v.hi(i)) v.x(i) = v.hi(i);
+      else {
+        v.x(i) = xt;
+        slope += v.a(i)*q;
+      }
+      r += v.a(i)*v.x(i);
+    }
+    r -= v.b;
+    if (std::fabs(r) <= tol) return 1;
+    // Bisection has run out of bits: infeasible only if a bracket end never moved.
+    if (nbisect > 64) return (lamhi == lamhi0 || lamlo == lamlo0) ? -1 : 1;
+    if (r > 0) lamhi = lambda; else lamlo = lambda;
+    lambda = slope != 0 ? lambda - r/slope : lamlo;
+    const Real margin = bisected_last ? 0 : 1e-3*(lamhi - lamlo);
+    bisected_last = lambda - lamlo < margin || lamhi - lambda < margin;
+    if (bisected_last) {
+      lambda = 0.5*(lamlo + lamhi);
+      ++nbisect;
+    }
+  }
+  return -2;
+}
+
+// cedr_local_inl.hpp:68-165: two variables in closed form. With early_exit_on_tol only
+// infeasibility returns early (the reference's inner `info` shadows the outer one, so a
+// corner that solves the problem falls through to the general case).
+template <typename V>
+CEDR_B200_LOCAL_HD Int solve_qp2 (V& v, const bool clip = true,
+                                  const bool early_exit_on_tol = true) {
+  if (early_exit_on_tol && impl::try_corners(v, impl::residual_tolerance(v)) == -1) return -1;
+  { // The optimum without the bounds, if it respects them.
+    Real qmass = 0, dm = v.b;
+    for (Int i = 0; i < 2; ++i) {
+      qmass += v.a(i)*(v.a(i)/v.w(i));
+      dm -= v.a(i)*v.y(i);
+    }
+    const Real lambda = dm/qmass;
+    bool inside = true;
+    for (Int i = 0; i < 2 && inside; ++i) {
+      v.x(i) = v.y(i) + lambda*(v.a(i)/v.w(i));
+      inside = ! (v.x(i) < v.lo(i) || v.x(i) > v.hi(i));
+    }
+    if (inside) return 1;
+  }
+  // Walk along the line a'x = b from its midpoint: the four bound lines cut it at cut[];
+  // the feasible segment lies between the two cuts that are neither the first minimum nor
+  // the first maximum. The better end of that segment is the solution.
+  const Real mid[2] = {0.5*v.b/v.a(0), 0.5*v.b/v.a(1)};
+  const Real dir[2] = {-v.a(1), v.a(0)};
+  const Real cut[4] = {(v.lo(1) - mid[1])/dir[1],    // bottom
+                       (v.hi(0) - mid[0])/dir[0],    // right
+                       (v.hi(1) - mid[1])/dir[1],    // top
+                       (v.lo(0) - mid[0])/dir[0]};   // left
+  Int kmin = 0, kmax = 0;
+  for (Int k = 1; k < 4; ++k) {
+    if (cut[k] < cut[kmin]) kmin = k;
+    if (cut[k] > cut[kmax]) kmax = k;
+  }
+  Int end[2] = {0, 0}, nend = 0;
+  for (Int k = 0; k < 4 && nend < 2; ++k)
+    if (k != kmin && k != kmax) end[nend++] = k;
+  Real cost[2];
+  for (Int e = 0; e < 2; ++e) {
+    Real c = 0;
+    for (Int i = 0; i < 2; ++i) {
+      v.x(i) = mid[i] + cut[end[e]]*dir[i];
+      const Real d = v.y(i) - v.x(i);
+      c += v.w(i)*(d*d);
+    }
+    cost[e] = c;
+  }
+  const Int side = end[cost[0] <= cost[1] ? 0 : 1];
+  // The chosen bound line pins one coordinate; the constraint gives the other.
+  const Int pinned = (side == 0 || side == 2) ? 1 : 0, other = 1 - pinned;
+  v.x(pinned) = (side == 0 || side == 3) ? v.lo(pinned) : v.hi(pinned);
+  v.x(other) = (v.b - v.a(pinned)*v.x(pinned))/v.a(other);
+  if (clip) v.x(other) = impl::lesser(v.hi(other), impl::greater(v.lo(other), v.x(other)));
+  return 1;
+}
+
+// cedr_local_inl.hpp:272-305: clip y into the bounds, then spread the mass defect over the
+// remaining capacities on the side it has to move to. Does not check feasibility.
+template <typename V>
+CEDR_B200_LOCAL_HD void clip_and_spread (V& v, const bool clip = true) {
+  const Int n = v.size();
+  Real dm = v.b;
+  for (Int i = 0; i < n; ++i) {
+    v.x(i) = impl::greater(v.lo(i), impl::lesser(v.hi(i), v.y(i)));
+    dm -= v.a(i)*v.x(i);
+  }
+  if (dm == 0) return;
+  const bool up = dm > 0;
+  Real cap = 0;
+  for (Int i = 0; i < n; ++i)
+    cap += v.a(i)*(up ? v.hi(i) - v.x(i) : v.x(i) - v.lo(i));
+  if (cap > 0) {
+    const Real fac = dm/cap;
+    for (Int i = 0; i < n; ++i)
+      v.x(i) += fac*(up ? v.hi(i) - v.x(i) : v.x(i) - v.lo(i));
+  }
+  if (clip)
+    for (Int i = 0; i < n; ++i)
+      v.x(i) = impl::greater(v.lo(i), impl::lesser(v.hi(i), v.x(i)));
+}
+
+// cedr_local_inl.hpp:307-330: x >= 0 in place of two-sided bounds; the upper bound b/a_i is
+// the value at which one entry holds all of the mass. The view's lo / hi are overwritten.
+template <int N>
+CEDR_B200_LOCAL_HD Int solve_nonneg (Registers<N>& v, const Method::Enum method) {
+  if (v.b < 0) return -1;
+#pragma unroll
+  for (Int i = 0; i < N; ++i) {
+    if (i >= v.n) break;
+    v.lo_[i] = 0;
+    v.hi_[i] = v.b/v.a_[i];
+  }
+  if (method == Method::caas) {
+    clip_and_spread(v);
+    return 1;
+  }
+  return v.n == 2 ? solve_qp2(v) : solve_qp(v);
+}
+
+// ---------------------------------------------------------------- the reference's names
+
 CEDR_B200_LOCAL_HD Int
 solve_1eq_bc_qp (const Int n, const Real* w, const Real* a, const Real b, const Real* xlo,
                  const Real* xhi, const Real* y, Real* x, const Int max_its = 100) {
-  const Real r_tol = impl::calc_r_tol(b, a, y, n);
-  Int info = impl::check_lu(n, a, b, xlo, xhi, r_tol, x);
-  if (info != 0) return info;
-  for (Int i = 0; i < n; ++i)
-    if (x[i] != y[i]) { info = 1; x[i] = y[i]; }
-  const Real wall_dist = 1e-3;
-  // Bracket of the dual variable within which some x_i is strictly inside its bounds.
-  Real lamlo = 0, lamhi = 0;
-  for (Int i = 0; i < n; ++i) {
-    const Real rq = w[i]/a[i];
-    const Real lamlo_i = rq*(xlo[i] - y[i]), lamhi_i = rq*(xhi[i] - y[i]);
-    if (i == 0) { lamlo = lamlo_i; lamhi = lamhi_i; }
-    else { lamlo = impl::min(lamlo, lamlo_i); lamhi = impl::max(lamhi, lamhi_i); }
-  }
-  const Real lamlo_feas = lamlo, lamhi_feas = lamhi;
-  Real lambda = lamlo <= 0 && lamhi >= 0 ? 0 : lamlo;
-  bool prev_step_bisect = false;
-  Int nbisect = 0;
-  info = -2;
-  for (Int iteration = 0; iteration < max_its; ++iteration) {
-    Real r, r_lambda;
-    impl::calc_r(n, w, a, b, xlo, xhi, y, lambda, x, r, r_lambda);
-    if (std::fabs(r) <= r_tol) { info = 1; break; }
-    if (nbisect > 64) {
-      // Bisection has run out of precision: infeasible only if a bracket end never moved.
-      info = (lamhi == lamhi_feas || lamlo == lamlo_feas) ? -1 : 1;
-      break;
-    }
-    if (r > 0) lamhi = lambda; else lamlo = lambda;
-    if (r_lambda != 0) lambda -= r/r_lambda; else lambda = lamlo;
-    const Real D = prev_step_bisect ? 0 : wall_dist*(lamhi - lamlo);
-    if (lambda - lamlo < D || lamhi - lambda < D) {
-      lambda = 0.5*(lamlo + lamhi);
-      ++nbisect;
-      prev_step_bisect = true;
-    } else {
-      prev_step_bisect = false;
-    }
-  }
-  return info;
+  Pointers v = {n, w, a, xlo, xhi, y, x, b};
+  return solve_qp(v, max_its);
 }
 
-// cedr_local_inl.hpp:68-165: the closed-form 2-variable case. With early_exit_on_tol only
-// infeasibility returns early (the reference's inner `info` shadows the outer one).
 CEDR_B200_LOCAL_HD Int
 solve_1eq_bc_qp_2d (const Real* w, const Real* a, const Real b, const Real* xlo,
                     const Real* xhi, const Real* y, Real* x, const bool clip = true,
                     const bool early_exit_on_tol = true) {
-  if (early_exit_on_tol) {
-    const Real r_tol = impl::calc_r_tol(b, a, y, 2);
-    if (impl::check_lu(2, a, b, xlo, xhi, r_tol, x) == -1) return -1;
-  }
-  { // Unconstrained optimum.
-    Real qmass = 0, dm = b;
-    for (Int i = 0; i < 2; ++i) {
-      const Real qi = a[i]/w[i];
-      qmass += a[i]*qi;
-      dm -= a[i]*y[i];
-    }
-    const Real lambda = dm/qmass;
-    bool ok = true;
-    for (Int i = 0; i < 2; ++i) {
-      x[i] = y[i] + lambda*(a[i]/w[i]);
-      if (x[i] < xlo[i] || x[i] > xhi[i]) { ok = false; break; }
-    }
-    if (ok) return 1;
-  }
-  // The line a'x = b cuts the four bound lines at alphas[]; the feasible segment lies
-  // between the two cuts that are neither the first minimum nor the first maximum.
-  Real x_base[2];
-  for (Int i = 0; i < 2; ++i) x_base[i] = 0.5*b/a[i];
-  const Real x_dir[2] = {-a[1], a[0]};
-  Real alphas[4];
-  alphas[0] = (xlo[1] - x_base[1])/x_dir[1];   // bottom
-  alphas[1] = (xhi[0] - x_base[0])/x_dir[0];   // right
-  alphas[2] = (xhi[1] - x_base[1])/x_dir[1];   // top
-  alphas[3] = (xlo[0] - x_base[0])/x_dir[0];   // left
-  Real mn = alphas[0], mx = alphas[0];
-  Int imin = 0, imax = 0;
-  for (Int i = 1; i < 4; ++i) {
-    if (alphas[i] < mn) { mn = alphas[i]; imin = i; }
-    if (alphas[i] > mx) { mx = alphas[i]; imax = i; }
-  }
-  Int ais[2] = {0, 0}, cnt = 0;
-  for (Int i = 0; i < 4 && cnt < 2; ++i)
-    if (i != imin && i != imax) ais[cnt++] = i;
-  Real objs[2];
-  for (Int j = 0; j < 2; ++j) {
-    const Real alpha = alphas[ais[j]];
-    Real obj = 0;
-    for (Int i = 0; i < 2; ++i) {
-      x[i] = x_base[i] + alpha*x_dir[i];
-      const Real d = y[i] - x[i];
-      obj += w[i]*(d*d);
-    }
-    objs[j] = obj;
-  }
-  const Int ai = ais[objs[0] <= objs[1] ? 0 : 1];
-  // Pin the coordinate whose bound line was chosen, solve the other from the constraint.
-  Int i0;
-  if (ai == 0 || ai == 2) { x[1] = ai == 0 ? xlo[1] : xhi[1]; i0 = 1; }
-  else { x[0] = ai == 1 ? xhi[0] : xlo[0]; i0 = 0; }
-  const Int i1 = (i0 + 1) % 2;
-  x[i1] = (b - a[i0]*x[i0])/a[i1];
-  if (clip) x[i1] = impl::min(xhi[i1], impl::max(xlo[i1], x[i1]));
-  return 1;
+  Pointers v = {2, w, a, xlo, xhi, y, x, b};
+  return solve_qp2(v, clip, early_exit_on_tol);
 }
 
-// cedr_local_inl.hpp:272-305: clip, then spread the mass defect over the remaining
-// capacities. Does not check feasibility.
 CEDR_B200_LOCAL_HD void
 caas (const Int n, const Real* a, const Real b, const Real* xlo, const Real* xhi,
       const Real* y, Real* x, const bool clip = true) {
-  Real dm = b;
-  for (Int i = 0; i < n; ++i) {
-    x[i] = impl::max(xlo[i], impl::min(xhi[i], y[i]));
-    dm -= a[i]*x[i];
-  }
-  if (dm == 0) return;
-  if (dm > 0) {
-    Real fac = 0;
-    for (Int i = 0; i < n; ++i) fac += a[i]*(xhi[i] - x[i]);
-    if (fac > 0) {
-      fac = dm/fac;
-      for (Int i = 0; i < n; ++i) x[i] += fac*(xhi[i] - x[i]);
-    }
-  } else if (dm < 0) {
-    Real fac = 0;
-    for (Int i = 0; i < n; ++i) fac += a[i]*(x[i] - xlo[i]);
-    if (fac > 0) {
-      fac = dm/fac;
-      for (Int i = 0; i < n; ++i) x[i] += fac*(x[i] - xlo[i]);
-    }
-  }
-  if (clip)
-    for (Int i = 0; i < n; ++i) x[i] = impl::max(xlo[i], impl::min(xhi[i], x[i]));
+  Pointers v = {n, nullptr, a, xlo, xhi, y, x, b};
+  clip_and_spread(v, clip);
 }
 
-struct Method { enum Enum { least_squares, caas }; };
-
-// cedr_local_inl.hpp:307-330: x >= 0 instead of two-sided bounds; n <= 16.
+// n <= 16 (cedr_local_inl.hpp:310); -3 otherwise.
 CEDR_B200_LOCAL_HD Int
 solve_1eq_nonneg (const Int n, const Real* a, const Real b, const Real* y, Real* x,
                   const Real* w, const Method::Enum lcl_method) {
   if (n > 16) return -3;
-  if (b < 0) return -1;
-  Real zero[16], xhi[16];
-  for (Int i = 0; i < n; ++i) { zero[i] = 0; xhi[i] = b/a[i]; }
-  if (lcl_method == Method::caas) {
-    caas(n, a, b, zero, xhi, y, x);
-    return 1;
-  }
-  if (n == 2) return solve_1eq_bc_qp_2d(w, a, b, zero, xhi, y, x);
-  return solve_1eq_bc_qp(n, w, a, b, zero, xhi, y, x);
+  if (b < 0) return -1;      // (x untouched, as in the reference)
+  Registers<16> v;
+  v.gather(n, w, a, b, nullptr, nullptr, y, 1);
+  const Int info = solve_nonneg(v, lcl_method);
+  v.scatter(x, 1);
+  return info;
 }
 
 } // namespace local

@@ -923,3 +923,82 @@ def test_bind_arrays_rejects_what_it_cannot_read_in_place():
         q.bind_arrays(a, z(), z(), z(), out=a)
     with pytest.raises(cb.CedrError, match="Qm_prev"):
         q.bind_arrays(z(), z(), z(), None, out=z())
+
+
+# ---------------------------------------------------------------- cedr::local (8f-4)
+
+@pytest.mark.parametrize("n", [2, 3, 4, 7, 16])
+def test_local_batched_solvers_bitwise(oracle, n):
+    """cedr_b200_local_solve: the element-local solvers of cedr_local_inl.hpp:68-330 for a
+    batch of elements in the coalesced SoA layout, one thread per element with the element
+    in registers -- x and the return codes bit for bit against the oracle's restatement of
+    the reference, for feasible, tight and infeasible problems."""
+    import torch
+    import compose_b200 as cb
+    rng = np.random.default_rng(100 + n)
+    nprob = 257
+    w = 0.1 + rng.random((n, nprob))
+    a = 0.1 + rng.random((n, nprob))
+    xlo = rng.random((n, nprob)) - 0.5
+    xhi = xlo + rng.random((n, nprob))*rng.choice([1.0, 1e-3], size=(1, nprob))
+    y = xlo + (xhi - xlo)*(1.6*rng.random((n, nprob)) - 0.3)
+    t = rng.random(nprob)*1.2 - 0.1          # some b outside [a'xlo, a'xhi]: infeasible
+    b = (a*xlo).sum(0)*(1 - t) + (a*xhi).sum(0)*t
+    dev = lambda v: torch.from_numpy(np.ascontiguousarray(v)).cuda()
+    d = {k: dev(v) for k, v in dict(w=w, a=a, xlo=xlo, xhi=xhi, y=y, b=b).items()}
+
+    def check(method, ref_fn, **kw):
+        x, info = cb.local_solve(method, d["b"], d["y"], **kw)
+        x, info = x.cpu().numpy(), info.cpu().numpy()
+        for p in range(nprob):
+            ri, rx = ref_fn(p)
+            assert info[p] == ri, (method, p, info[p], ri)
+            assert np.array_equal(x[:, p], rx), (method, p)
+
+    check(cb.LOCAL_QP, lambda p: oracle.solve_1eq_bc_qp(w[:, p], a[:, p], b[p], xlo[:, p],
+                                                        xhi[:, p], y[:, p]),
+          xlo=d["xlo"], xhi=d["xhi"], w=d["w"], a=d["a"])
+    check(cb.LOCAL_CAAS, lambda p: (0, oracle.local_caas(a[:, p], b[p], xlo[:, p], xhi[:, p],
+                                                         y[:, p])),
+          xlo=d["xlo"], xhi=d["xhi"], a=d["a"])
+    bn = np.abs(b) * np.where(rng.random(nprob) < 0.1, -1.0, 1.0)
+    d["b"] = dev(bn)
+    yn = rng.random((n, nprob)) - 0.2
+    d["y"] = dev(yn)
+
+    def nn(method):
+        def f(p):
+            info, x = oracle.solve_1eq_nonneg(a[:, p], bn[p], yn[:, p], w[:, p], method)
+            return info, (x if info != -1 or bn[p] >= 0 else np.zeros(n))
+        return f
+    check(cb.LOCAL_NONNEG_LS, nn(0), w=d["w"], a=d["a"])
+    check(cb.LOCAL_NONNEG_CAAS, nn(1), w=d["w"], a=d["a"])
+    if n == 2:
+        d["b"], d["y"] = dev(b), dev(y)
+        check(cb.LOCAL_QP_2D, lambda p: oracle.solve_1eq_bc_qp_2d(w[:, p], a[:, p], b[p],
+                                                                  xlo[:, p], xhi[:, p], y[:, p]),
+              xlo=d["xlo"], xhi=d["xhi"], w=d["w"], a=d["a"])
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_transport1d_device_harness_bitwise(oracle, use_graph):
+    """BASELINE.json config 5 entirely on the device (cedr_b200_transport1d_cycle): the 351
+    steps of cedr_test_1d_transport.cpp on 111 cells -- interpolation + set_Qm, CDR::run,
+    get_Qm per step, optionally replayed from a CUDA graph -- must end on the same bits as
+    the host loop driving the oracle, for qltnn, qlt and caas."""
+    import compose_b200 as cb
+    import transport1d as T
+    from test_oracle_golden import t1d_runners
+    ncells = 111
+    p, oruns = t1d_runners(oracle, ncells, caas_tree=True)
+    nsteps = int(3.17*ncells)
+    y0 = p.y0()
+    for name, kind, pt in (("yqltnn", "qlt", 1 | 8), ("yqlt", "qlt", 1 | 2), ("ycaas", "caas", 3)):
+        ref = p.cycle(nsteps, y0, oruns[name])
+        c = cb.QLT(ncells) if kind == "qlt" else cb.CAAS(ncells)
+        c.declare_tracer(pt)
+        c.end_tracer_declarations()
+        c.finish_setup()
+        yf, us = c.transport1d_cycle(nsteps, y0, use_graph=use_graph)
+        assert np.array_equal(yf, ref), name
+        assert us > 0
