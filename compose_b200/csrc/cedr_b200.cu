@@ -152,6 +152,13 @@ struct cedr_b200_cdr {
   std::vector<int> own_blocks; // tier-0 blocks this rank owns (all of them on one rank)
   int nown_max = 0;            // blocks per rank in the exchange message (padded)
   std::string partition_error; // why this rank's cells are not a subtree partition
+  // Replicated mode for cell -> rank maps that cut blocks (kernels.cuh repl_*): a one-rank
+  // CDR over the whole tree, fed by an all-gather of every rank's rows.
+  bool repl = false;
+  std::unique_ptr<cedr_b200_cdr> whole;
+  int nlcl_max = 0;
+  DevBuf<int> d_pos, d_pos_off;
+  int pos_me_off = 0;
   int64_t caas_cell0 = 0;
 
   // Tracers.
@@ -1074,6 +1081,7 @@ void launch_down (cedr_b200_cdr& c, int cls, int k) {
 // Doubles per rank in the exchange message: per owned block its index, its root's rhom
 // and the 4 nt record words. (Multi-rank runs exchange block roots: split == 0.)
 size_t exchange_count (const cedr_b200_cdr& c) {
+  if (c.repl) return static_cast<size_t>(c.nrows)*c.nlcl_max;
   return static_cast<size_t>(c.nown_max)*(1 + (4*c.trcr_prob.size() + 1));
 }
 
@@ -1405,7 +1413,37 @@ void run_bfb (cedr_b200_cdr& c, int phase) {
   launch_sweep_any(c, CLS_BFB, top, MODE_TOP, base_args(c, CLS_BFB, top));
 }
 
+void run_repl (cedr_b200_cdr& c, int phase) {
+  cedr_b200_cdr& w = *c.whole;
+  const int nt = static_cast<int>(c.trcr_prob.size());
+  if (phase <= 0) {
+    LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 0);
+    repl_pack_kernel<<<grid_for(exchange_count(c)), kThreads, 0, c.stream>>>(
+      c.in, c.ld, c.nlcl, c.nrows, c.nlcl_max, c.xsend);
+    CUDA_CHECK(cudaGetLastError());
+    ++c.last_launches;
+  }
+  if (phase < 0) exchange_allgather(c);
+  if (phase == 0) return;
+  {
+    LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 1);
+    repl_unpack_kernel<<<grid_for(exchange_count(c)*c.nranks), kThreads, 0, c.stream>>>(
+      c.xrecv, c.nranks, c.nrows, c.nlcl_max, c.d_pos.p, c.d_pos_off.p, w.in, w.ld);
+    CUDA_CHECK(cudaGetLastError());
+    ++c.last_launches;
+  }
+  w.stream = c.stream;
+  w.last_launches = 0;
+  run_qlt(w, -1);
+  c.last_launches += w.last_launches;
+  repl_keep_own_kernel<<<grid_for(static_cast<long long>(c.nlcl)*nt), kThreads, 0, c.stream>>>(
+    w.out, w.ld, c.d_pos.p + c.pos_me_off, c.nlcl, nt, c.out, c.ld);
+  CUDA_CHECK(cudaGetLastError());
+  ++c.last_launches;
+}
+
 void run_any (cedr_b200_cdr& c, int phase) {
+  if (c.repl) { run_repl(c, phase); return; }
   if (c.is_bfb) run_bfb(c, phase);
   else if (c.is_caas) run_caas(c, phase);
   else run_qlt(c, phase);
@@ -1445,6 +1483,29 @@ void finish_setup (cedr_b200_cdr& c) {
   const int nt = static_cast<int>(c.trcr_prob.size());
   c.d_trcr_row.upload(c.trcr_row);
   c.d_trcr_prob.upload(c.trcr_prob);
+  if (c.repl) {
+    // Only the caller-facing buffers, the exchange buffers and the cell -> leaf table live
+    // here; the sweeps belong to the whole-tree CDR.
+    std::vector<int> pos, off(c.nranks + 1, 0);
+    for (int r = 0; r < c.nranks; ++r) {
+      for (int i = 0; i < c.ncells; ++i)
+        if (c.plan.leaf_rank[i] == r) pos.push_back(i);
+      off[r + 1] = static_cast<int>(pos.size());
+    }
+    c.pos_me_off = off[c.rank];
+    c.d_pos.upload(pos);
+    c.d_pos_off.upload(off);
+    if ( ! c.xsend) {
+      c.xsend_own.alloc(exchange_count(c));
+      c.xrecv_own.alloc(exchange_count(c)*c.nranks);
+      c.xsend = c.xsend_own.p;
+      c.xrecv = c.xrecv_own.p;
+    }
+    c.whole->stream = c.stream;
+    finish_setup(*c.whole);
+    c.finished = true;
+    return;
+  }
   for (int k = 0; k < NCLS; ++k) c.d_cls_tracers[k].upload(c.cls_tracers[k]);
   c.fast_ok = c.fast_enabled && c.plan.tier0_fast &&
     reinterpret_cast<uintptr_t>(c.in) % 16 == 0 &&
@@ -1820,29 +1881,65 @@ int cedr_b200_declare_tracer (cedr_b200_cdr* c, int problem_type, int rhomidx) {
   });
 }
 
-int cedr_b200_end_tracer_declarations (cedr_b200_cdr* c) {
-  return guarded([&] {
-    cedr_b200_throw_if(! c->declaring, "end_tracer_declarations was already called.");
-    if (c->is_caas)
-      cedr_b200_throw_if(c->trcr_prob.size() == 0, "#tracers is 0.");
-    const int nt = static_cast<int>(c->trcr_prob.size());
-    c->trcr_row.resize(nt);
-    int row = 1; // row 0 is rhom
-    for (int k = 0; k < NCLS; ++k) c->cls_tracers[k].clear();
-    for (int t = 0; t < nt; ++t) {
-      c->trcr_row[t] = row;
-      const int cls = c->trcr_cls[t];
-      row += c->is_caas ? (c->caas_need_conserve ? 4 : 3) : qlt_l2r_words(cls);
-      c->cls_tracers[cls].push_back(t);
+namespace {
+void end_tracer_declarations (cedr_b200_cdr& c) {
+  cedr_b200_throw_if(! c.declaring, "end_tracer_declarations was already called.");
+  if (c.is_caas)
+    cedr_b200_throw_if(c.trcr_prob.size() == 0, "#tracers is 0.");
+  const int nt = static_cast<int>(c.trcr_prob.size());
+  c.trcr_row.resize(nt);
+  int row = 1; // row 0 is rhom
+  for (int k = 0; k < NCLS; ++k) c.cls_tracers[k].clear();
+  for (int t = 0; t < nt; ++t) {
+    c.trcr_row[t] = row;
+    const int cls = c.trcr_cls[t];
+    row += c.is_caas ? (c.caas_need_conserve ? 4 : 3) : qlt_l2r_words(cls);
+    c.cls_tracers[cls].push_back(t);
+  }
+  c.nrows = row;
+  c.ld = round_up(std::max(1, c.nlcl), 16);
+  // QLT with a cell -> rank map that cuts blocks of the plan (every rank sees the same
+  // plan, so all take this branch together): replicated mode.
+  bool cut = false;
+  if (c.nranks > 1 && ! c.is_caas && ! c.is_bfb) {
+    cut = c.plan.tiers.size() < 2;
+    for (const Block& b : c.plan.tiers[0].blocks) cut |= b.owner < 0;
+  }
+  if (cut) {
+    c.repl = true;
+    std::vector<int> cnt(c.nranks, 0);
+    for (int i = 0; i < c.ncells; ++i) {
+      const int r = c.plan.leaf_rank[i];
+      cedr_b200_throw_if(r < 0 || r >= c.nranks, "leaf " << i << " has rank " << r);
+      ++cnt[r];
     }
-    c->nrows = row;
-    c->ld = round_up(std::max(1, c->nlcl), 16);
-    cedr_b200_throw_if( ! c->partition_error.empty(), c->partition_error);
-    cedr_b200_throw_if(c->nranks > 1 && c->plan.tiers.size() < 2,
-                       "with nranks > 1 the tree plan needs >= 2 tiers "
-                       "(lower max_block_leaves for tiny trees)");
-    c->declaring = false;
-  });
+    c.nlcl_max = *std::max_element(cnt.begin(), cnt.end());
+    c.whole.reset(new cedr_b200_cdr);
+    cedr_b200_cdr& w = *c.whole;
+    w.prefer_mass_con = c.prefer_mass_con;
+    w.ncells = c.ncells;
+    w.tree_kids = c.tree_kids;
+    w.tree_cellidx = c.tree_cellidx;
+    w.tree_root = c.tree_root;
+    w.max_block_leaves = c.max_block_leaves;
+    w.fast_enabled = c.fast_enabled;
+    build_plan(w);
+    w.trcr_prob = c.trcr_prob;
+    w.trcr_cls = c.trcr_cls;
+    end_tracer_declarations(w);
+    c.declaring = false;
+    return;
+  }
+  cedr_b200_throw_if( ! c.partition_error.empty(), c.partition_error);
+  cedr_b200_throw_if(c.nranks > 1 && c.plan.tiers.size() < 2,
+                     "with nranks > 1 the tree plan needs >= 2 tiers "
+                     "(lower max_block_leaves for tiny trees)");
+  c.declaring = false;
+}
+} // namespace
+
+int cedr_b200_end_tracer_declarations (cedr_b200_cdr* c) {
+  return guarded([&] { end_tracer_declarations(*c); });
 }
 
 int cedr_b200_get_buffers_sizes (cedr_b200_cdr* c, size_t* b1, size_t* b2) {
@@ -1926,6 +2023,9 @@ int cedr_b200_print (const cedr_b200_cdr* c, char* buf, size_t bufsize) {
       ss << "\n  tier " << k << ": " << c->plan.tiers[k].nleaves << " leaves, "
          << c->plan.tiers[k].blocks.size() << " blocks (max "
          << c->plan.tiers[k].max_nl << " leaves)";
+    if (c->repl)
+      ss << "\n  cell -> rank map cuts blocks: replicated mode (all-gather of " << c->nrows
+         << " rows x " << c->nlcl_max << " cells per rank, whole tree swept on every rank)";
     ss << "\n";
     const std::string s = ss.str();
     if (buf && bufsize) {
@@ -2264,6 +2364,8 @@ int cedr_b200_p2p_get_handle (cedr_b200_cdr* c, void* handle64) {
   return guarded([&] {
     cedr_b200_throw_if( ! c->finished, "finish_setup must be called first.");
     cedr_b200_throw_if(c->nranks < 2, "peer-to-peer exchange needs nranks > 1");
+    cedr_b200_throw_if(c->repl, "peer-to-peer exchange: this cell -> rank map cuts blocks of "
+                       "the tree plan (replicated mode uses the all-gather)");
     cedr_b200_throw_if(c->nranks > 16, "peer-to-peer exchange supports up to 16 ranks");
     if ( ! c->p2p_arena.p) {
       c->p2p_arena.alloc(p2p_arena_doubles(*c));

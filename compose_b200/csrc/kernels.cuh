@@ -504,6 +504,50 @@ unpack_kernel (const double* recv, const int nranks, const int nown_max, const i
   }
 }
 
+// General cell -> rank maps: where a rank's cells are not whole blocks of the
+// tree plan -- the reference's pseudorandom test map rank = (ci + ci/nranks) % nranks,
+// cedr_tree.cpp:366-375, cuts every block -- every rank gathers every rank's rows, sweeps
+// the WHOLE tree as the one-rank path does, and keeps its own cells (replicated mode).
+// A rank's message: row-major [nrows][nlcl_max], zero padded.
+__global__ void __launch_bounds__(256)
+repl_pack_kernel (const double* in, const long long ld, const int nlcl, const int nrows,
+                  const int nlcl_max, double* send) {
+  const long long n = static_cast<long long>(nrows)*nlcl_max;
+  for (long long k = blockIdx.x*static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<long long>(gridDim.x)*blockDim.x) {
+    const long long row = k/nlcl_max;
+    const int i = static_cast<int>(k % nlcl_max);
+    send[k] = i < nlcl ? in[row*ld + i] : 0.0;
+  }
+}
+
+// Cell i of rank r is leaf pos[pos_off[r] + i] of the whole tree (DFS order).
+__global__ void __launch_bounds__(256)
+repl_unpack_kernel (const double* recv, const int nranks, const int nrows, const int nlcl_max,
+                    const int* pos, const int* pos_off, double* whole_in,
+                    const long long whole_ld) {
+  const long long per = static_cast<long long>(nrows)*nlcl_max, n = per*nranks;
+  for (long long k = blockIdx.x*static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<long long>(gridDim.x)*blockDim.x) {
+    const int r = static_cast<int>(k/per);
+    const long long kk = k % per, row = kk/nlcl_max;
+    const int i = static_cast<int>(kk % nlcl_max);
+    if (i < pos_off[r + 1] - pos_off[r]) whole_in[row*whole_ld + pos[pos_off[r] + i]] = recv[k];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+repl_keep_own_kernel (const double* whole_out, const long long whole_ld, const int* pos_me,
+                      const int nlcl, const int nt, double* out, const long long ld) {
+  const long long n = static_cast<long long>(nlcl)*nt;
+  for (long long k = blockIdx.x*static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<long long>(gridDim.x)*blockDim.x) {
+    const long long t = k/nlcl;
+    const int i = static_cast<int>(k % nlcl);
+    out[t*ld + i] = whole_out[t*whole_ld + pos_me[i]];
+  }
+}
+
 // CAAS::finish_locally, cedr_caas.cpp:211-253, per-cell part; also writes the
 // clipped value the reference stores in place during reduce_locally
 // (cedr_caas.cpp:177).

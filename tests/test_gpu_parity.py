@@ -430,11 +430,72 @@ def test_caas_subtree_partition_bitwise(oracle, ncells, P, mbl):
 
 def test_partition_must_be_whole_blocks():
     import compose_b200 as cb
-    # 3 ranks over 5400 cells: 1800-cell ranges cut the 675-leaf blocks.
+    # 3 ranks over 5400 cells: 1800-cell ranges cut the 675-leaf blocks. CAAS's built-in
+    # tree-ordered sums need whole blocks (any cell sets work with a UserAllReducer); QLT
+    # switches to its replicated mode (next test).
+    c = cb.CAAS(1800, cell0=1800, ncells_global=5400, rank=1, nranks=3)
+    c.declare_tracer(7)
+    with pytest.raises(cb.CedrError, match="whole blocks"):
+        c.end_tracer_declarations()
     q = cb.QLT(5400, rank=1, nranks=3)
     q.declare_tracer(7)
-    with pytest.raises(cb.CedrError, match="whole blocks"):
+    q.end_tracer_declarations()
+    assert "replicated mode" in q.print()
+
+
+def _rank_of_cell(kind, ci, ncells, P):
+    """oned::Mesh::rank, cedr_tree.cpp:366-375."""
+    if kind == "pseudorandom":
+        return (ci + ci//P) % P
+    return min(P - 1, ci//(ncells//P))
+
+
+@pytest.mark.parametrize("P", [2, 3, 8])
+@pytest.mark.parametrize("mult", [1, 2, 7, 21, 167])
+@pytest.mark.parametrize("decomp", ["contiguous", "pseudorandom"])
+@pytest.mark.parametrize("imbalanced", [False, True])
+def test_qlt_general_rank_maps_bitwise(oracle, P, mult, decomp, imbalanced):
+    """The reference's own multi-rank sweep (cedr_qlt.cpp:745-772): ncells = {1, 2, 7,
+    21} nranks (and a larger one) x {contiguous, pseudorandom cell -> rank map,
+    cedr_tree.cpp:366-375} x {balanced, imbalanced tree} x prefer_mass_con, P ranks emulated
+    on one device. Maps that cut blocks of the tree plan run in replicated mode; the
+    single-rank oracle on the whole problem is the reference, bit for bit."""
+    import torch
+    import compose_b200 as cb
+    ncells = mult*P
+    prefer = (mult + P) % 2 == 1
+    ts, v = R.generate(ncells, seed=31*ncells + P)
+    pts = [t.problem_type for t in ts]
+    tree = oracle.bisection_tree(ncells, imbalanced)
+    ref = oracle.qlt(tree, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev, prefer)
+    kids, cellidx, root = cb.make_1d_tree(ncells, imbalanced)
+    node_rank = np.array([_rank_of_cell(decomp, int(ci), ncells, P) if ci >= 0 else 0
+                          for ci in cellidx], np.int32)
+    cdrs, gcis = [], []
+    for r in range(P):
+        q = cb.QLT(ncells, tree=(kids, cellidx, root), node_rank=node_rank, rank=r, nranks=P,
+                   prefer_numerical_mass_conservation_to_numerical_bounds=prefer)
+        for p in pts:
+            q.declare_tracer(int(p))
         q.end_tracer_declarations()
+        q.use_tensor_exchange_buffers(P)
+        q.finish_setup()
+        g = q.get_owned_glblcells()
+        assert sorted(g.tolist()) == [ci for ci in range(ncells)
+                                      if _rank_of_cell(decomp, ci, ncells, P) == r]
+        for i in range(0, len(g), max(1, len(g)//5)):
+            assert q.gci2lci(int(g[i])) == i
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a)[..., g])).cuda()
+        q.set_rhom(dev(v.rhom))
+        q.set_Qm(dev(v.Qm), dev(v.Qm_min), dev(v.Qm_max), dev(v.Qm_prev))
+        cdrs.append(q)
+        gcis.append(g)
+    _emulate_exchange(cdrs)
+    res = np.empty((len(pts), ncells))
+    for q, g in zip(cdrs, gcis):
+        res[:, g] = q.get_Qm().cpu().numpy()
+    assert np.array_equal(res, ref)
+    assert R.check(ts, v, res, prefer) == []
 
 
 # ------------------------------------------------------------------ config 5 (1-D transport)

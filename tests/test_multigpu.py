@@ -24,7 +24,7 @@ def _ngpus():
         return 0
 
 
-def _worker(rank, world, port, ncells, nt, p2p, q, side_stream=False):
+def _worker(rank, world, port, ncells, nt, p2p, q, side_stream=False, pseudorandom=False):
     import torch
     import torch.distributed as dist
     import compose_b200 as cb
@@ -45,8 +45,17 @@ def _worker(rank, world, port, ncells, nt, p2p, q, side_stream=False):
         nl = ncells//world
         sl = slice(rank*nl, (rank + 1)*nl)
         dev = lambda a: torch.from_numpy(np.ascontiguousarray(a[..., sl])).cuda()
-        for kind in ("qlt", "caas"):
-            if kind == "qlt":
+        for kind in (("qlt",) if pseudorandom else ("qlt", "caas")):
+            if pseudorandom:
+                # rank = (ci + ci/nranks) % nranks (cedr_tree.cpp:366-375) cuts every block:
+                # replicated mode, one NCCL all-gather of the ranks' rows per run().
+                kids, cellidx, root = cb.make_1d_tree(ncells)
+                nr = np.array([(int(ci) + int(ci)//world) % world if ci >= 0 else 0
+                               for ci in cellidx], np.int32)
+                c = cb.QLT(ncells, tree=(kids, cellidx, root), node_rank=nr, rank=rank,
+                           nranks=world)
+                ref = o.qlt(tree, pts, rhom, lo, qq, hi, prev)
+            elif kind == "qlt":
                 c = cb.QLT(ncells, rank=rank, nranks=world)
                 ref = o.qlt(tree, pts, rhom, lo, qq, hi, prev)
             else:
@@ -64,6 +73,10 @@ def _worker(rank, world, port, ncells, nt, p2p, q, side_stream=False):
                 c.finish_setup()
             if p2p:
                 c.enable_p2p(world)
+            if pseudorandom:
+                g = c.get_owned_glblcells()
+                dev = lambda a: torch.from_numpy(np.ascontiguousarray(a[..., g])).cuda()
+                sl = g
             d = [dev(x) for x in (rhom, qq, lo, hi, prev)]
             torch.cuda.synchronize()
             c.set_rhom(d[0])
@@ -80,14 +93,17 @@ def _worker(rank, world, port, ncells, nt, p2p, q, side_stream=False):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("p2p,side_stream", [(False, False), (True, False), (False, True)])
-def test_two_gpus_bitwise(p2p, side_stream):
+@pytest.mark.parametrize("p2p,side_stream,pseudorandom",
+                         [(False, False, False), (True, False, False), (False, True, False),
+                          (True, False, True)])
+def test_two_gpus_bitwise(p2p, side_stream, pseudorandom):
     import torch.multiprocessing as mp
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 1000) + int(p2p) + 2*int(side_stream)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 5400, 24, p2p, q, side_stream))
+    port = 29600 + (os.getpid() % 1000) + int(p2p) + 2*int(side_stream) + 4*int(pseudorandom)
+    procs = [ctx.Process(target=_worker,
+                         args=(r, world, port, 5400, 24, p2p, q, side_stream, pseudorandom))
              for r in range(world)]
     for p in procs:
         p.start()
