@@ -376,13 +376,14 @@ def main():
 
     # ---- roofline of the dominant reconstructor pass (QLT run()): algorithmic bytes
     # (40 B x the updates one run() processes on this GPU) over the CUDA-event duration
-    # of the run's launches; traffic = DRAM bytes of the same launches from the committed
-    # ncu capture (profiles/r01_traffic.json, bytes per update x updates).
+    # of the run's launches; traffic = DRAM bytes of the same kernels from the committed
+    # ncu capture (profiles/r02_traffic.json, bytes per update x updates) -- NOT measured in
+    # this run (ncu cannot run inside a timed bench): "traffic_source" says so.
     peak, peak_src = measured_peaks()
     upd_gpu = updates/world
     ach = BYTES_PER_UPDATE*upd_gpu/(ms_qlt*1e-3)/1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     bpu = json.load(open(tpath))["bytes_per_update"] if os.path.exists(tpath) else None
     per_kernel = {}
     if kernels:
@@ -400,10 +401,14 @@ def main():
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach/peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel": "QLT::run(): fast::up_kernel + tier-1 sweep + fast::down2_kernel "
-                          "(dominant: down2_kernel); per GPU",
+                          "(dominant: down2_kernel); per GPU; duration = CUDA events around "
+                          "run() on its stream",
                 "algorithmic_bytes_per_update": BYTES_PER_UPDATE,
                 "algorithmic_bytes": BYTES_PER_UPDATE*upd_gpu,
                 "traffic_bytes_per_update": bpu["qlt"]["run_total"] if bpu else None,
+                "traffic_source": ("committed ncu --set full capture of the same kernels "
+                                   "(profiles/r02_traffic.json, profiles/r02_qlt_ne120_ncu.txt), "
+                                   "bytes per update x this run's updates; not re-measured here"),
                 "kernels": per_kernel,
                 "kernels_note": "per-kernel frac is against the measured COPY bandwidth (read + "
                                 "write); a read-mostly stream such as the up-sweep can exceed it",

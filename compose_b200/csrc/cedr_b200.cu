@@ -131,6 +131,7 @@ struct cedr_b200_cdr {
     double* qm_out = nullptr;
   } bound;
   DevBuf<int> d_ident;          // 0, 1, 2, ...: tracer -> row of a bound array
+  DevBuf<const double*> d_rowaddr;   // [4 nt]: row_map() per tracer and role, for the fast kernels
   // CAAS::UserAllReducer (CEDR_B200_CAAS_SUM_USER)
   cedr_b200_user_reducer_fn user_reducer = nullptr;
   void* user_reducer_ctx = nullptr;
@@ -375,6 +376,24 @@ RowMap row_map (const cedr_b200_cdr& c, int cls) {
   return rm;
 }
 
+// The fast kernels' table of row addresses (FastArgs::rowaddr), rebuilt whenever the rows
+// move (finish_setup, bind_arrays). Stream-ordered before the next run().
+void upload_rowaddr (cedr_b200_cdr& c) {
+  const size_t nt = c.trcr_prob.size();
+  if (nt == 0) return;
+  std::vector<const double*> h(4*nt, nullptr);
+  for (size_t t = 0; t < nt; ++t) {
+    const RowMap rm = row_map(c, c.trcr_cls[t]);
+    const long long o = c.bound.on ? static_cast<long long>(t)*rm.ld :
+      static_cast<long long>(c.trcr_row[t])*rm.ld;
+    for (int f = 0; f < 4; ++f)
+      if (rm.p[f]) h[4*t + f] = rm.p[f] + o;
+  }
+  if (c.d_rowaddr.n != h.size()) c.d_rowaddr.alloc(h.size());
+  CUDA_CHECK(cudaMemcpyAsync(c.d_rowaddr.p, h.data(), h.size()*sizeof(const double*),
+                             cudaMemcpyHostToDevice, c.stream));
+}
+
 SweepArgs base_args (cedr_b200_cdr& c, int cls, int tier) {
   SweepArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -434,7 +453,7 @@ fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
   a.rh = c.d_frh.p;
   a.in = c.in;
   a.in_ld = c.ld;
-  a.rows = row_map(c, cls);
+  a.rowaddr = c.d_rowaddr.p;
   a.trcr_row = c.d_trcr_row.p;
   a.trcr_prob = c.d_trcr_prob.p;
   a.rec_out = c.d_rec[1].p;
@@ -1584,6 +1603,7 @@ void finish_setup (cedr_b200_cdr& c) {
     c.xrecv = c.xrecv_own.p;
   }
   ring_setup(c);
+  upload_rowaddr(c);
   c.finished = true;
 }
 
@@ -2130,6 +2150,7 @@ int cedr_b200_bind_arrays (cedr_b200_cdr* c, int64_t lda, const double* qm_min, 
     cedr_b200_throw_if( ! c->finished, "finish_setup must be called first.");
     if ( ! qm) {          // unbind
       c->bound = cedr_b200_cdr::Bound();
+      upload_rowaddr(*c);
       return;
     }
     cedr_b200_throw_if(c->is_bfb, "bind_arrays is for QLT and CAAS");
@@ -2167,6 +2188,7 @@ int cedr_b200_bind_arrays (cedr_b200_cdr* c, int64_t lda, const double* qm_min, 
     c->bound.qm_max = qm_max;
     c->bound.qm_prev = qm_prev;
     c->bound.qm_out = qm_out;
+    upload_rowaddr(*c);
   });
 }
 

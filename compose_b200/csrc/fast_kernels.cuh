@@ -102,7 +102,11 @@ struct FastArgs {
   const NodeRh* rh;
   const double* in;             // tier-0 rows (the CDR's own buffer)
   long long in_ld;
-  RowMap rows;                  // where the tracers' leaf rows are (own buffer or bound arrays)
+  // Where the tracers' leaf rows are (the CDR's own buffer or arrays bound by the caller):
+  // rowaddr[4 t + role], role = 0 min, 1 Qm, 2 max, 3 prev; null where the class has none.
+  // (A table rather than the RowMap's four base pointers: the thread that issues the TMA
+  // copies then carries one pointer, which keeps down2_kernel at its register budget.)
+  const double* const* rowaddr;
   const int* trcr_row;
   const int* trcr_prob;
   double* rec_out;              // UP: [(4 t + f) rec_ld + block]
@@ -203,6 +207,9 @@ up_kernel (const FastArgs a) {
   auto issue = [&] (const int i) {
     const int t = a.tracers[g0 + i];
     double* dst = stage + (i & 1)*nrows*a.sbuf;
+    // (One load of the tracer's row index: the asm statements below are memory barriers
+    // to the compiler.)
+    const double* const* const ra = a.rowaddr + 4*t;
     mbar_expect_tx(&mbar[i & 1], nstage*bytes);
 #pragma unroll
     for (int f = 0; f < nrows; ++f)
@@ -210,7 +217,7 @@ up_kernel (const FastArgs a) {
         // Staged row f holds role (min, Qm, max, prev)[f]; the nonnegative classes stage
         // Qm[, prev] only.
         const int role = bounds ? f : (f == 0 ? 1 : 3);
-        tma_load(dst + f*a.sbuf, a.rows.row(role, t) + src0, bytes, &mbar[i & 1]);
+        tma_load(dst + f*a.sbuf, ra[role] + src0, bytes, &mbar[i & 1]);
       }
   };
   if (tid == 0) {
@@ -653,11 +660,11 @@ down2_kernel (const FastArgs a) {
   auto issue = [&] (const int i) {
     const int t = a.tracers[g0 + i];
     double* dst = stage + (i & 1)*3*sbuf;
+    const double* const* const ra = a.rowaddr + 4*t;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&mbar[i & 1], 3*bytes);
 #pragma unroll
-    for (int f = 0; f < 3; ++f)
-      tma_load(dst + f*sbuf, a.rows.row(f, t) + src0, bytes, &mbar[i & 1]);
+    for (int f = 0; f < 3; ++f) tma_load(dst + f*sbuf, ra[f] + src0, bytes, &mbar[i & 1]);
   };
   if (tid == 0) {
     issue(0);
