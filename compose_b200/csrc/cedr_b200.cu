@@ -310,7 +310,12 @@ void launch_sweep (cedr_b200_cdr& c, int tier, const SweepArgs& a) {
   cedr_b200_throw_if(grid > 0x7fffffffLL, "grid too large");
   LaunchTimer lt(c, MODE == MODE_UP ? CEDR_B200_TAG_UP : MODE == MODE_TOP ?
                  CEDR_B200_TAG_TOP : CEDR_B200_TAG_DOWN, tier);
-  sweep_kernel<CLS, MODE><<<static_cast<unsigned>(grid), kThreads, smem, c.stream>>>(a);
+  // One thread per leaf of the largest block (the widest level), 64..256: small blocks --
+  // the tier above the tier-0 blocks has 128 leaves at ne120 -- get more CTAs per SM and
+  // cheaper barriers.
+  const int threads = std::max(64, std::min(kThreads,
+                                            (c.plan.tiers[tier].max_nl + 31)/32*32));
+  sweep_kernel<CLS, MODE><<<static_cast<unsigned>(grid), threads, smem, c.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++c.last_launches;
 }
@@ -1148,7 +1153,7 @@ void exchange_p2p (cedr_b200_cdr& c, bool with_rhom) {
   }
   {
     LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 0);
-    pack_p2p_kernel<<<grid_for(cnt), kThreads, 0, c.stream>>>(
+    pack_p2p_kernel<<<dim3(grid_for(cnt), c.nranks), kThreads, 0, c.stream>>>(
       c.d_blocks[0].p, nblocks_dev(c, 0), c.nown_max, static_cast<int>(c.trcr_prob.size()), 1,
       with_rhom ? c.d_rhom_tier[1].p : nullptr, c.d_rec[1].p, c.tier_ld[1], pp, c.rank,
       c.nranks, static_cast<long long>(cnt));
@@ -1159,7 +1164,8 @@ void exchange_p2p (cedr_b200_cdr& c, bool with_rhom) {
     LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 2);
     p2p_barrier_kernel<<<1, 32, 0, c.stream>>>(
       pp, reinterpret_cast<unsigned long long*>(c.p2p_arena.p), c.rank, c.nranks, c.p2p_epoch,
-      c.d_status.p);
+      c.d_status.p,
+      static_cast<unsigned long long>(env_int("CEDR_B200_P2P_TIMEOUT_MS", 30000))*1000000ull);
     CUDA_CHECK(cudaGetLastError());
     ++c.last_launches;
   }
@@ -1466,6 +1472,17 @@ void run_any (cedr_b200_cdr& c, int phase) {
   if (c.is_bfb) run_bfb(c, phase);
   else if (c.is_caas) run_caas(c, phase);
   else run_qlt(c, phase);
+  if (c.p2p_on && phase != 0 && ! c.is_bfb && ! c.bound.on) {
+    // (see poison_kernel) CAAS results are its Qm rows, QLT's the out rows.
+    const int nt = static_cast<int>(c.trcr_prob.size());
+    if (c.is_caas)
+      poison_kernel<<<148, kThreads, 0, c.stream>>>(c.d_status.p, c.in, c.ld, c.nlcl, nt, 2,
+                                                    c.caas_need_conserve ? 4 : 3);
+    else
+      poison_kernel<<<148, kThreads, 0, c.stream>>>(c.d_status.p, c.out, c.ld, c.nlcl, nt, 0, 1);
+    CUDA_CHECK(cudaGetLastError());
+    ++c.last_launches;
+  }
 }
 
 void get_buffers_sizes (cedr_b200_cdr& c, size_t& b1, size_t& b2) {

@@ -404,36 +404,42 @@ rhom_kernel (const RhomArgs a) {
 }
 
 // Multi-rank exchange (replaces the per-level messages of cedr_qlt.cpp:327-337, 432-439
-// and CAAS's MPI_Allreduce, cedr_caas.cpp:203-209): a rank's message is one entry per
-// owned tier-0 block, [global block index, rhom of the block root, the 4 nt words of its
-// record], padded with index -1 to the same length on every rank. After the all-gather
-// every rank scatters all entries into its (replicated) tier-1 leaf arrays.
+// and CAAS's MPI_Allreduce, cedr_caas.cpp:203-209): a rank's message carries, for each of
+// its (at most nown_max) tier-0 blocks, the global block index, the rhom of the block root
+// and the 4 nt words of its record. Layout: WORD-major, message[w*nown_max + j] for block
+// j -- word 0 the index (-1 pads), word 1 + e*(4 nt + 1) + i the i-th value of sub-root e --
+// so that consecutive threads move consecutive blocks: a rank's blocks are consecutive
+// leaves of the tier above, which makes both the gather from / scatter to the record rows
+// and the message accesses coalesced. After the exchange every rank scatters all entries
+// into its (replicated) tier-1 leaf arrays.
+__device__ __forceinline__ double
+exchange_word (const BlockDev* blocks, const int nown, const int j, const long long w,
+               const long long per, const int E, const double* rhom1, const double* rec,
+               const long long rec_ld) {
+  if (j >= nown) return w == 0 ? -1.0 : 0.0;
+  const long long g = blocks[j].gidx;
+  if (w == 0) return static_cast<double>(g);
+  const long long e = (w - 1)/per, i = (w - 1) % per, leaf = g*E + e;
+  return i == 0 ? (rhom1 ? rhom1[leaf] : 0.0) : rec[(i - 1)*rec_ld + leaf];
+}
+
 __global__ void __launch_bounds__(256)
 pack_kernel (const BlockDev* blocks, const int nown, const int nown_max, const int nt,
              const int E, const double* rhom1, const double* rec, const long long rec_ld,
              double* send) {
-  // Entry of a block: [gidx | E x (rhom, 4 nt record words)], word index w = 1 + e*(4nt+1) + i.
-  const long long per = 4LL*nt + 1, stride = 1 + E*per, n = stride*nown_max;
+  const long long per = 4LL*nt + 1, nw = 1 + E*per, n = nw*nown_max;
   for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
        k += (long long) gridDim.x*blockDim.x) {
-    const int j = (int) (k / stride);
-    const long long w = k % stride;
-    double v = w == 0 ? -1.0 : 0.0;
-    if (j < nown) {
-      const long long g = blocks[j].gidx;
-      if (w == 0) v = (double) g;
-      else {
-        const long long e = (w - 1)/per, i = (w - 1) % per, leaf = g*E + e;
-        v = i == 0 ? (rhom1 ? rhom1[leaf] : 0.0) : rec[(i - 1)*rec_ld + leaf];
-      }
-    }
-    send[k] = v;
+    const int j = (int) (k % nown_max);
+    send[k] = exchange_word(blocks, nown, j, k / nown_max, per, E, rhom1, rec, rec_ld);
   }
 }
 
 // The same message, stored straight into every rank's receive buffer over peer-mapped
 // memory (NVLink): rank `me` owns slot `me` of each peer's rank-major buffer. Replaces
-// pack + all-gather; p2p_barrier_kernel then publishes and awaits the epoch.
+// pack + all-gather; p2p_barrier_kernel then publishes and awaits the epoch. blockIdx.y is
+// the peer: the gather is repeated per peer (L2 hits) so that the stores to the eight peers
+// go out in parallel rather than one after the other from each thread.
 struct PeerPtrs { double* recv[16]; unsigned long long* flags[16]; };
 
 __global__ void __launch_bounds__(256)
@@ -441,23 +447,15 @@ pack_p2p_kernel (const BlockDev* blocks, const int nown, const int nown_max, con
                  const int E, const double* rhom1, const double* rec, const long long rec_ld,
                  const PeerPtrs peers, const int me, const int nranks,
                  const long long rank_stride) {
-  const long long per = 4LL*nt + 1, stride = 1 + E*per, n = stride*nown_max;
+  const long long per = 4LL*nt + 1, nw = 1 + E*per, n = nw*nown_max;
+  double* const dst = peers.recv[blockIdx.y] + me*rank_stride;
   for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
        k += (long long) gridDim.x*blockDim.x) {
-    const int j = (int) (k / stride);
-    const long long w = k % stride;
-    double v = w == 0 ? -1.0 : 0.0;
-    if (j < nown) {
-      const long long g = blocks[j].gidx;
-      if (w == 0) v = (double) g;
-      else {
-        const long long e = (w - 1)/per, i = (w - 1) % per, leaf = g*E + e;
-        v = i == 0 ? (rhom1 ? rhom1[leaf] : 0.0) : rec[(i - 1)*rec_ld + leaf];
-      }
-    }
-    for (int r = 0; r < nranks; ++r) peers.recv[r][me*rank_stride + k] = v;
+    const int j = (int) (k % nown_max);
+    dst[k] = exchange_word(blocks, nown, j, k / nown_max, per, E, rhom1, rec, rec_ld);
   }
-  __threadfence_system();
+  // (No fence here: the kernel boundary orders these stores before p2p_barrier_kernel,
+  // whose system-scope release publishes them together with the epoch flag.)
 }
 
 // Epoch barrier across the ranks' GPUs: publish "rank me has delivered epoch e" into every
@@ -466,37 +464,61 @@ pack_p2p_kernel (const BlockDev* blocks, const int nown, const int nown_max, con
 // wait cannot starve the writer (unlike two spinning kernels on ONE device).
 __global__ void p2p_barrier_kernel (const PeerPtrs peers, unsigned long long* my_flags,
                                     const int me, const int nranks,
-                                    const unsigned long long epoch, int* status) {
+                                    const unsigned long long epoch, int* status,
+                                    const unsigned long long timeout_ns) {
   const int r = threadIdx.x;
   __threadfence_system();
   if (r < nranks) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(peers.flags[r] + me), "l"(epoch)
                  : "memory");
-    unsigned long long v = 0;
+    unsigned long long v = 0, t0 = 0;
     unsigned spins = 0;
     for (;;) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(my_flags + r)
                    : "memory");
       if (v >= epoch) break;
       __nanosleep(100);
-      if (++spins > (1u << 24)) { atomicExch(status, 2); break; }   // ~2 s: a rank is gone
+      // A rank that is late (first step, I/O, load imbalance) is waited for; one that is
+      // gone must not hang the device: give up after timeout_ns (CEDR_B200_P2P_TIMEOUT_MS,
+      // default 30 s) and let poison_kernel mark this run's results.
+      if ((++spins & 1023u) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > timeout_ns) { atomicExch(status, 2); break; }
+      }
     }
   }
   __threadfence_system();
+}
+
+// After a run() whose exchange gave up: the results were formed from stale or partial peer
+// data -- overwrite them with NaN so that no caller mistakes them for an answer (the error
+// itself is reported by cedr_b200_synchronize). Costs one load per thread otherwise.
+__global__ void __launch_bounds__(256)
+poison_kernel (const int* status, double* out, const long long ld, const int ncells,
+               const int nrows, const int row0, const int row_stride) {
+  if (*status == 0) return;
+  const long long n = static_cast<long long>(ncells)*nrows;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (long long k = blockIdx.x*static_cast<long long>(blockDim.x) + threadIdx.x; k < n;
+       k += static_cast<long long>(gridDim.x)*blockDim.x)
+    out[(row0 + (k/ncells)*row_stride)*ld + k % ncells] = nan;
 }
 
 __global__ void __launch_bounds__(256)
 unpack_kernel (const double* recv, const int nranks, const int nown_max, const int nt,
                const int E, double* rhom1, double* rec, const long long rec_ld,
                const long long rank_stride) {
-  const long long per = 4LL*nt + 1, stride = 1 + E*per, nper = stride*nown_max;
+  const long long per = 4LL*nt + 1, nw = 1 + E*per, nper = nw*nown_max;
   const long long n = nper*nranks;
   for (long long k = blockIdx.x*(long long) blockDim.x + threadIdx.x; k < n;
        k += (long long) gridDim.x*blockDim.x) {
     const long long r = k / nper, kk = k % nper;
     const double* const msg = recv + r*rank_stride;
-    const long long ent = kk / stride, w = kk % stride;
-    const long long g = (long long) msg[ent*stride];
+    const long long w = kk / nown_max;
+    const int j = (int) (kk % nown_max);
+    const long long g = (long long) msg[j];
     if (g < 0 || w == 0) continue;
     const long long e = (w - 1)/per, i = (w - 1) % per, leaf = g*E + e;
     if (i == 0) { if (rhom1) rhom1[leaf] = msg[kk]; }

@@ -51,19 +51,21 @@ def _worker(rank, world, port, ncells, mbl, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         p = cb.partition_probe(ncells, rank, world, max_block_leaves=mbl)
-        stride = 2
-        send = torch.full((p["nown_max"]*stride,), -1.0, dtype=torch.float64)
+        # The kernels' message layout (kernels.cuh pack_kernel): word-major,
+        # message[w*nown_max + j]; word 0 = global block index (-1 pads), word 1 = payload.
+        nwords, nmax = 2, p["nown_max"]
+        send = torch.full((nwords*nmax,), -1.0, dtype=torch.float64)
         for j, (g, l0, nl) in enumerate(zip(p["gidx"], p["leaf0"], p["nl"])):
-            send[j*stride] = float(g)
-            send[j*stride + 1] = float(sum(range(l0, l0 + nl)))   # "up-sweep" of cell ids
+            send[j] = float(g)
+            send[nmax + j] = float(sum(range(l0, l0 + nl)))   # "up-sweep" of cell ids
         recv = torch.empty(world*send.numel(), dtype=torch.float64)
         dist.all_gather_into_tensor(recv, send)
         tier1 = np.full(p["nblocks"], np.nan)
-        e = recv.numpy().reshape(-1, stride)
-        for g, val in e:
-            if g >= 0:
-                assert np.isnan(tier1[int(g)])      # each block arrives exactly once
-                tier1[int(g)] = val
+        for msg in recv.numpy().reshape(world, nwords, nmax):
+            for g, val in zip(msg[0], msg[1]):
+                if g >= 0:
+                    assert np.isnan(tier1[int(g)])      # each block arrives exactly once
+                    tier1[int(g)] = val
         q.put((rank, float(tier1.sum()), bool(np.isnan(tier1).any())))
     finally:
         dist.destroy_process_group()
