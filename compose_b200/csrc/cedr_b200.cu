@@ -441,9 +441,15 @@ SweepArgs base_args (cedr_b200_cdr& c, int cls, int tier) {
 // ---- fast tier-0 kernels (fast_kernels.cuh)
 
 bool fast_class (int cls, int mode) {
-  if (mode == MODE_UP) return cls == CLS_ST || cls == CLS_CST || cls == CLS_CAAS;
-  return cls == CLS_ST || cls == CLS_CST;
+  if (std::getenv("CEDR_B200_FAST_ST_ONLY") && cls != CLS_ST && cls != CLS_CST &&
+      cls != CLS_CAAS)
+    return false;
+  if (mode == MODE_UP) return cls <= CLS_CAAS;
+  return cls < CLS_CAAS;
 }
+
+// Classes the mid kernels (local split of a multi-rank run) cover.
+bool three_field_class (int cls) { return cls == CLS_ST || cls == CLS_CST; }
 
 fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
   fast::FastArgs a;
@@ -480,7 +486,7 @@ fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
   a.n7buf = c.d_n7.p;
   a.rq = c.d_frq.p;
   a.caas_rows = c.caas_need_conserve ? 4 : 3;
-  if (c.split && cls != CLS_CAAS) {
+  if (c.split && cls != CLS_CAAS && (c.x_tier || three_field_class(cls))) {
     a.split = c.split;
     a.rec_out = c.d_xrec.p;
     a.rec_ld = c.x_ld;
@@ -520,17 +526,35 @@ void launch_fast (cedr_b200_cdr& c, K kernel, const fast::FastArgs& a, size_t sm
 
 void launch_fast_up (cedr_b200_cdr& c, int cls) {
   const fast::FastArgs a = fast_args(c, cls);
-  const int nrows = cls == CLS_ST ? 3 : 4;
+  const int nrows = (cls == CLS_ST || cls == CLS_T) ? 3 : cls == CLS_NN ? 1 : cls == CLS_CNN ? 2 : 4;
   const size_t smem = sizeof(double)*2*nrows*a.sbuf + 16 + sizeof(double)*32;
   switch (cls) {
   case CLS_ST: launch_fast(c, fast::up_kernel<CLS_ST>, a, smem, CEDR_B200_TAG_UP); break;
   case CLS_CST: launch_fast(c, fast::up_kernel<CLS_CST>, a, smem, CEDR_B200_TAG_UP); break;
+  case CLS_T: launch_fast(c, fast::up_kernel<CLS_T>, a, smem, CEDR_B200_TAG_UP); break;
+  case CLS_CT: launch_fast(c, fast::up_kernel<CLS_CT>, a, smem, CEDR_B200_TAG_UP); break;
+  case CLS_NN: launch_fast(c, fast::up_kernel<CLS_NN>, a, smem, CEDR_B200_TAG_UP); break;
+  case CLS_CNN: launch_fast(c, fast::up_kernel<CLS_CNN>, a, smem, CEDR_B200_TAG_UP); break;
   case CLS_CAAS: launch_fast(c, fast::up_kernel<CLS_CAAS>, a, smem, CEDR_B200_TAG_UP); break;
   }
 }
 
 void launch_fast_down (cedr_b200_cdr& c, int cls) {
   const fast::FastArgs a = fast_args(c, cls);
+  if ( ! three_field_class(cls)) {
+    const size_t smem1 = fast::down1_smem_bytes(a.sbuf);
+    switch (cls) {
+    case CLS_T: launch_fast(c, fast::down1_kernel<CLS_T>, a, smem1, CEDR_B200_TAG_DOWN,
+                            fast::kDown2Threads); break;
+    case CLS_CT: launch_fast(c, fast::down1_kernel<CLS_CT>, a, smem1, CEDR_B200_TAG_DOWN,
+                             fast::kDown2Threads); break;
+    case CLS_NN: launch_fast(c, fast::down1_kernel<CLS_NN>, a, smem1, CEDR_B200_TAG_DOWN,
+                             fast::kDown2Threads); break;
+    case CLS_CNN: launch_fast(c, fast::down1_kernel<CLS_CNN>, a, smem1, CEDR_B200_TAG_DOWN,
+                              fast::kDown2Threads); break;
+    }
+    return;
+  }
   size_t smem = fast::down2_smem_bytes(a.sbuf);
   if (const char* e = std::getenv("CEDR_B200_SMEM_PAD")) smem += std::atoi(e);  // occupancy experiments
   if (cls == CLS_ST)
@@ -1002,8 +1026,14 @@ template <int CLS> void launch_top_x_cls (cedr_b200_cdr& c, int cls) {
 }
 
 void launch_top_x (cedr_b200_cdr& c, int cls) {
-  if (cls == CLS_ST) launch_top_x_cls<CLS_ST>(c, cls);
-  else launch_top_x_cls<CLS_CST>(c, cls);
+  switch (cls) {
+  case CLS_ST: launch_top_x_cls<CLS_ST>(c, cls); break;
+  case CLS_CST: launch_top_x_cls<CLS_CST>(c, cls); break;
+  case CLS_T: launch_top_x_cls<CLS_T>(c, cls); break;
+  case CLS_CT: launch_top_x_cls<CLS_CT>(c, cls); break;
+  case CLS_NN: launch_top_x_cls<CLS_NN>(c, cls); break;
+  case CLS_CNN: launch_top_x_cls<CLS_CNN>(c, cls); break;
+  }
 }
 
 // Build the expanded tier: every leaf b of the tier-1 block (a tier-0 block root) becomes
@@ -1247,7 +1277,7 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
   }
   // Multi-rank: the fast classes' blocks are split locally (build_split).
   auto local_split = [&] (int cls) {
-    return c.split && ! c.x_tier && c.fast_ok && fast_class(cls, MODE_DOWN);
+    return c.split && ! c.x_tier && c.fast_ok && three_field_class(cls);
   };
   if (phase <= 0) {
     run_rhom(c, 0, multi ? 1 : ntiers);

@@ -289,10 +289,12 @@ up_kernel (const FastArgs a) {
       if (f == 3 && ! prev) continue;
       r[f] = __shfl_sync(0xffffffffu, r[f], src_lane);
     }
-    if ((CLS == CLS_ST || CLS == CLS_CST) && a.n7buf) {
+    if ( ! R::caas && a.n7buf) {
+      // Depth-7 sums for the down-sweep's top warp (the one-field classes need Qm only).
       double* const n7 = a.n7buf + (static_cast<long long>(t)*a.nblocks + b)*384;
 #pragma unroll
-      for (int f = 0; f < 3; ++f) n7[f*128 + tid] = r[f];
+      for (int f = 0; f < 3; ++f)
+        if (f == 1 || (CLS == CLS_ST || CLS == CLS_CST)) n7[f*128 + tid] = r[f];
     }
     // Depths 6..2 inside the warp: lane l (l % 2^(L+1) == 0) takes left + right.
 #pragma unroll
@@ -772,6 +774,219 @@ down2_kernel (const FastArgs a) {
   }
   if (tid == 0) tma_store_wait_read();
   if (tid == 0) CEDR_PHASE_FLUSH(0);
+}
+
+// ------------------------------------------------------- DOWN, one-field classes
+//
+// QLT::r2l_solve_qp for the classes whose node problems need only the Qm sums: consistent
+// only (t, ct: the bounds are the tracer's global q_min, q_max times the node's rhom,
+// cedr_qlt_inl.hpp:175-188) and nonnegative (nn, cnn: bounds [0, b], :188-197). Same
+// pipeline as down2_kernel -- a top warp walks depths 0..6 a tracer ahead of four leaf warps
+// that own the depth-7 micro-subtrees -- over one staged row per tracer instead of three.
+inline size_t down1_smem_bytes (const int sbuf) {
+  return sizeof(double)*(2*static_cast<size_t>(sbuf) + 2*128 + 2*128 + 2*256 + kD9) +
+    128*(sizeof(dev::NodeWQ) + sizeof(dev::NodeRh)) + 32;
+}
+
+template <int CLS>
+__device__ __forceinline__ void
+solve_one_field (const dev::NodeWQ& c, const dev::NodeRh& r, const bool prefer,
+                 const double qmin, const double qmax, const double ym, const double bm,
+                 const double y0, const double y1, double& x0, double& x1) {
+  dev::NodeConst nc;
+  nc.w0 = c.w0; nc.w1 = c.w1; nc.q0 = c.q0; nc.q1 = c.q1; nc.rh0 = r.rh0; nc.rh1 = r.rh1;
+  if (Rows<CLS>::nonneg) {
+    dev::solve_node_nonneg(nc, bm, y0, y1, x0, x1);
+  } else {
+    const double rh = r.rh0 + r.rh1;
+    dev::solve_node_bounded(nc, prefer, qmin*rh, ym, qmax*rh, bm, qmin*r.rh0, y0, qmax*r.rh0,
+                            qmin*r.rh1, y1, qmax*r.rh1, x0, x1);
+  }
+}
+
+template <int CLS>
+__global__ void __launch_bounds__(kDown2Threads)
+down1_kernel (const FastArgs a) {
+  typedef Rows<CLS> R;
+  static_assert(R::nonneg || R::consistent_only, "one-field down-sweep: t, ct, nn, cnn");
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int sbuf = a.sbuf;
+  double* const stage = reinterpret_cast<double*>(smraw);            // [2][sbuf]
+  double* const n7s = stage + 2*sbuf;                                // [2][128]
+  double* const un = n7s + 2*128;                                    // [2][128]
+  double* const xs = un + 2*128;                                     // [2][256]
+  double* const d9x = xs + 2*256;                                    // [4][128]
+  dev::NodeWQ* const topc = reinterpret_cast<dev::NodeWQ*>(d9x + kD9);    // [128]
+  dev::NodeRh* const toprh = reinterpret_cast<dev::NodeRh*>(topc + 128);  // [128]
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(toprh + 128);   // [2] rows, [2] n7
+  constexpr int BAR_T = 1, BAR_C = 3, BAR_LEAF = 5;
+
+  const int b = blockIdx.x % a.nblocks, grp = blockIdx.x / a.nblocks;
+  const BlockDev B = a.blocks[b];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int src0 = B.leaf0 & ~1, shift = B.leaf0 - src0;
+  const unsigned bytes = 8u*static_cast<unsigned>(((B.leaf0 + B.nl + 1) & ~1) - src0);
+  const int g0 = grp*a.group;
+  const int gn = min(a.group, a.ntr - g0);
+  const dev::NodeWQ* const wq = a.wq + B.fbase;
+  const dev::NodeRh* const rh = a.rh + B.fbase;
+  const bool prefer = a.prefer_mass_con != 0;
+
+  if (tid < kHeapNodes/4) { topc[tid] = wq[tid]; toprh[tid] = rh[tid]; }
+  if (tid == 0) {
+    for (int q = 0; q < 4; ++q) mbar_init(&mbar[q], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == 4) {
+    // ------------------------------------------------------------- TOP warp
+    auto issue_n7 = [&] (const int i) {
+      const int t = a.tracers[g0 + i];
+      const double* src = a.n7buf + (static_cast<long long>(t)*a.nblocks + b)*384 + 128;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&mbar[2 + (i & 1)], 128*8);
+      tma_load(n7s + (i & 1)*128, src, 128*8, &mbar[2 + (i & 1)]);
+    };
+    if (lane == 0) {
+      issue_n7(0);
+      if (gn > 1) issue_n7(1);
+    }
+    for (int i = 0; i < gn; ++i) {
+      const int t = a.tracers[g0 + i];
+      const double* const s7 = n7s + (i & 1)*128;
+      double* const u = un + (i & 1)*128;
+      double* const x = xs + (i & 1)*256;
+      const int S = a.split, E = 1 << S;
+      double xroot = 0, qmin = 0, qmax = 0;
+      if (lane < E)
+        xroot = __ldcg(a.sol_in + static_cast<long long>(t)*a.sol_in_ld +
+                       static_cast<long long>(B.gidx)*E + lane);
+      if (R::consistent_only) { qmin = __ldcg(a.qglob + 2*t); qmax = __ldcg(a.qglob + 2*t + 1); }
+      mbar_wait(&mbar[2 + (i & 1)], (i >> 1) & 1);
+      if (i >= 2) bar_sync<BAR_C, kDown2Threads>(i & 1);   // C(i-2) is done with x, u
+      {
+        // Sums of depths 6..0 (heap node h has kids 2h+1, 2h+2; left + right).
+        const double2 v01 = reinterpret_cast<const double2*>(s7)[2*lane];
+        const double2 v23 = reinterpret_cast<const double2*>(s7)[2*lane + 1];
+        const double d6a = v01.x + v01.y, d6b = v23.x + v23.y;
+        u[63 + 2*lane] = d6a;
+        u[64 + 2*lane] = d6b;
+        double r = d6a + d6b;
+        u[31 + lane] = r;
+#pragma unroll
+        for (int Lv = 0; Lv < 5; ++Lv) {
+          if (Lv > 4 - S) break;
+          r = r + __shfl_down_sync(0xffffffffu, r, 1 << Lv);
+          if ((lane & ((2 << Lv) - 1)) == 0) u[(16 >> Lv) - 1 + (lane >> (Lv + 1))] = r;
+        }
+      }
+      if (lane < E) x[E - 1 + lane] = xroot;
+      __syncwarp();
+      for (int dd = S; dd <= 6; ++dd) {
+        for (int p = lane; p < (1 << dd); p += 32) {
+          const int h = (1 << dd) - 1 + p;
+          double y0, y1;
+          if (dd < 6) { y0 = u[2*h + 1]; y1 = u[2*h + 2]; }
+          else { const double2 v = reinterpret_cast<const double2*>(s7)[p]; y0 = v.x; y1 = v.y; }
+          double x0, x1;
+          solve_one_field<CLS>(topc[h], toprh[h], prefer, qmin, qmax, u[h], x[h], y0, y1, x0, x1);
+          x[2*h + 1] = x0;
+          x[2*h + 2] = x1;
+        }
+        __syncwarp();
+      }
+      if (lane == 0 && i + 2 < gn) issue_n7(i + 2);
+      bar_arrive<BAR_T, kDown2Threads>(i & 1);   // T(i): x[127..254] are solved
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------- LEAF warps
+  const int node = a.perm[B.fperm_off + tid];
+  const ushort4 e = reinterpret_cast<const ushort4*>(a.dtab + B.ftab_off)[node];
+  const int off[4] = {(e.x & 0x7fff) + shift, (e.y & 0x7fff) + shift,
+                      (e.z & 0x7fff) + shift, (e.w & 0x7fff) + shift};
+  const bool pr[4] = {(e.x >> 15) != 0, (e.y >> 15) != 0, (e.z >> 15) != 0,
+                      (e.w >> 15) != 0};
+  const unsigned* const pent = a.pent + B.fpent_off;
+  const int ps = pent[warp], pe = pent[warp + 1];
+  const dev::NodeWQ c7 = wq[127 + node], c8a = wq[255 + 2*node], c8b = wq[256 + 2*node];
+  const dev::NodeRh h7 = rh[127 + node], h8a = rh[255 + 2*node], h8b = rh[256 + 2*node];
+
+  auto issue = [&] (const int i) {
+    const int t = a.tracers[g0 + i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&mbar[i & 1], bytes);
+    tma_load(stage + (i & 1)*sbuf, a.rowaddr[4*t + 1] + src0, bytes, &mbar[i & 1]);
+  };
+  if (tid == 0) {
+    issue(0);
+    if (gn > 1) issue(1);
+  }
+
+  for (int k = 0; k < gn; ++k) {
+    const int t = a.tracers[g0 + k];
+    double* const s = stage + (k & 1)*sbuf;      // solved leaves replace the Qm row
+    const double* const x = xs + (k & 1)*256;
+    double qmin = 0, qmax = 0;
+    if (R::consistent_only) { qmin = __ldcg(a.qglob + 2*t); qmax = __ldcg(a.qglob + 2*t + 1); }
+    mbar_wait(&mbar[k & 1], (k >> 1) & 1);
+    double n9[4], n8[2], n7;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      n9[q] = s[off[q]];
+      if (pr[q]) n9[q] = n9[q] + s[off[q] + 1];
+    }
+    n8[0] = n9[0] + n9[1];
+    n8[1] = n9[2] + n9[3];
+    n7 = n8[0] + n8[1];
+    if (tid == 0 && k >= 1) {
+      tma_store_wait_read();
+      if (k + 1 < gn) issue(k + 1);
+    }
+    bar_sync<BAR_T, kDown2Threads>(k & 1);       // T(k) published
+    const double x7 = x[127 + node];
+    bar_arrive<BAR_C, kDown2Threads>(k & 1);     // xs / un of tracer k may be reused
+    double x8[2];
+    solve_one_field<CLS>(c7, h7, prefer, qmin, qmax, n7, x7, n8[0], n8[1], x8[0], x8[1]);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      double x9[2];
+      solve_one_field<CLS>(hf ? c8b : c8a, hf ? h8b : h8a, prefer, qmin, qmax, n8[hf], x8[hf],
+                           n9[2*hf], n9[2*hf + 1], x9[0], x9[1]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int q = 2*hf + j;
+        if (pr[q]) d9x[q*128 + tid] = x9[j];
+        else s[off[q]] = x9[j];
+      }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int j = ps + lane; j < pe; j += 32) {
+      const unsigned pe_j = pent[j];
+      const int r = pe_j >> 20, o = (pe_j & 0x7ff) + shift;
+      const double y0 = s[o], y1 = s[o + 1];
+      double x0, x1;
+      solve_one_field<CLS>(wq[kHeapNodes + r], rh[kHeapNodes + r], prefer, qmin, qmax, y0 + y1,
+                           d9x[(pe_j >> 11) & 0x1ff], y0, y1, x0, x1);
+      s[o] = x0;
+      s[o + 1] = x1;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    bar_sync_i<BAR_LEAF, kLeafThreads>();
+    if (tid == 0) {
+      double* const o = a.out + static_cast<long long>(t)*a.out_ld + B.leaf0;
+      const int q0 = B.leaf0 & 1;
+      const int nint = (B.nl - q0) & ~1;
+      if (nint) tma_store(o + q0, s + shift + q0, 8u*static_cast<unsigned>(nint));
+      tma_store_commit();
+      if (q0) o[0] = s[shift];
+      if (q0 + nint < B.nl) o[B.nl - 1] = s[shift + B.nl - 1];
+    }
+  }
+  if (tid == 0) tma_store_wait_read();
 }
 
 } // namespace fast

@@ -306,6 +306,33 @@ def test_caas_without_conserving_tracers_exact_buffers(oracle, ncells, ring):
     assert np.array_equal(c.get_Qm().cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("ncells", [5400, 2*1023, 8*513])
+@pytest.mark.parametrize("prefer", [False, True])
+def test_one_field_classes_fast_and_generic_kernels_agree(oracle, ncells, prefer, monkeypatch):
+    """The consistent-only (t, ct) and nonnegative (nn, cnn) classes,
+    cedr_qlt_inl.hpp:175-197, run fast::up_kernel + fast::down1_kernel on fast-shaped
+    blocks; CEDR_B200_FAST_ST_ONLY sends them through the generic sweep instead. Both must
+    equal the oracle bit for bit, for many tracers per class (several per CTA group)."""
+    import compose_b200 as cb
+    from gpu_util import run_qlt_gpu
+    ts, v = R.generate(ncells, seed=11*ncells + prefer)
+    S, C, T, N = cb.SHAPEPRESERVE, cb.CONSERVE, cb.CONSISTENT, cb.NONNEGATIVE
+    keep = [i for i, t in enumerate(ts) if t.problem_type in (T, C | T, N, C | N)]
+    assert len(keep) == 24
+    keep = keep*3       # 72 tracers: 18 per class
+    pts = [ts[i].problem_type for i in keep]
+    lo, q, hi, prev = (np.ascontiguousarray(a[keep]) for a in
+                       (v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev))
+    tree = oracle.bisection_tree(ncells)
+    ref = oracle.qlt(tree, pts, v.rhom, lo, q, hi, prev, prefer)
+    got, c = run_qlt_gpu(ncells, pts, v.rhom, lo, q, hi, prev, prefer=prefer, nrun=2)
+    assert c.uses_fast_path()
+    assert np.array_equal(got, ref)
+    monkeypatch.setenv("CEDR_B200_FAST_ST_ONLY", "1")
+    got2, c2 = run_qlt_gpu(ncells, pts, v.rhom, lo, q, hi, prev, prefer=prefer)
+    assert np.array_equal(got2, ref)
+
+
 def test_fast_and_generic_paths_agree_on_headline_inputs(oracle):
     import torch
     import compose_b200 as cb

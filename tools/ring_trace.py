@@ -19,6 +19,7 @@ ncells = int(sys.argv[2]) if len(sys.argv) > 2 else 86400
 nt = int(sys.argv[3]) if len(sys.argv) > 3 else 640
 rhom, lo, q, hi, prev = cb.fill_headline(ncells, nt, 2)
 c = cb.QLT(ncells) if kind == "qlt" else cb.CAAS(ncells)
+c.set_ring(True)
 for _ in range(nt):
     c.declare_tracer(7)
 c.end_tracer_declarations()
