@@ -421,21 +421,26 @@ def main():
     if not args.no_e2e:
         del qlt, caas
         torch.cuda.empty_cache()
-        pipe = HostStepPipeline(ncells, nt_lcl, rank=rank, nranks=world, p2p=P2P)
-        pin = lambda x: x.cpu().pin_memory()
-        rhom_h, lo_h, q_h, hi_h, prev_h = (pin(x) for x in (rhom, lo, q, hi, prev))
-        out_h = {k: torch.empty((nt_lcl, nl), dtype=torch.float64).pin_memory()
-                 for k in pipe.kinds}
-        pipe.step(rhom_h, lo_h, q_h, hi_h, prev_h, out_h)       # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        e0, e1 = ev(), ev()
-        e0.record()
-        for _ in range(args.steps):
-            pipe.step(rhom_h, lo_h, q_h, hi_h, prev_h, out_h)
-        e1.record()
-        barrier()
-        wall = time.perf_counter() - t0
+        from compose_b200.pipeline import near_gpu
+        # Pinned buffers and the copy-issuing thread on the GPU's NUMA node (restored
+        # afterwards: the CPU baseline leg uses every core).
+        with near_gpu(local_rank) as ng:
+            pipe = HostStepPipeline(ncells, nt_lcl, rank=rank, nranks=world, p2p=P2P)
+            pin = lambda x: x.cpu().pin_memory()
+            rhom_h, lo_h, q_h, hi_h, prev_h = (pin(x) for x in (rhom, lo, q, hi, prev))
+            out_h = {k: torch.empty((nt_lcl, nl), dtype=torch.float64).pin_memory()
+                     for k in pipe.kinds}
+            for _ in range(2):
+                pipe.step(rhom_h, lo_h, q_h, hi_h, prev_h, out_h)       # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(args.steps):
+                pipe.step(rhom_h, lo_h, q_h, hi_h, prev_h, out_h)
+            e1.record()
+            barrier()
+            wall = time.perf_counter() - t0
         ms_e2e = max(e0.elapsed_time(e1), 0.0)/args.steps
         t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -445,9 +450,13 @@ def main():
                "h2d_bytes_per_step": pipe.h2d_bytes_per_step*world,
                "d2h_bytes_per_step": pipe.d2h_bytes_per_step*world,
                "ms_per_step": ms_e2e, "wall_ms_per_step": 1e3*wall/args.steps,
-               "how": "pinned host SoA arrays -> chunked H2D / set_Qm / run / get_Qm / D2H "
-                      "pipeline over %d tracer chunks on %d streams (compose_b200.pipeline)"
-                      % (pipe.nchunks, len(pipe.slots))}
+               "host_gb_per_s": (pipe.h2d_bytes_per_step + pipe.d2h_bytes_per_step)*world
+                                /(ms_e2e*1e-3)/1e9,
+               "numa_local_cpus": len(ng.cpus) if ng.cpus else None,
+               "how": "pinned host SoA arrays -> chunked H2D / run() on the bound chunk arrays "
+                      "/ D2H pipeline over %d tracer chunks on %d streams "
+                      "(compose_b200.pipeline; bound=%s)"
+                      % (pipe.nchunks, len(pipe.slots), pipe.bound)}
         launches += pipe.launches_per_step*args.steps
 
     # ---- config 5 flavour: many tiny runs (111 cells x 1 tracer), device time per run()

@@ -555,6 +555,23 @@ class CAAS(CDR):
                                                              int(n_accum)))
 
 
+def allreduce_sum_reducer(group=None):
+    """The reference's default global reduction (cedr_caas.cpp:203-209: one partial sum per
+    field and rank, accumulated cell after cell, then MPI_Allreduce(SUM)) as a UserAllReducer
+    over torch.distributed. Use with n_accum = nlclcells, so that each rank contributes its
+    single sequential partial; this rank's cells may then be ANY set (cedr_caas.cpp:37-48
+    takes only nlclcells). The order in which the ranks' partials are added is the
+    collective's, as it is MPI's in the reference (two ranks: exact either way)."""
+    def reducer(send, recv, nlocal, nfld):
+        import torch.distributed as dist
+        if nlocal != 1:
+            raise ValueError("allreduce_sum_reducer needs n_accum == nlclcells (one partial "
+                             "per rank); got %d partials" % nlocal)
+        recv.copy_(send[:, 0])
+        dist.all_reduce(recv, op=dist.ReduceOp.SUM, group=group)
+    return reducer
+
+
 def _wrap_device(ptr, n):
     """A cuda float64 tensor over n doubles at device address `ptr` (no copy)."""
     import torch

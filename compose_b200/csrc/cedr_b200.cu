@@ -278,6 +278,11 @@ struct LaunchTimer {
 
 namespace {
 
+int env_int (const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+
 size_t sweep_smem_bytes (const cedr_b200_cdr& c, int tier) {
   return sizeof(double)*4*static_cast<size_t>(2*c.plan.tiers[tier].max_nl);
 }
@@ -313,8 +318,8 @@ void launch_sweep (cedr_b200_cdr& c, int tier, const SweepArgs& a) {
   // One thread per leaf of the largest block (the widest level), 64..256: small blocks --
   // the tier above the tier-0 blocks has 128 leaves at ne120 -- get more CTAs per SM and
   // cheaper barriers.
-  const int threads = std::max(64, std::min(kThreads,
-                                            (c.plan.tiers[tier].max_nl + 31)/32*32));
+  const int threads = std::max(env_int("CEDR_B200_SWEEP_MIN_THREADS", 64),
+                               std::min(kThreads, (c.plan.tiers[tier].max_nl + 31)/32*32));
   sweep_kernel<CLS, MODE><<<static_cast<unsigned>(grid), threads, smem, c.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++c.last_launches;
@@ -583,10 +588,6 @@ const void* ring_kernel_ptr (int cls, int np, int sw) {
 #undef CEDR_RK
 }
 
-int env_int (const char* name, int dflt) {
-  const char* e = std::getenv(name);
-  return e ? std::atoi(e) : dflt;
-}
 
 // Decide whether run() can be the ring kernel and build its tables; called from
 // finish_setup. One piece per CTA: consecutive depth-S subtrees of the tier-0 blocks.

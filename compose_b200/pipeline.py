@@ -9,9 +9,58 @@ independent problems, so chunking does not change any result). It uses only the
 public CDR API of compose_b200 (declare/finish_setup once, then bulk
 set_Qm/run/get_Qm per chunk).
 """
+import os
+
 import torch
 
 import compose_b200 as cb
+
+
+def cpus_near_gpu(device_index):
+    """The CPUs NVML reports as local to a CUDA device (its NUMA node), intersected with
+    what this process may run on; None when that cannot be determined."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(device_index)
+        try:
+            bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        nwords = (os.cpu_count() + 63)//64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, nwords)
+        cpus = {64*i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
+
+
+class near_gpu:
+    """Context manager: run the calling thread on the GPU's NUMA node, so that pinned host
+    buffers allocated (first touched) inside it are local to the GPU's PCIe root and the
+    copy-issuing thread is too. A no-op where NVML gives no answer."""
+
+    def __init__(self, device_index=None):
+        self.dev = torch.cuda.current_device() if device_index is None else device_index
+        self.cpus = None
+        self.saved = None
+
+    def __enter__(self):
+        self.cpus = cpus_near_gpu(self.dev)
+        if self.cpus:
+            try:
+                self.saved = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.cpus)
+            except OSError:
+                self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved:
+            os.sched_setaffinity(0, self.saved)
+        return False
 
 
 class HostStepPipeline:

@@ -899,6 +899,73 @@ def test_caas_user_reducer_sequential(oracle, ncells, n_accum):
         assert np.array_equal(got, oracle.caas(ncells, pts, lo, q, hi, prev, tree=None))
 
 
+@pytest.mark.parametrize("split", ["ragged", "pseudorandom"])
+def test_caas_any_cell_sets_per_rank_through_the_reducer(oracle, split):
+    """cedr_caas.cpp:37-48 takes only nlclcells: a rank's cells may be any set, the
+    cross-rank sum is the reducer's (default MPI_Allreduce of one sequential partial per
+    rank, :203-209). Three ranks emulated on one device with unequal, non-block-aligned
+    (or interleaved) cell sets and n_accum = nlclcells; the reducer plays the all-reduce
+    (partials added in rank order). Checked against a numpy CAAS summing in that order."""
+    import torch
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    ncells, nt, P = 2731, 5, 3
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, 13)
+    pts = [7, 3, 2, 7, 3]
+    if split == "ragged":
+        cuts = [0, 700, 701, ncells]
+        own = [np.arange(cuts[r], cuts[r + 1]) for r in range(P)]
+    else:
+        ci = np.arange(ncells)
+        rank_of = (ci + ci//P) % P          # cedr_tree.cpp:366-375
+        own = [ci[rank_of == r] for r in range(P)]
+    partials, total = {}, {}
+
+    def make(r, phase):
+        def reducer(send, recv, nlocal, nfld):
+            assert (nlocal, nfld) == (1, 4*nt)
+            if phase == 0:
+                partials[r] = send[:, 0].clone()
+                recv.copy_(send[:, 0])
+            else:
+                recv.copy_(total["v"])
+        return reducer
+
+    def run(phase):
+        outs = []
+        for r in range(P):
+            g = own[r]
+            c = cb.CAAS(len(g), user_reducer=make(r, phase), n_accum=len(g))
+            for p in pts:
+                c.declare_tracer(p)
+            c.end_tracer_declarations()
+            c.finish_setup()
+            dev = lambda a: torch.from_numpy(np.ascontiguousarray(a[..., g])).cuda()
+            c.set_rhom(dev(rhom))
+            c.set_Qm(dev(q), dev(lo), dev(hi), dev(prev))
+            c.run()
+            c.synchronize()
+            outs.append(c.get_Qm().cpu().numpy())
+        return outs
+    run(0)
+    t = partials[0].clone()
+    for r in range(1, P):
+        t = t + partials[r]
+    total["v"] = t
+    outs = run(1)
+    got = np.empty((nt, ncells))
+    for r in range(P):
+        got[:, own[r]] = outs[r]
+
+    def sums(v):
+        per_rank = [np.add.accumulate(v[:, own[r]], axis=1)[:, -1] for r in range(P)]
+        tot = per_rank[0]
+        for r in range(1, P):
+            tot = tot + per_rank[r]
+        return tot
+    assert np.array_equal(got, _numpy_caas(pts, lo, q, hi, prev, sums))
+
+
 def test_caas_user_reducer_backed_by_bfb_tree_allreducer(oracle):
     """the public BfbTreeAllReducer as the CAAS UserAllReducer (transpose =
     True is CAAS's (nlocal, nfld) send layout, cedr_caas.cpp:153-154): same bits as the

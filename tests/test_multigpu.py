@@ -92,6 +92,65 @@ def _worker(rank, world, port, ncells, nt, p2p, q, side_stream=False, pseudorand
         dist.destroy_process_group()
 
 
+def _caas_allreduce_worker(rank, world, port, ncells, nt, q):
+    """CAAS with arbitrary per-rank cell sets (cedr_caas.cpp:37-48): the cross-rank sum is
+    an NCCL all-reduce of one sequential partial per rank (cedr_caas.cpp:203-209)."""
+    import torch
+    import torch.distributed as dist
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["NCCL_DEBUG"] = "WARN"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        rhom, lo, qq, hi, prev = W.headline(ncells, nt, 31)
+        pts = [7, 3, 2]*(nt//3)
+        ci = np.arange(ncells)
+        own = [ci[((ci + ci//3) % 3 == 0) == (r == 0)] for r in range(2)]   # ~1/3 vs ~2/3
+        g = own[rank]
+        c = cb.CAAS(len(g), user_reducer=cb.allreduce_sum_reducer(), n_accum=len(g))
+        for p in pts:
+            c.declare_tracer(p)
+        c.end_tracer_declarations()
+        c.finish_setup()
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a[..., g])).cuda()
+        c.set_rhom(dev(rhom))
+        c.set_Qm(dev(qq), dev(lo), dev(hi), dev(prev))
+        c.run()
+        c.synchronize()
+        got = c.get_Qm().cpu().numpy()
+        from test_gpu_parity import _numpy_caas
+
+        def sums(v):   # two ranks: a + b in either order
+            return (np.add.accumulate(v[:, own[0]], axis=1)[:, -1] +
+                    np.add.accumulate(v[:, own[1]], axis=1)[:, -1])
+        ref = _numpy_caas(pts, lo, qq, hi, prev, sums)
+        q.put((rank, bool(np.array_equal(got, ref[:, g]))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
+def test_two_gpus_caas_any_cell_sets_allreduce():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_caas_allreduce_worker, args=(r, world, port, 2731, 6, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in out)
+
+
 @pytest.mark.skipif(_ngpus() < 2, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("p2p,side_stream,pseudorandom",
                          [(False, False, False), (True, False, False), (False, True, False),

@@ -1,7 +1,7 @@
 """What the host side of the box can feed: every rank copies pinned host buffers to its GPU
 and back at the same time (the traffic pattern of bench.py's end-to-end leg, no kernels).
 Explains the e2e numbers at N > 1: the aggregate host<->device rate, not the GPUs, is the
-limit.    torchrun --nproc-per-node N tools/h2d_aggregate.py [GB per rank]"""
+limit.    torchrun --nproc-per-node N tools/h2d_aggregate.py [GB per rank]   (H2D_NUMA=1: allocate on the GPU's NUMA node)"""
 import os
 import sys
 import time
@@ -15,8 +15,15 @@ torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
-gb = float(sys.argv[1]) if len(sys.argv) > 1 else 2.0
+argv = sys.argv[1:]
+gb = float(argv[0]) if argv else 2.0
 n = int(gb*1e9/8)
+numa = None
+if os.environ.get("H2D_NUMA"):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from compose_b200.pipeline import near_gpu
+    numa = near_gpu()
+    numa.__enter__()
 h_in = torch.empty(n, dtype=torch.float64).pin_memory()
 h_out = torch.empty(n//2, dtype=torch.float64).pin_memory()
 d_in = torch.empty(n, dtype=torch.float64, device="cuda")
@@ -45,6 +52,7 @@ if world > 1:
 dt = (time.perf_counter() - t0)/3
 if rank == 0:
     per = (n + n//2)*8/dt/1e9
+    print("numa-local cpus: %s" % (len(numa.cpus) if numa and numa.cpus else None))
     print("ranks %d: %.1f GB in + %.1f GB out per rank per step, %.1f ms -> %.1f GB/s per rank, "
           "%.1f GB/s aggregate" % (world, n*8/1e9, n*4/1e9, 1e3*dt, per, per*world))
 if world > 1:
