@@ -185,6 +185,7 @@ struct cedr_b200_cdr {
   DevBuf<FastRh> d_frh;
   DevBuf<double> d_frq;
   bool fast_enabled = true;   // cedr_b200_set_fast_path
+  BlockDev solo_block;        // tier 0's only block, when run() is the solo kernel
   bool fast_ok = false;       // plan + buffers allow the fast tier-0 kernels
   DevBuf<unsigned long long> d_phase_clk;   // debug (CEDR_B200_PHASE_CLOCKS builds)
   DevBuf<double> d_n7;        // depth-7 sums per own block x tracer (fast path)
@@ -318,8 +319,8 @@ void launch_sweep (cedr_b200_cdr& c, int tier, const SweepArgs& a) {
   // One thread per leaf of the largest block (the widest level), 64..256: small blocks --
   // the tier above the tier-0 blocks has 128 leaves at ne120 -- get more CTAs per SM and
   // cheaper barriers.
-  const int threads = std::max(env_int("CEDR_B200_SWEEP_MIN_THREADS", 64),
-                               std::min(kThreads, (c.plan.tiers[tier].max_nl + 31)/32*32));
+  int threads = std::max(64, std::min(kThreads, (c.plan.tiers[tier].max_nl + 31)/32*32));
+  if (const int e = env_int("CEDR_B200_SWEEP_THREADS", 0)) threads = std::min(threads, e);
   sweep_kernel<CLS, MODE><<<static_cast<unsigned>(grid), threads, smem, c.stream>>>(a);
   CUDA_CHECK(cudaGetLastError());
   ++c.last_launches;
@@ -1241,9 +1242,11 @@ template <int CLS> void launch_solo_cls (cedr_b200_cdr& c, int cls) {
   const SweepArgs a = base_args(c, cls, 0);
   if (a.ntr == 0) return;
   const size_t nn = 2*static_cast<size_t>(c.plan.tiers[0].max_nl);
-  const size_t smem = sizeof(double)*(5*nn + 2) + sizeof(dev::NodeConst)*nn;
+  // 4 nn sweep fields, nn rhom sums, ni < nn/2 node constants, 2 ni + nlev + 1 table ints.
+  const size_t smem = sizeof(double)*(5*nn + 2) + sizeof(dev::NodeConst)*(nn/2) +
+    sizeof(int)*(3*(nn/2) + 2);
   LaunchTimer lt(c, CEDR_B200_TAG_TOP, 0);
-  solo_kernel<CLS><<<a.ntr, kThreads, smem, c.stream>>>(a);
+  solo_kernel<CLS><<<a.ntr, kThreads, smem, c.stream>>>(a, c.solo_block);
   CUDA_CHECK(cudaGetLastError());
   ++c.last_launches;
 }
@@ -1616,6 +1619,7 @@ void finish_setup (cedr_b200_cdr& c) {
       hb[b].fbase = blk.ibase;
     }
     if (hb.empty()) hb.resize(1);
+    if (k == 0) c.solo_block = hb[0];
     c.d_blocks[k].upload(hb);
     c.tier_ld[k] = k == 0 ? c.ld : round_up(tier.nleaves, 16);
     if (k > 0) {

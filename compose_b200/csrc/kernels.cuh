@@ -97,7 +97,13 @@ struct SweepArgs {
 template <int CLS, int MODE>
 __device__ __forceinline__ void
 sweep_block (const SweepArgs& a, const int b, const int t, double* const sm,
-             const dev::NodeConst* const nc_block = nullptr) {
+             const dev::NodeConst* const nc_block = nullptr, double* const rh_solo = nullptr,
+             dev::NodeConst* const nc_solo = nullptr, const BlockDev* const block_solo = nullptr,
+             const int* const tabs_solo = nullptr) {
+  // solo_kernel's extras. rh_solo / nc_solo: also form the block's rhom sums (in the same
+  // level loop as the tracer's sums) and its node constants (one pass over all nodes).
+  // block_solo: the block descriptor, passed as a kernel argument. tabs_solo: the block's
+  // tree tables staged in shared memory by the caller, [kid0 (ni) | kid1 (ni) | lvlptr].
   constexpr bool caas = CLS == CLS_CAAS;
   constexpr bool bfb = CLS == CLS_BFB;
   constexpr bool nonneg = CLS == CLS_NN || CLS == CLS_CNN || bfb;   // one word: row 0
@@ -109,7 +115,7 @@ sweep_block (const SweepArgs& a, const int b, const int t, double* const sm,
   constexpr bool need_bounds = ! nonneg && (MODE != MODE_DOWN || ! consistent_only);
   constexpr bool need_prev = has_prev && MODE != MODE_DOWN && ! bfb;
 
-  const BlockDev B = a.blocks[b];
+  const BlockDev B = block_solo ? *block_solo : a.blocks[b];
   const int nn = B.nl + B.ni;
   const int tid = threadIdx.x, nth = blockDim.x;
   double* const f0 = sm;
@@ -128,40 +134,74 @@ sweep_block (const SweepArgs& a, const int b, const int t, double* const sm,
       const double* base = a.in + (long long) t*4*a.in_ld + B.leaf0;
       p0 = base; p1 = base + a.in_ld; p2 = base + 2*a.in_ld; p3 = base + 3*a.in_ld;
     }
+    if (rh_solo)
+      for (int i = tid; i < B.nl; i += nth) rh_solo[i] = a.in[B.leaf0 + i];   // row 0: rhom
     if (caas && a.tier0) {
       // CAAS::reduce_locally, cedr_caas.cpp:129-201 through calc_Qm_scalars
       // (cedr_caas_inl.hpp:44-57): clip, and the four summands. Each enters the
       // reduction as 0 + value (accumulator start, cedr_caas.cpp:145-151).
       const bool conserve = a.trcr_prob[t] & 1;
-      for (int i = tid; i < B.nl; i += nth) {
-        const double lo = __ldcg(p0 + i), q = __ldcg(p1 + i), hi = __ldcg(p2 + i);
-        const double term = conserve ? __ldcg(p3 + i) : q;
-        const double clip = dev::rmin(hi, dev::rmax(lo, q));
-        f0[i] = 0.0 + lo;
-        f1[i] = 0.0 + clip;
-        f2[i] = 0.0 + hi;
-        f3[i] = 0.0 + term;
+      // (Four elements per thread and pass: all their loads are in flight before the first
+      // is used; a rolled loop pays one memory round trip per element.)
+      for (int i0 = tid; i0 < B.nl; i0 += 4*nth) {
+        double lo[4], q[4], hi[4], term[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k*nth;
+          if (i < B.nl) {
+            lo[k] = __ldcg(p0 + i); q[k] = __ldcg(p1 + i); hi[k] = __ldcg(p2 + i);
+            term[k] = conserve ? __ldcg(p3 + i) : q[k];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k*nth;
+          if (i < B.nl) {
+            const double clip = dev::rmin(hi[k], dev::rmax(lo[k], q[k]));
+            f0[i] = 0.0 + lo[k];
+            f1[i] = 0.0 + clip;
+            f2[i] = 0.0 + hi[k];
+            f3[i] = 0.0 + term[k];
+          }
+        }
       }
     } else {
       // Read-once data; for tiers >= 1 it may have been written by other SMs of the
       // same (fused) launch, so bypass L1.
-      for (int i = tid; i < B.nl; i += nth) {
-        if (need_bounds) { f0[i] = __ldcg(p0 + i); f2[i] = __ldcg(p2 + i); }
-        f1[i] = __ldcg(p1 + i);
-        if (need_prev) f3[i] = __ldcg(p3 + i);
+      for (int i0 = tid; i0 < B.nl; i0 += 4*nth) {
+        double v0[4], v1[4], v2[4], v3[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k*nth;
+          if (i < B.nl) {
+            if (need_bounds) { v0[k] = __ldcg(p0 + i); v2[k] = __ldcg(p2 + i); }
+            v1[k] = __ldcg(p1 + i);
+            if (need_prev) v3[k] = __ldcg(p3 + i);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k*nth;
+          if (i < B.nl) {
+            if (need_bounds) { f0[i] = v0[k]; f2[i] = v2[k]; }
+            f1[i] = v1[k];
+            if (need_prev) f3[i] = v3[k];
+          }
+        }
       }
     }
   }
   __syncthreads();
 
   // Up-sweep inside the block, level by level (kids before parents).
-  const int* const lvlptr = a.lvlptr + B.lvlptr_off;
-  const int* const kid0 = a.kid0 + B.kid_off;
-  const int* const kid1 = a.kid1 + B.kid_off;
+  const int* const lvlptr = tabs_solo ? tabs_solo + 2*B.ni : a.lvlptr + B.lvlptr_off;
+  const int* const kid0 = tabs_solo ? tabs_solo : a.kid0 + B.kid_off;
+  const int* const kid1 = tabs_solo ? tabs_solo + B.ni : a.kid1 + B.kid_off;
   for (int l = 0; l < B.nlev; ++l) {
     const int je = lvlptr[l+1];
     for (int j = lvlptr[l] + tid; j < je; j += nth) {
       const int k0 = kid0[j], k1 = kid1[j], me = B.nl + j;
+      if (rh_solo) rh_solo[me] = rh_solo[k0] + rh_solo[k1];
       if (bfb) {
         f1[me] = (0.0 + f1[k0]) + f1[k1];
       } else if (caas) {
@@ -188,6 +228,21 @@ sweep_block (const SweepArgs& a, const int b, const int t, double* const sm,
     __syncthreads();
   }
   const int root = B.ni ? nn - 1 : 0;
+  if (nc_solo) {
+    // Node constants (what rhom_kernel leaves in global memory for larger problems); the
+    // barriers below order them before the down-sweep.
+    for (int j = tid; j < B.ni; j += nth) {
+      const double rh0 = rh_solo[kid0[j]], rh1 = rh_solo[kid1[j]];
+      dev::NodeConst c;
+      c.w0 = 1/rh0;
+      c.w1 = 1/rh1;
+      c.q0 = 1/c.w0;
+      c.q1 = 1/c.w1;
+      c.rh0 = rh0;
+      c.rh1 = rh1;
+      nc_solo[j] = c;
+    }
+  }
 
   if (MODE == MODE_UP) {
     if (tid == 0) {
@@ -289,13 +344,22 @@ sweep_kernel (const SweepArgs a) {
 // then ni node constants.
 template <int CLS>
 __global__ void __launch_bounds__(256)
-solo_kernel (const SweepArgs a) {
+solo_kernel (const SweepArgs a, const BlockDev B) {
   extern __shared__ double sm[];
   const int t = a.tracers[blockIdx.x];
-  const BlockDev B = a.blocks[0];
   const int nn = B.nl + B.ni, tid = threadIdx.x, nth = blockDim.x;
+  double* const rh = sm + 4*nn;
+  dev::NodeConst* const nc = reinterpret_cast<dev::NodeConst*>(rh + nn + (nn & 1));
+  // The tree tables go to shared memory in one round trip, together with the leaf loads
+  // (from global memory every level of the sweep would wait for its own).
+  int* const tabs = reinterpret_cast<int*>(nc + B.ni);
+  for (int i = tid; i < B.ni; i += nth) {
+    tabs[i] = a.kid0[B.kid_off + i];
+    tabs[B.ni + i] = a.kid1[B.kid_off + i];
+  }
+  for (int i = tid; i <= B.nlev; i += nth) tabs[2*B.ni + i] = a.lvlptr[B.lvlptr_off + i];
   if (CLS == CLS_CAAS) {
-    sweep_block<CLS_CAAS, MODE_TOP>(a, 0, t, sm);
+    sweep_block<CLS_CAAS, MODE_TOP>(a, 0, t, sm, nullptr, nullptr, nullptr, &B, tabs);
     __syncthreads();
     // CAAS::finish_locally (cedr_caas.cpp:211-253) on this tracer's cells.
     const double mode = a.caas_scal[2*t], fac = a.caas_scal[2*t+1];
@@ -311,30 +375,7 @@ solo_kernel (const SweepArgs a) {
     }
     return;
   }
-  double* const rh = sm + 4*nn;
-  dev::NodeConst* const nc = reinterpret_cast<dev::NodeConst*>(rh + nn + (nn & 1));
-  for (int i = tid; i < B.nl; i += nth) rh[i] = a.in[B.leaf0 + i];   // row 0: rhom
-  __syncthreads();
-  const int* const lvlptr = a.lvlptr + B.lvlptr_off;
-  const int* const kid0 = a.kid0 + B.kid_off;
-  const int* const kid1 = a.kid1 + B.kid_off;
-  for (int l = 0; l < B.nlev; ++l) {
-    const int je = lvlptr[l+1];
-    for (int j = lvlptr[l] + tid; j < je; j += nth) {
-      const double rh0 = rh[kid0[j]], rh1 = rh[kid1[j]];
-      rh[B.nl + j] = rh0 + rh1;
-      dev::NodeConst c;
-      c.w0 = 1/rh0;
-      c.w1 = 1/rh1;
-      c.q0 = 1/c.w0;
-      c.q1 = 1/c.w1;
-      c.rh0 = rh0;
-      c.rh1 = rh1;
-      nc[j] = c;
-    }
-    __syncthreads();
-  }
-  sweep_block<CLS, MODE_TOP>(a, 0, t, sm, nc);
+  sweep_block<CLS, MODE_TOP>(a, 0, t, sm, nc, rh, nc, &B, tabs);
 }
 
 // rhom sweep: word 0 of every slot in the reference (cedr_qlt.cpp:356-360),
