@@ -96,6 +96,8 @@ SYMBOLS = [
     ("cedr_b200_debug_phase_clocks", C.c_int, [_H, C.POINTER(C.c_ulonglong)]),
     ("cedr_b200_set_ring", C.c_int, [_H, C.c_int]),
     ("cedr_b200_uses_ring", C.c_int, [_H, _ip]),
+    ("cedr_b200_set_graph", C.c_int, [_H, C.c_int]),
+    ("cedr_b200_uses_graph", C.c_int, [_H, _ip]),
     ("cedr_b200_ring_info", C.c_int, [_H, _ip]),
     ("cedr_b200_ring_trace", C.c_int, [_H, C.POINTER(C.c_ulonglong), C.c_size_t,
                                        C.POINTER(C.c_size_t)]),
@@ -409,6 +411,16 @@ class CDR:
 
     def set_ring(self, on=True):
         _check(self._lib.cedr_b200_set_ring(self._h, int(bool(on))))
+
+    def set_graph(self, mode):
+        """run() as a replayed CUDA graph: -1 auto (multi-rank peer-to-peer runs), 0 never,
+        1 whenever run() is pure stream work (cedr_b200_set_graph)."""
+        _check(self._lib.cedr_b200_set_graph(self._h, int(mode)))
+
+    def uses_graph(self):
+        v = C.c_int(0)
+        _check(self._lib.cedr_b200_uses_graph(self._h, C.byref(v)))
+        return bool(v.value)
 
     def uses_ring(self):
         v = C.c_int(0)

@@ -240,7 +240,20 @@ struct cedr_b200_cdr {
   DevBuf<double> p2p_arena;
   std::vector<void*> p2p_peer;           // peer r's arena in this process's address space
   bool p2p_on = false;
-  unsigned long long p2p_epoch = 0;
+  unsigned long long p2p_epoch = 0;   // host mirror of the device counter (parity of buffers)
+  // run() as a replayed CUDA graph (cedr_b200_set_graph): one per exchange-buffer parity.
+  struct RunGraph { cudaGraphExec_t exec = nullptr; int launches = 0; };
+  RunGraph graph[2];
+  int graph_mode = -1;         // -1: where it pays (multi-rank p2p), 0: never, 1: whenever possible
+  int graph_plain_runs = 0;    // plain run() calls since the last reset (the first ones stay plain)
+  cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's may be stream 0)
+  void graph_reset () {
+    for (RunGraph& g : graph) {
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+      g.exec = nullptr;
+    }
+    graph_plain_runs = 0;
+  }
   int last_launches = 0;
 
   // Optional per-launch timing (cedr_b200_set_profiling).
@@ -249,6 +262,8 @@ struct cedr_b200_cdr {
   std::vector<Timed> timed;
   size_t ntimed = 0;
   ~cedr_b200_cdr () {
+    graph_reset();
+    if (cap_stream) cudaStreamDestroy(cap_stream);
     for (auto& t : timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     for (size_t r = 0; r < p2p_peer.size(); ++r)
       if (p2p_peer[r] && static_cast<int>(r) != rank) cudaIpcCloseMemHandle(p2p_peer[r]);
@@ -1167,6 +1182,10 @@ void exchange_unpack (cedr_b200_cdr& c, bool with_rhom) {
   ++c.last_launches;
 }
 
+// Word of the arena's 64-word header that counts this rank's exchanges (the flags written by
+// the peers are words 0..nranks-1, nranks <= 16).
+constexpr int kP2pEpochWord = 48;
+
 size_t p2p_arena_doubles (const cedr_b200_cdr& c) {
   return 64 + 2*exchange_count(c)*c.nranks;
 }
@@ -1195,8 +1214,8 @@ void exchange_p2p (cedr_b200_cdr& c, bool with_rhom) {
   {
     LaunchTimer lt(c, CEDR_B200_TAG_EXCHANGE, 2);
     p2p_barrier_kernel<<<1, 32, 0, c.stream>>>(
-      pp, reinterpret_cast<unsigned long long*>(c.p2p_arena.p), c.rank, c.nranks, c.p2p_epoch,
-      c.d_status.p,
+      pp, reinterpret_cast<unsigned long long*>(c.p2p_arena.p), c.rank, c.nranks,
+      reinterpret_cast<unsigned long long*>(c.p2p_arena.p) + kP2pEpochWord, c.d_status.p,
       static_cast<unsigned long long>(env_int("CEDR_B200_P2P_TIMEOUT_MS", 30000))*1000000ull);
     CUDA_CHECK(cudaGetLastError());
     ++c.last_launches;
@@ -1517,6 +1536,56 @@ void run_any (cedr_b200_cdr& c, int phase) {
     CUDA_CHECK(cudaGetLastError());
     ++c.last_launches;
   }
+}
+
+// run() as a CUDA graph: the launches of run_any are captured once per exchange-buffer
+// parity and replayed, which takes the per-launch host cost and the gaps between the dozen
+// small kernels of a multi-rank run() off the critical path (at 8 GPUs they were ~10 % of the
+// step). Only for runs that are pure stream work: no profiling events, no host callbacks
+// (all-gather hook, UserAllReducer), no cooperative ring kernel.
+bool graph_eligible (const cedr_b200_cdr& c) {
+  if (c.graph_mode == 0 || std::getenv("CEDR_B200_NO_GRAPH")) return false;
+  if (c.profiling || c.repl || c.is_bfb || c.ring_ok || solo_ok(c)) return false;
+  if (c.is_caas && c.caas_sum_mode != CEDR_B200_CAAS_SUM_TREE) return false;
+  if (c.nranks > 1 && ! c.p2p_on) return false;
+  return c.graph_mode == 1 || c.nranks > 1;
+}
+
+void run_graphed (cedr_b200_cdr& c) {
+  if ( ! graph_eligible(c)) { run_any(c, -1); return; }
+  // The first run stays plain: it sets kernel attributes, which is not stream work.
+  if (c.graph_plain_runs < 1) { ++c.graph_plain_runs; run_any(c, -1); return; }
+  const int parity = c.nranks > 1 ? static_cast<int>((c.p2p_epoch + 1) & 1) : 0;
+  cedr_b200_cdr::RunGraph& g = c.graph[parity];
+  if ( ! g.exec) {
+    // Captured on a stream of our own (the caller's may be the legacy default stream,
+    // which cannot capture) and replayed on the caller's.
+    if ( ! c.cap_stream)
+      CUDA_CHECK(cudaStreamCreateWithFlags(&c.cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    const cudaStream_t user = c.stream;
+    CUDA_CHECK(cudaStreamBeginCapture(c.cap_stream, cudaStreamCaptureModeThreadLocal));
+    c.stream = c.cap_stream;
+    try {
+      run_any(c, -1);      // advances the host epoch mirror itself
+    } catch (...) {
+      c.stream = user;
+      cudaStreamEndCapture(c.cap_stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    c.stream = user;
+    CUDA_CHECK(cudaStreamEndCapture(c.cap_stream, &graph));
+    const cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CUDA_CHECK(e);
+    g.launches = c.last_launches;
+  } else if (c.nranks > 1) {
+    ++c.p2p_epoch;
+    c.xrecv = c.p2p_arena.p + 64 + parity*exchange_count(c)*c.nranks;
+  }
+  CUDA_CHECK(cudaGraphLaunch(g.exec, c.stream));
+  c.last_launches = g.launches;
 }
 
 void get_buffers_sizes (cedr_b200_cdr& c, size_t& b1, size_t& b2) {
@@ -2050,7 +2119,7 @@ int cedr_b200_run (cedr_b200_cdr* c) {
     cedr_b200_throw_if(! c->finished, "finish_setup must be called before run.");
     c->last_launches = 0;
     c->ntimed = 0;
-    run_any(*c, -1);
+    run_graphed(*c);
   });
 }
 
@@ -2075,6 +2144,7 @@ int cedr_b200_set_exchange_buffers (cedr_b200_cdr* c, double* send, double* recv
   return guarded([&] {
     c->xsend = send;
     c->xrecv = recv;
+    c->graph_reset();
   });
 }
 
@@ -2234,6 +2304,7 @@ int cedr_b200_bind_arrays (cedr_b200_cdr* c, int64_t lda, const double* qm_min, 
       c->d_ident.upload(id);
     }
     c->bound.on = true;
+    c->graph_reset();
     c->bound.lda = lda;
     c->bound.qm_min = qm_min;
     c->bound.qm = qm;
@@ -2474,7 +2545,20 @@ int cedr_b200_p2p_enable (cedr_b200_cdr* c, int on) {
         cedr_b200_throw_if(r >= static_cast<int>(c->p2p_peer.size()) || ! c->p2p_peer[r],
                            "peer " << r << " was not set (cedr_b200_p2p_set_peer)");
     c->p2p_on = on != 0;
+    c->graph_reset();
   });
+}
+
+int cedr_b200_set_graph (cedr_b200_cdr* c, int mode) {
+  return guarded([&] {
+    cedr_b200_throw_if(mode < -1 || mode > 1, "graph mode must be -1 (auto), 0 or 1");
+    c->graph_mode = mode;
+    c->graph_reset();
+  });
+}
+
+int cedr_b200_uses_graph (const cedr_b200_cdr* c, int* on) {
+  return guarded([&] { *on = c->graph[0].exec || c->graph[1].exec; });
 }
 
 int cedr_b200_last_run_launches (const cedr_b200_cdr* c, int* n) {

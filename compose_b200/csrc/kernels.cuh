@@ -503,11 +503,16 @@ pack_p2p_kernel (const BlockDev* blocks, const int nown, const int nown_max, con
 // peer's flag array, then wait until every rank has delivered to this one. One warp; lane
 // r talks to rank r. The ranks are different devices, each running its own stream, so the
 // wait cannot starve the writer (unlike two spinning kernels on ONE device).
+// The epoch is counted on the device (*epoch_ctr, one more per barrier) so that a captured
+// CUDA graph of run() can be replayed: the host only has to know its parity.
 __global__ void p2p_barrier_kernel (const PeerPtrs peers, unsigned long long* my_flags,
                                     const int me, const int nranks,
-                                    const unsigned long long epoch, int* status,
+                                    unsigned long long* epoch_ctr, int* status,
                                     const unsigned long long timeout_ns) {
   const int r = threadIdx.x;
+  const unsigned long long epoch = *epoch_ctr + 1;
+  __syncwarp();
+  if (r == 0) *epoch_ctr = epoch;
   __threadfence_system();
   if (r < nranks) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(peers.flags[r] + me), "l"(epoch)

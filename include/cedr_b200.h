@@ -304,6 +304,17 @@ int cedr_b200_transport1d_cycle(cedr_b200_cdr* cdr, int nsteps, const double* y0
 
 /* ---- introspection for tests / benches --------------------------------- */
 
+/* run() as a replayed CUDA graph: its launches are captured once (per exchange-buffer parity)
+ * and replayed, so a run() of a dozen small kernels costs one launch on the host and no
+ * gaps between kernels on the device. mode -1 (default): where it pays, i.e. multi-rank
+ * runs over the peer-to-peer exchange; 0: never; 1: whenever run() is pure stream work (no
+ * profiling, no all-gather hook or UserAllReducer, not the ring kernel, not the one-launch
+ * tiny-problem path). The first run() after setup or after a change of bindings stays
+ * plain. Results are identical either way. (No reference counterpart: the reference's
+ * run() is host code, cedr_qlt.cpp:618-640.) */
+int cedr_b200_set_graph (cedr_b200_cdr* c, int mode);
+int cedr_b200_uses_graph (const cedr_b200_cdr* c, int* on);
+
 /* Number of kernels launched by the last run() on this CDR. */
 int cedr_b200_last_run_launches(const cedr_b200_cdr* cdr, int* n);
 /* Tier-0 kernel selection. Blocks shaped like a recursive bisection with 513..1024

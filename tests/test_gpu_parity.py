@@ -1000,6 +1000,60 @@ def test_caas_user_reducer_backed_by_bfb_tree_allreducer(oracle):
     assert np.array_equal(got, got2)
 
 
+@pytest.mark.parametrize("kind", ["qlt", "caas"])
+@pytest.mark.parametrize("bound", [False, True])
+def test_run_replayed_as_cuda_graph_bitwise(oracle, kind, bound):
+    """cedr_b200_set_graph(1): run() is captured once and replayed. Every replay must read
+    the inputs of ITS step (they change between runs) and give the oracle's bits; the launch
+    count reported stays that of the plain run."""
+    import torch
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    ncells, nt = 5400, 12
+    pts = [7, 3]*(nt//2)
+    tree = oracle.bisection_tree(ncells)
+    c = cb.QLT(ncells) if kind == "qlt" else cb.CAAS(ncells)
+    c.set_graph(1)
+    for p in pts:
+        c.declare_tracer(p)
+    c.end_tracer_declarations()
+    c.finish_setup()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    if bound:
+        arrs = [torch.empty((nt, ncells), dtype=torch.float64, device="cuda") for _ in range(5)]
+        lo_d, q_d, hi_d, prev_d, out_d = arrs
+        if kind == "qlt":
+            c.bind_arrays(q_d, lo_d, hi_d, prev_d, out=out_d)
+        else:
+            c.bind_arrays(q_d, lo_d, hi_d, prev_d)
+    launches = None
+    for step in range(5):
+        rhom, lo, q, hi, prev = W.headline(ncells, nt, 40 + step)
+        ref = (oracle.qlt(tree, pts, rhom, lo, q, hi, prev) if kind == "qlt"
+               else oracle.caas(ncells, pts, lo, q, hi, prev, tree=tree))
+        c.set_rhom(dev(rhom))
+        if bound:
+            for d, h in zip((lo_d, q_d, hi_d, prev_d), (lo, q, hi, prev)):
+                d.copy_(dev(h))
+        else:
+            c.set_Qm(dev(q), dev(lo), dev(hi), dev(prev))
+        c.run()
+        c.synchronize()
+        if bound:
+            got = (out_d if kind == "qlt" else q_d).cpu().numpy()
+        else:
+            got = c.get_Qm().cpu().numpy()
+        assert np.array_equal(got, ref), step
+        assert c.uses_graph() == (step >= 1)
+        if launches is None:
+            launches = c.last_run_launches()
+        assert c.last_run_launches() == launches
+    c.set_graph(0)
+    assert not c.uses_graph()
+    c.run()
+    c.synchronize()
+
+
 # ---------------------------------------------------------------- zero-copy binding (8f-1)
 
 @pytest.mark.parametrize("ncells", [111, 1000, 5400])

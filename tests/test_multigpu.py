@@ -80,13 +80,16 @@ def _worker(rank, world, port, ncells, nt, p2p, q, side_stream=False, pseudorand
             d = [dev(x) for x in (rhom, qq, lo, hi, prev)]
             torch.cuda.synchronize()
             c.set_rhom(d[0])
-            for rep in range(3):
+            for rep in range(6):
                 c.set_Qm(d[1], d[2], d[3], d[4])
                 c.run()
                 out = c.get_Qm()
                 c.synchronize()
                 got = out.cpu().numpy()
                 ok = ok and np.array_equal(got, ref[:, sl])
+            # Peer-to-peer runs replay a captured graph per buffer parity from the second
+            # run() on (cedr_b200_set_graph, auto mode); the others stay plain launches.
+            ok = ok and c.uses_graph() == (p2p and not pseudorandom)
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
