@@ -461,7 +461,7 @@ class CDR:
         tags, tiers, n = (C.c_int*cap)(), (C.c_int*cap)(), C.c_int(0)
         _check(self._lib.cedr_b200_get_launch_times(self._h, cap, ms, tags, tiers,
                                                     C.byref(n)))
-        names = ["rhom", "up", "top", "down", "caas_adjust", "exchange", "fused"]
+        names = ["rhom", "up", "top", "down", "caas_adjust", "exchange", "fused", "mid"]
         return [(names[tags[i]], tiers[i], ms[i]) for i in range(n.value)]
 
     def last_run_launches(self):

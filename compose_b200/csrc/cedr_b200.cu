@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "fast_kernels.cuh"
 #include "ring_kernels.cuh"
+#include "transposed_kernels.cuh"
 #include "cedr_b200_local.hpp"
 #include "tree_plan.h"
 
@@ -189,6 +190,7 @@ struct cedr_b200_cdr {
   bool fast_ok = false;       // plan + buffers allow the fast tier-0 kernels
   DevBuf<unsigned long long> d_phase_clk;   // debug (CEDR_B200_PHASE_CLOCKS builds)
   DevBuf<double> d_n7;        // depth-7 sums per own block x tracer (fast path)
+  DevBuf<double> d_x7;        // depth-7 masses per own block x tracer (transposed_kernels.cuh)
   // Expanded tier above the fast blocks (FastArgs::split): its leaves are the 2^split
   // depth-`split` nodes of every tier-0 block; one block, swept by the generic kernels.
   int split = 0;
@@ -524,9 +526,9 @@ fast::FastArgs fast_args (cedr_b200_cdr& c, int cls) {
   return a;
 }
 
-template <typename K>
+template <typename K, typename... Extra>
 void launch_fast (cedr_b200_cdr& c, K kernel, const fast::FastArgs& a, size_t smem, int tag,
-                  int threads = fast::kThreads) {
+                  int threads = fast::kThreads, Extra... extra) {
   if (a.ntr == 0) return;
   // Raise (never lower) the kernel's dynamic shared memory limit, once per size.
   static std::map<std::pair<int, const void*>, size_t> configured;
@@ -540,7 +542,7 @@ void launch_fast (cedr_b200_cdr& c, K kernel, const fast::FastArgs& a, size_t sm
   const long long grid = static_cast<long long>(a.nblocks)*((a.ntr + a.group - 1)/a.group);
   cedr_b200_throw_if(grid > 0x7fffffffLL, "grid too large");
   LaunchTimer lt(c, tag, 0);
-  kernel<<<static_cast<unsigned>(grid), threads, smem, c.stream>>>(a);
+  kernel<<<static_cast<unsigned>(grid), threads, smem, c.stream>>>(a, extra...);
   CUDA_CHECK(cudaGetLastError());
   ++c.last_launches;
 }
@@ -560,6 +562,43 @@ void launch_fast_up (cedr_b200_cdr& c, int cls) {
   }
 }
 
+// The transposed down-sweep (transposed_kernels.cuh) takes the three-field classes when the
+// block tops come from the tier above (split 2 or 3) and a class has enough tracers to fill
+// the lanes of a warp.
+bool transposed_down_ok (const cedr_b200_cdr& c, const fast::FastArgs& a) {
+  return env_int("CEDR_B200_TRANSPOSED", 1) && (a.split == 2 || a.split == 3) &&
+    a.ntr >= env_int("CEDR_B200_TRANSPOSED_MIN", 16) && c.d_x7.p;
+}
+
+template <int CLS, bool PREFER>
+void launch_mid_cls (cedr_b200_cdr& c, const fast::FastArgs& a, const fast::TArgs& ta) {
+  const unsigned ngroups = static_cast<unsigned>((a.ntr + fast::kTLanes - 1)/fast::kTLanes);
+  cedr_b200_throw_if(ngroups > 65535u, "grid too large");
+  LaunchTimer lt(c, CEDR_B200_TAG_MID, 0);
+  fast::midT_kernel<CLS, PREFER><<<dim3(4u*a.nblocks, ngroups), 128, 0, c.stream>>>(a, ta);
+  CUDA_CHECK(cudaGetLastError());
+  ++c.last_launches;
+}
+
+void launch_transposed_down (cedr_b200_cdr& c, int cls, const fast::FastArgs& a) {
+  if (a.ntr == 0) return;
+  fast::TArgs ta;
+  ta.x7 = c.d_x7.p;
+  const bool prefer = a.prefer_mass_con != 0;
+  const size_t smem = fast::down3_smem_bytes(a.sbuf);
+  if (cls == CLS_ST) {
+    if (prefer) launch_mid_cls<CLS_ST, true>(c, a, ta);
+    else launch_mid_cls<CLS_ST, false>(c, a, ta);
+    launch_fast(c, fast::down3_kernel<CLS_ST>, a, smem, CEDR_B200_TAG_DOWN,
+                fast::kLeafThreads, ta);
+  } else {
+    if (prefer) launch_mid_cls<CLS_CST, true>(c, a, ta);
+    else launch_mid_cls<CLS_CST, false>(c, a, ta);
+    launch_fast(c, fast::down3_kernel<CLS_CST>, a, smem, CEDR_B200_TAG_DOWN,
+                fast::kLeafThreads, ta);
+  }
+}
+
 void launch_fast_down (cedr_b200_cdr& c, int cls) {
   const fast::FastArgs a = fast_args(c, cls);
   if ( ! three_field_class(cls)) {
@@ -574,6 +613,10 @@ void launch_fast_down (cedr_b200_cdr& c, int cls) {
     case CLS_CNN: launch_fast(c, fast::down1_kernel<CLS_CNN>, a, smem1, CEDR_B200_TAG_DOWN,
                               fast::kDown2Threads); break;
     }
+    return;
+  }
+  if (transposed_down_ok(c, a)) {
+    launch_transposed_down(c, cls, a);
     return;
   }
   size_t smem = fast::down2_smem_bytes(a.sbuf);
@@ -1707,9 +1750,12 @@ void finish_setup (cedr_b200_cdr& c) {
     c.d_fwq.alloc(std::max(1, c.plan.ninternal));
     c.d_frh.alloc(std::max(1, c.plan.ninternal));
     c.d_frq.alloc(std::max(1, c.plan.ninternal));
-    if ( ! c.is_caas)
+    if ( ! c.is_caas) {
       c.d_n7.alloc(static_cast<size_t>(384)*std::max<size_t>(1, c.own_blocks.size())*
                    std::max(1, nt));
+      c.d_x7.alloc(static_cast<size_t>(128)*std::max<size_t>(1, c.own_blocks.size())*
+                   std::max(1, nt));
+    }
   }
   c.d_qglob.alloc(2*static_cast<size_t>(nt));
   c.d_caas_scal.alloc(2*static_cast<size_t>(nt));

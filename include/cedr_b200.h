@@ -349,7 +349,7 @@ int cedr_b200_ring_trace(cedr_b200_cdr* cdr, unsigned long long* host, size_t ca
 enum {
   CEDR_B200_TAG_RHOM = 0, CEDR_B200_TAG_UP = 1, CEDR_B200_TAG_TOP = 2,
   CEDR_B200_TAG_DOWN = 3, CEDR_B200_TAG_CAAS_ADJUST = 4, CEDR_B200_TAG_EXCHANGE = 5,
-  CEDR_B200_TAG_FUSED = 6
+  CEDR_B200_TAG_FUSED = 6, CEDR_B200_TAG_MID = 7
 };
 int cedr_b200_set_profiling(cedr_b200_cdr* cdr, int on);
 int cedr_b200_get_launch_times(cedr_b200_cdr* cdr, int cap, float* ms_host,
