@@ -567,7 +567,7 @@ void launch_fast_up (cedr_b200_cdr& c, int cls) {
 // the lanes of a warp.
 bool transposed_down_ok (const cedr_b200_cdr& c, const fast::FastArgs& a) {
   return env_int("CEDR_B200_TRANSPOSED", 1) && (a.split == 2 || a.split == 3) &&
-    a.ntr >= env_int("CEDR_B200_TRANSPOSED_MIN", 16) && c.d_x7.p;
+    a.ntr >= env_int("CEDR_B200_TRANSPOSED_MIN", 4) && c.d_x7.p;
 }
 
 template <int CLS, bool PREFER>

@@ -50,8 +50,11 @@ __device__ __forceinline__ void cp_async_wait_all () {
 }
 
 // ------------------------------------------------------------------------ MID
+#ifndef CEDR_MIDT_MINB
+# define CEDR_MIDT_MINB 4
+#endif
 template <int CLS, bool PREFER>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, CEDR_MIDT_MINB)
 midT_kernel (const FastArgs a, const TArgs ta) {
   static_assert(CLS == CLS_ST || CLS == CLS_CST, "transposed down-sweep: st / cst only");
   __shared__ double tile[kTLanes*kTPitch];
@@ -176,8 +179,11 @@ inline size_t down3_smem_bytes (const int sbuf) {
   return sizeof(double)*(6*static_cast<size_t>(sbuf) + 2*128 + kD9) + 16;
 }
 
+#ifndef CEDR_DOWN3_MINB
+# define CEDR_DOWN3_MINB 4
+#endif
 template <int CLS>
-__global__ void __launch_bounds__(kLeafThreads, 4)
+__global__ void __launch_bounds__(kLeafThreads, CEDR_DOWN3_MINB)
 down3_kernel (const FastArgs a, const TArgs ta) {
   static_assert(CLS == CLS_ST || CLS == CLS_CST, "fast down-sweep: st / cst only");
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -228,7 +234,13 @@ down3_kernel (const FastArgs a, const TArgs ta) {
                       (e.w >> 15) != 0};
   const unsigned* const pent = a.pent + B.fpent_off;
   const int ps = pent[warp], pe = pent[warp + 1];
+#ifdef CEDR_DOWN3_CLDG
+# define c7 wq[127 + node]
+# define c8a wq[255 + 2*node]
+# define c8b wq[256 + 2*node]
+#else
   const dev::NodeWQ c7 = wq[127 + node], c8a = wq[255 + 2*node], c8b = wq[256 + 2*node];
+#endif
 
   auto issue = [&] (const int i) {
     const int t = a.tracers[g0 + i];
@@ -328,6 +340,9 @@ down3_kernel (const FastArgs a, const TArgs ta) {
     }
   }
   if (tid == 0) tma_store_wait_read();
+#undef c7
+#undef c8a
+#undef c8b
 }
 
 } // namespace fast

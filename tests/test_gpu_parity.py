@@ -207,13 +207,20 @@ def test_errors_mirror_reference():
 
 @pytest.mark.parametrize("ncells", [5400, 8*513, 8*768, 8192, 2*1023, 3*700 + 1])
 @pytest.mark.parametrize("prefer", [False, True])
-@pytest.mark.parametrize("ring", [False, True])
-def test_fast_path_blocks_bitwise(oracle, ncells, prefer, ring):
+@pytest.mark.parametrize("ring", [False, True, "down2"])
+def test_fast_path_blocks_bitwise(oracle, ncells, prefer, ring, monkeypatch):
     """Tier-0 blocks of 513..1024 leaves run the fast kernels (TMA + register
-    micro-subtrees) for the st/cst classes -- as separate launches (default) or as the
-    persistent ring kernel -- with the same bits as the oracle, for every block size class
-    (few pairs .. all pairs)."""
+    micro-subtrees) for the st/cst classes -- as separate launches (default: the down-sweep
+    as midT_kernel + down3_kernel; "down2": the one-kernel down-sweep with a top warp) or as
+    the persistent ring kernel -- with the same bits as the oracle, for every block size
+    class (few pairs .. all pairs)."""
     from gpu_util import run_qlt_gpu
+    # The randomized set has only a handful of tracers per class: below the default
+    # threshold of the split down-sweep.
+    monkeypatch.setenv("CEDR_B200_TRANSPOSED_MIN", "1")
+    if ring == "down2":
+        monkeypatch.setenv("CEDR_B200_TRANSPOSED", "0")
+        ring = False
     ts, v = R.generate(ncells, seed=3*ncells + prefer)
     pts = [t.problem_type for t in ts]
     tree = oracle.bisection_tree(ncells)
