@@ -232,6 +232,10 @@ struct cedr_b200_cdr {
   DevBuf<double> d_qglob, d_caas_scal;
 
   cudaStream_t stream = 0;
+  // run_qlt computes the node constants (rhom sweeps) beside the up-sweep, which does not
+  // read them: a stream of our own, forked from and joined to `stream` by events.
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cedr_b200_allgather_fn allgather = nullptr;
   void* allgather_ctx = nullptr;
   DevBuf<double> xsend_own, xrecv_own;   // exchange message / gathered messages
@@ -266,6 +270,9 @@ struct cedr_b200_cdr {
   ~cedr_b200_cdr () {
     graph_reset();
     if (cap_stream) cudaStreamDestroy(cap_stream);
+    if (side_stream) cudaStreamDestroy(side_stream);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     for (auto& t : timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     for (size_t r = 0; r < p2p_peer.size(); ++r)
       if (p2p_peer[r] && static_cast<int>(r) != rank) cudaIpcCloseMemHandle(p2p_peer[r]);
@@ -1345,9 +1352,34 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
   auto local_split = [&] (int cls) {
     return c.split && ! c.x_tier && c.fast_ok && three_field_class(cls);
   };
-  if (phase <= 0) {
+  // One rank, every class on the fast kernels: the rhom sweeps run on the side stream
+  // while the first class's up-sweep runs on the CDR's (joined before its tier above).
+  bool rhom_aside = ! multi && phase < 0 && ! c.profiling && ! c.ring_ok &&
+    ! std::getenv("CEDR_B200_NO_SIDE_STREAM");
+  for (int cls = 0; cls < CLS_CAAS && rhom_aside; ++cls)
+    if ( ! c.cls_tracers[cls].empty() && ! via_x(cls)) rhom_aside = false;
+  if (rhom_aside) {
+    if ( ! c.side_stream) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&c.side_stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
+    CUDA_CHECK(cudaStreamWaitEvent(c.side_stream, c.ev_fork, 0));
+    const cudaStream_t main_stream = c.stream;
+    c.stream = c.side_stream;
+    try {
+      run_rhom(c, 0, ntiers);
+      run_rhom_x(c);
+    } catch (...) { c.stream = main_stream; throw; }
+    c.stream = main_stream;
+    CUDA_CHECK(cudaEventRecord(c.ev_join, c.side_stream));
+  }
+  if (phase <= 0 && ! rhom_aside) {
     run_rhom(c, 0, multi ? 1 : ntiers);
     if ( ! multi) run_rhom_x(c);
+  }
+  if (phase <= 0) {
     if (c.ring_ok) ring_gather(c);
     if (multi) {
       for (int cls = 0; cls < CLS_CAAS; ++cls)
@@ -1369,6 +1401,10 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
       if (c.ring_ok && ring_class(cls) && ! c.bound.on) { launch_ring(c, cls); continue; }
       if (via_x(cls)) {
         if ( ! multi) launch_up(c, cls, 0);
+        if (rhom_aside) {
+          CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
+          rhom_aside = false;
+        }
         launch_top_x(c, cls);
         launch_down(c, cls, 0);
         continue;
