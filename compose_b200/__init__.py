@@ -96,6 +96,8 @@ SYMBOLS = [
     ("cedr_b200_debug_phase_clocks", C.c_int, [_H, C.POINTER(C.c_ulonglong)]),
     ("cedr_b200_set_ring", C.c_int, [_H, C.c_int]),
     ("cedr_b200_uses_ring", C.c_int, [_H, _ip]),
+    ("cedr_b200_set_cluster_caas", C.c_int, [_H, C.c_int]),
+    ("cedr_b200_uses_cluster_caas", C.c_int, [_H, _ip]),
     ("cedr_b200_set_graph", C.c_int, [_H, C.c_int]),
     ("cedr_b200_uses_graph", C.c_int, [_H, _ip]),
     ("cedr_b200_ring_info", C.c_int, [_H, _ip]),
@@ -425,6 +427,16 @@ class CDR:
     def uses_ring(self):
         v = C.c_int(0)
         _check(self._lib.cedr_b200_uses_ring(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def set_cluster_caas(self, mode):
+        """Opt-in: CAAS::run as one cluster kernel (a tracer on chip, one pass over HBM):
+        1 on where it applies, 0 off (cedr_b200_set_cluster_caas)."""
+        _check(self._lib.cedr_b200_set_cluster_caas(self._h, int(mode)))
+
+    def uses_cluster_caas(self):
+        v = C.c_int(0)
+        _check(self._lib.cedr_b200_uses_cluster_caas(self._h, C.byref(v)))
         return bool(v.value)
 
     def ring_info(self):

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libcedr_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", f) for f in ("cedr_b200.cu", "tree_plan.cpp")]
 HEADERS = [os.path.join(HERE, "csrc", f) for f in
-           ("kernels.cuh", "node_solve.cuh", "fast_kernels.cuh", "ring_kernels.cuh", "transposed_kernels.cuh",
+           ("kernels.cuh", "node_solve.cuh", "fast_kernels.cuh", "ring_kernels.cuh", "transposed_kernels.cuh", "cluster_caas.cuh",
             "tree_plan.h")] + \
           [os.path.join(ROOT, "include", f) for f in
            ("cedr_b200.h", "cedr_b200_device_op.h", "cedr_b200_local.hpp")]

@@ -23,6 +23,7 @@
 #include "fast_kernels.cuh"
 #include "ring_kernels.cuh"
 #include "transposed_kernels.cuh"
+#include "cluster_caas.cuh"
 #include "cedr_b200_local.hpp"
 #include "tree_plan.h"
 
@@ -200,6 +201,12 @@ struct cedr_b200_cdr {
   DevBuf<BlockDev> d_xblock;
   DevBuf<dev::NodeConst> d_xnc;
   DevBuf<double> d_xrhom, d_xrec, d_xsol;
+  // CAAS::run as one cluster kernel (cluster_caas.cuh): a tracer on chip, one pass over HBM.
+  int cluster_mode = 0;       // cedr_b200_set_cluster_caas: 0 off (default: slower today), 1 on
+  bool cluster_ok = false;
+  ccaas::Args cluster_args;
+  int cluster_ng = 0;
+  size_t cluster_smem = 0;
   // Persistent single-read kernel (ring_kernels.cuh), the default run() where it applies.
   bool ring_enabled = false;  // cedr_b200_set_ring (opt-in: slower than the multi-launch path today)
   bool ring_ok = false;
@@ -654,6 +661,120 @@ const void* ring_kernel_ptr (int cls, int np, int sw) {
 #undef CEDR_RK
 }
 
+
+// ---- cluster-resident CAAS (cluster_caas.cuh)
+
+const void* cluster_kernel_ptr (int ng) {
+  switch (ng) {
+  case 1: return reinterpret_cast<const void*>(ccaas::run_kernel<1>);
+  case 2: return reinterpret_cast<const void*>(ccaas::run_kernel<2>);
+  default: return reinterpret_cast<const void*>(ccaas::run_kernel<4>);
+  }
+}
+
+void cluster_launch_config (const cedr_b200_cdr& c, int nclusters, cudaLaunchConfig_t& cfg,
+                            cudaLaunchAttribute* at) {
+  std::memset(&cfg, 0, sizeof(cfg));
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = c.cluster_args.cs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(static_cast<unsigned>(nclusters)*c.cluster_args.cs);
+  cfg.blockDim = dim3(128u*c.cluster_ng);
+  cfg.dynamicSmemBytes = c.cluster_smem;
+  cfg.stream = c.stream;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+}
+
+// Decide whether CAAS::run can be the cluster kernel; called from finish_setup. A CTA takes
+// whole tier-0 blocks (at most 2 per 128-thread group, 4 groups), a cluster at most 16 CTAs,
+// and five row slots of a CTA's slice must fit its shared memory.
+void cluster_setup (cedr_b200_cdr& c) {
+  c.cluster_ok = false;
+  if ( ! c.is_caas || c.is_bfb || ! c.fast_ok || c.nranks > 1) return;
+  if (c.cluster_mode <= 0 && ! env_int("CEDR_B200_CLUSTER_CAAS", 0)) return;
+  if (c.caas_sum_mode != CEDR_B200_CAAS_SUM_TREE) return;
+  if (c.plan.tiers.size() != 2 || c.plan.tiers[1].blocks.size() != 1) return;
+  const int nt = static_cast<int>(c.trcr_prob.size());
+  if (nt == 0) return;
+  const std::vector<Block>& blocks = c.plan.tiers[0].blocks;
+  const int nb = static_cast<int>(blocks.size());
+  for (int b = 0; b + 1 < nb; ++b)
+    if (blocks[b + 1].leaf0 != blocks[b].leaf0 + blocks[b].nl ||
+        c.leaf_lci[blocks[b + 1].leaf0] != c.leaf_lci[blocks[b].leaf0] + blocks[b].nl) return;
+  if (c.leaf_lci[blocks[0].leaf0] != blocks[0].leaf0) return;
+  int dev = 0, smem_max = 0, cluster_launch = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&cluster_launch, cudaDevAttrClusterLaunch, dev));
+  if ( ! cluster_launch) return;
+  const Block& tb = c.plan.tiers[1].blocks[0];
+  const Shape& ts = c.plan.shapes[tb.shape];
+  ccaas::Args& a = c.cluster_args;
+  std::memset(&a, 0, sizeof(a));
+  a.top.nl = ts.nl;
+  a.top.ni = ts.ni;
+  a.top.nlev = ts.nlev;
+  a.top.lvlptr_off = ts.dev_lvlptr_off;
+  a.top.kid_off = ts.dev_kid_off;
+  // As many whole blocks per CTA as its shared memory holds (fewer, fatter CTAs: a cluster
+  // of one needs no exchange at all), up to 2 per 128-thread group x 4 groups.
+  const int max_cs = env_int("CEDR_B200_CLUSTER_SIZE", 16);
+  int bpc = std::min(nb, 4*ccaas::kMaxBlocksPerGroup);
+  for (; bpc >= 1; --bpc) {
+    int slice = 0;
+    for (int b = 0; b < nb; b += bpc) {
+      const int e = std::min(nb, b + bpc) - 1;
+      slice = std::max(slice, blocks[e].leaf0 + blocks[e].nl - blocks[b].leaf0);
+    }
+    a.cap = (slice + 2 + 1) & ~1;
+    c.cluster_ng = bpc >= 3 ? 4 : bpc;     // bpc 1 -> 1 group, 2 -> 2, 3..8 -> 4
+    c.cluster_smem = ccaas::smem_bytes(a, c.cluster_ng);
+    if (c.cluster_smem <= static_cast<size_t>(smem_max)) break;
+  }
+  if (bpc < 1 || (nb + bpc - 1)/bpc > max_cs) return;
+  a.bpc = bpc;
+  a.cs = (nb + bpc - 1)/bpc;
+  a.nblocks = nb;
+  a.ntr = nt;
+  a.need_prev = c.caas_need_conserve;
+  const void* const k = cluster_kernel_ptr(c.cluster_ng);
+  CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(c.cluster_smem)));
+  if (a.cs > 8)
+    CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at[1];
+  cluster_launch_config(c, 1, cfg, at);
+  int maxc = 0;
+  if (cudaOccupancyMaxActiveClusters(&maxc, k, &cfg) != cudaSuccess || maxc < 1) {
+    cudaGetLastError();
+    return;
+  }
+  a.nclusters = std::min(maxc, nt);
+  if (const char* e = std::getenv("CEDR_B200_CLUSTERS")) a.nclusters = std::max(1, std::atoi(e));
+  c.cluster_ok = true;
+}
+
+void launch_cluster_caas (cedr_b200_cdr& c) {
+  ccaas::Args a = c.cluster_args;
+  a.blocks = c.d_blocks[0].p;
+  a.dtab = c.d_dtab.p;
+  a.perm = c.d_perm.p;
+  a.rowaddr = c.d_rowaddr.p;
+  a.trcr_prob = c.d_trcr_prob.p;
+  a.lvlptr = c.d_lvlptr.p;
+  a.kid0 = c.d_kid0.p;
+  a.kid1 = c.d_kid1.p;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at[1];
+  cluster_launch_config(c, a.nclusters, cfg, at);
+  void* args[1] = {&a};
+  LaunchTimer lt(c, CEDR_B200_TAG_FUSED, 0);
+  CUDA_CHECK(cudaLaunchKernelExC(&cfg, cluster_kernel_ptr(c.cluster_ng), args));
+  ++c.last_launches;
+}
 
 // Decide whether run() can be the ring kernel and build its tables; called from
 // finish_setup. One piece per CTA: consecutive depth-S subtrees of the tier-0 blocks.
@@ -1476,6 +1597,7 @@ void run_caas (cedr_b200_cdr& c, int phase) {
   }
   if (c.ring_ok && ! c.bound.on) { launch_ring(c, CLS_CAAS); return; }
   if (solo_ok(c)) { launch_solo(c, CLS_CAAS); return; }
+  if (c.cluster_ok) { launch_cluster_caas(c); return; }
   const int ntiers = static_cast<int>(c.plan.tiers.size());
   const int top = ntiers - 1;
   if (phase <= 0 && multi) {
@@ -1806,6 +1928,7 @@ void finish_setup (cedr_b200_cdr& c) {
     c.xrecv = c.xrecv_own.p;
   }
   ring_setup(c);
+  cluster_setup(c);
   upload_rowaddr(c);
   c.finished = true;
 }
@@ -2562,6 +2685,17 @@ int cedr_b200_set_ring (cedr_b200_cdr* c, int on) {
 
 int cedr_b200_uses_ring (const cedr_b200_cdr* c, int* on) {
   return guarded([&] { *on = c->ring_ok; });
+}
+
+int cedr_b200_set_cluster_caas (cedr_b200_cdr* c, int mode) {
+  return guarded([&] {
+    cedr_b200_throw_if(c->finished, "set_cluster_caas must precede finish_setup");
+    c->cluster_mode = mode;
+  });
+}
+
+int cedr_b200_uses_cluster_caas (const cedr_b200_cdr* c, int* on) {
+  return guarded([&] { *on = c->cluster_ok && ! c->ring_ok && ! solo_ok(*c); });
 }
 
 int cedr_b200_ring_info (const cedr_b200_cdr* c, int* info8) {

@@ -335,6 +335,17 @@ int cedr_b200_uses_fast_path(const cedr_b200_cdr* cdr, int* on);
  * the choice; ring_info returns {grid, sub-root depth, depth-7 nodes per piece, tracers
  * per unit, 100 x UP slots + DOWN slots, L groups, S warps, dynamic smem bytes}. */
 int cedr_b200_set_ring(cedr_b200_cdr* cdr, int on);
+/* Opt-in: CAAS::run (cedr_caas.cpp:258-270: reduce_locally, reduce_globally, finish_locally)
+ * as ONE kernel of thread-block clusters (cluster_caas.cuh): a cluster of up to 16 CTAs
+ * holds a whole tracer in its shared memory, so the rows cross HBM once (4 rows in, 1 out)
+ * where the two-pass kernels read them twice. Applies on one rank with tree-ordered sums
+ * when every tier-0 block has the fast shape, a CTA's slice (at most 8 blocks) fits five
+ * row slots of shared memory and the cluster has at most 16 CTAs (86,400 cells at 675-leaf
+ * blocks). Bit-identical to the two-pass kernels, which stay the default because they are
+ * faster today. mode 1 = on where it applies, 0 = off (before
+ * finish_setup); uses_cluster_caas reports the choice. */
+int cedr_b200_set_cluster_caas(cedr_b200_cdr* cdr, int mode);
+int cedr_b200_uses_cluster_caas(const cedr_b200_cdr* cdr, int* on);
 int cedr_b200_uses_ring(const cedr_b200_cdr* cdr, int* on);
 int cedr_b200_ring_info(const cedr_b200_cdr* cdr, int* info8_host);
 /* Debug: per-unit, per-stage device timestamps of the last ring launch (only recorded when

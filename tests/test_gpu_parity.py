@@ -161,6 +161,39 @@ def test_caas_headline_inputs_bitwise(oracle):
     assert np.all(got >= lo) and np.all(got <= hi)
 
 
+@pytest.mark.parametrize("ncells,nt,conserve", [(5400, 37, True), (8*768, 20, True),
+                                                (3*700 + 1, 9, False), (86400, 12, True)])
+def test_caas_cluster_kernel_bitwise(oracle, ncells, nt, conserve):
+    """Opt-in CAAS::run as ONE kernel of thread-block clusters (cluster_caas.cuh: a tracer
+    held in the shared memory of up to 16 CTAs, block records exchanged through distributed
+    shared memory, rows read once): one launch, the oracle's bits, for a cluster of one CTA
+    (5,400 cells), of two (6,144 cells: 7 + 1 blocks), with and without a Qm_prev row, and
+    the full 16-CTA cluster at 86,400 cells; run twice (the row ring's parity)."""
+    import torch
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    rhom, lo, q, hi, prev = W.headline(ncells, nt, 1)
+    pt = 7 if conserve else 6
+    pts = [pt]*nt
+    ref = oracle.caas(ncells, pts, lo, q, hi, prev, tree=oracle.bisection_tree(ncells))
+    c = cb.CAAS(ncells)
+    c.set_cluster_caas(1)
+    for p in pts:
+        c.declare_tracer(p)
+    c.end_tracer_declarations()
+    c.finish_setup()
+    assert c.uses_cluster_caas()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    c.set_rhom(dev(rhom))
+    for _ in range(2):
+        c.set_Qm(dev(q), dev(lo), dev(hi), dev(prev))
+        c.run()
+        assert c.last_run_launches() == 1
+        got = c.get_Qm().cpu().numpy()
+        c.synchronize()
+        assert np.array_equal(got, ref)
+
+
 @pytest.mark.parametrize("ncells", [1, 2, 21, 111, 256])
 def test_single_block_problems_run_in_one_launch(oracle, ncells, monkeypatch):
     """A tree that is one small block (cedr_test_1d_transport's 111 cells, the randomized

@@ -1,2 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fast_path_blocks or default_path_full_size or replayed_as_cuda_graph or bound_arrays or headline" 2>&1 | tail -3
-for wl in ne30x72x40 ne120x128x40; do for m in 0 1; do echo $wl no_side=$m; if [ $m = 1 ]; then export CEDR_B200_NO_SIDE_STREAM=1; else unset CEDR_B200_NO_SIDE_STREAM; fi; python tools/time_run.py qlt $wl; done; done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
