@@ -377,22 +377,28 @@ def main():
     # ---- roofline of the dominant reconstructor pass (QLT run()): algorithmic bytes
     # (40 B x the updates one run() processes on this GPU) over the CUDA-event duration
     # of the run's launches; traffic = DRAM bytes of the same kernels from the committed
-    # ncu capture (profiles/r02_traffic.json, bytes per update x updates) -- NOT measured in
+    # ncu capture (profiles/r02b_traffic.json, bytes per update x updates) -- NOT measured in
     # this run (ncu cannot run inside a timed bench): "traffic_source" says so.
     peak, peak_src = measured_peaks()
     upd_gpu = updates/world
     ach = BYTES_PER_UPDATE*upd_gpu/(ms_qlt*1e-3)/1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02b_traffic.json")
     bpu = json.load(open(tpath))["bytes_per_update"] if os.path.exists(tpath) else None
     per_kernel = {}
     if kernels:
         # Each kernel against the bytes it must move itself: up reads 4 rows (32 B), down
-        # reads 3 rows and writes 1 (32 B), caas_adjust likewise.
+        # reads 3 rows and writes 1 (32 B), caas_adjust likewise; mid (the block tops of the
+        # down-sweep) reads the depth-7 sums and writes the depth-7 masses: 4 KB per block x
+        # tracer (a block is ncells / 2^k <= 1024 leaves: 675 at ne30 / ne120, 768 at ne256).
+        nblk = 1
+        while ncells/nblk > 1024:
+            nblk *= 2
+        mid_b = 4096.0/(ncells/nblk)
         for kind in ("qlt", "caas"):
             for name, tier, ms in kernels[kind]:
-                if tier == 0 and name in ("up", "down", "caas_adjust", "fused") and ms > 0:
-                    b = 40.0 if name == "fused" else 32.0
+                if tier == 0 and name in ("up", "down", "caas_adjust", "fused", "mid") and ms > 0:
+                    b = 40.0 if name == "fused" else mid_b if name == "mid" else 32.0
                     g = b*upd_gpu/(ms*1e-3)/1e9
                     per_kernel["%s.%s" % (kind, name)] = {
                         "ms": ms, "bytes_per_update": b, "achieved": g, "frac": g/peak}
@@ -400,14 +406,15 @@ def main():
         traffic = bpu["qlt"]["run_total"]*upd_gpu
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach/peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel": "QLT::run(): fast::up_kernel + tier-1 sweep + fast::down2_kernel "
-                          "(dominant: down2_kernel); per GPU; duration = CUDA events around "
+                "kernel": "QLT::run(): fast::up_kernel + tier-1 sweep + fast::midT_kernel + "
+                          "fast::down3_kernel (dominant: down3_kernel); per GPU; duration = "
+                          "CUDA events around "
                           "run() on its stream",
                 "algorithmic_bytes_per_update": BYTES_PER_UPDATE,
                 "algorithmic_bytes": BYTES_PER_UPDATE*upd_gpu,
                 "traffic_bytes_per_update": bpu["qlt"]["run_total"] if bpu else None,
                 "traffic_source": ("committed ncu --set full capture of the same kernels "
-                                   "(profiles/r02_traffic.json, profiles/r02_qlt_ne120_ncu.txt), "
+                                   "(profiles/r02b_traffic.json, profiles/r02b_qlt_ne120_ncu.txt), "
                                    "bytes per update x this run's updates; not re-measured here"),
                 "kernels": per_kernel,
                 "kernels_note": "per-kernel frac is against the measured COPY bandwidth (read + "

@@ -1,30 +1,34 @@
-// Transposed down-sweep of the fast-path blocks: LANES ARE TRACERS.
+// The down-sweep of the fast-path blocks as TWO kernels (the default for the st / cst
+// classes when the block tops come from the tier above, FastArgs::split = 2 or 3).
 //
-// down2_kernel (fast_kernels.cuh) spreads one tracer's block over a CTA -- a lane is a tree
-// node -- so every level of the tree costs it a hand-off (named barriers, shuffles, a top
-// warp that runs a tracer ahead), its narrow levels leave lanes idle (23.5 of 32 active),
-// and each thread carries its nodes' constants in registers. Here a warp takes ONE node and
-// 32 tracers: the tree structure, the node constants and every structural branch (leaf or
-// pair?) are warp-uniform, a thread walks its micro-subtree alone with no barrier, shuffle
-// or hand-off, and all lanes are active at every level. The price is a transposition of the
-// cell-fastest rows (cedr_qlt_inl.hpp:21-58), done through shared memory: a CTA stages the
-// <= 32 contiguous leaves of four depth-7 nodes for 32 tracers with coalesced 8-byte
-// cp.async copies (lanes along cells), its threads then read them with lanes along tracers
-// (row pitch 33 doubles, tracer pitch 99: conflict-free), and the solved leaves go back
-// the same way.
+// down2_kernel (fast_kernels.cuh) does a whole block x tracer in one CTA: a top warp solves
+// depths 0..6 one tracer ahead of four leaf warps. That top warp is the kernel's critical
+// resource -- its levels are narrower than a warp (8, 16, 32, 64 nodes: 75 % of its lanes
+// work), every level is a shared-memory round trip, the leaf warps wait for it (13-20 % of
+// their time) and it costs the CTA 32 threads x 128 registers, so only three CTAs fit an SM.
 //
-//   midT_kernel   depths S..6 of a block (S = FastArgs::split, 2 or 3): a thread owns one
-//                 depth-4 node of one tracer (8 depth-7 sums from up_kernel's n7buf as its
-//                 leaves) and solves down to the depth-7 masses; the one or two levels above
-//                 depth 4 are solved redundantly by the 2 / 4 threads below them. Masses go
-//                 to x7[(tracer*nblocks + block)*128 + depth-7 node], 16 bytes per store.
+//   midT_kernel   depths S..6 with LANES = TRACERS: a warp takes one depth-4 node and 32
+//                 tracers, so the tree structure and the node constants are warp-uniform,
+//                 all lanes work at every level and a thread walks its subtree (8 depth-7
+//                 sums from up_kernel's n7buf as leaves) alone: no barrier, shuffle or
+//                 hand-off. The one or two levels above depth 4 are solved redundantly by
+//                 the 2 / 4 threads below them. The depth-7 sums reach the lanes through a
+//                 shared-memory transposition: coalesced 8-byte cp.async copies with lanes
+//                 along nodes, then reads with lanes along tracers (row pitch 33 doubles,
+//                 tracer pitch 99: conflict-free). Masses go to
+//                 x7[(tracer*nblocks + block)*128 + depth-7 node], 16 bytes per store.
 //   down3_kernel  depths 7..9: down2_kernel's four leaf warps (a lane is a depth-7 node, one
-//                 tracer at a time, TMA-staged rows) without its top warp: the depth-7
+//                 tracer at a time, TMA-staged rows) without the top warp: the depth-7
 //                 masses arrive as a fourth staged row. 128 threads and 38 KB of shared
-//                 memory per CTA, so four CTAs fit an SM where down2_kernel fits three, and
-//                 no leaf warp ever waits for a top warp.
+//                 memory per CTA, so four CTAs fit an SM, and no leaf warp waits for a top
+//                 warp.
 //
 // Same node arithmetic (node_solve.cuh), same tree order: bit-identical to down2_kernel.
+// Measured at ne120 x 1280 cst tracers: midT 0.23 + down3 0.95 ms against down2 1.28 ms.
+// (A leaf-level kernel with lanes = tracers was also built -- 32 tracers x the <= 32 leaves
+// of four depth-7 nodes transposed through shared memory, double-buffered: 1.41 ms, half of
+// its instructions and two thirds of its time in the transposition, so the leaf levels keep
+// the lane = node form.)
 #ifndef CEDR_B200_TRANSPOSED_KERNELS_CUH
 #define CEDR_B200_TRANSPOSED_KERNELS_CUH
 
@@ -50,11 +54,8 @@ __device__ __forceinline__ void cp_async_wait_all () {
 }
 
 // ------------------------------------------------------------------------ MID
-#ifndef CEDR_MIDT_MINB
-# define CEDR_MIDT_MINB 4
-#endif
 template <int CLS, bool PREFER>
-__global__ void __launch_bounds__(128, CEDR_MIDT_MINB)
+__global__ void __launch_bounds__(128, 4)
 midT_kernel (const FastArgs a, const TArgs ta) {
   static_assert(CLS == CLS_ST || CLS == CLS_CST, "transposed down-sweep: st / cst only");
   __shared__ double tile[kTLanes*kTPitch];
@@ -179,11 +180,11 @@ inline size_t down3_smem_bytes (const int sbuf) {
   return sizeof(double)*(6*static_cast<size_t>(sbuf) + 2*128 + kD9) + 16;
 }
 
-#ifndef CEDR_DOWN3_MINB
-# define CEDR_DOWN3_MINB 4
-#endif
+// (Measured at ne120 x 1280 tracers, 0.95 ms as is: 5 CTAs/SM at 96-102 registers 1.07-1.23 ms
+// even with the depth-9 sums re-formed instead of kept; node constants fetched at their use
+// 0.98 ms.)
 template <int CLS>
-__global__ void __launch_bounds__(kLeafThreads, CEDR_DOWN3_MINB)
+__global__ void __launch_bounds__(kLeafThreads, 4)
 down3_kernel (const FastArgs a, const TArgs ta) {
   static_assert(CLS == CLS_ST || CLS == CLS_CST, "fast down-sweep: st / cst only");
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -234,13 +235,7 @@ down3_kernel (const FastArgs a, const TArgs ta) {
                       (e.w >> 15) != 0};
   const unsigned* const pent = a.pent + B.fpent_off;
   const int ps = pent[warp], pe = pent[warp + 1];
-#ifdef CEDR_DOWN3_CLDG
-# define c7 wq[127 + node]
-# define c8a wq[255 + 2*node]
-# define c8b wq[256 + 2*node]
-#else
   const dev::NodeWQ c7 = wq[127 + node], c8a = wq[255 + 2*node], c8b = wq[256 + 2*node];
-#endif
 
   auto issue = [&] (const int i) {
     const int t = a.tracers[g0 + i];
@@ -340,9 +335,6 @@ down3_kernel (const FastArgs a, const TArgs ta) {
     }
   }
   if (tid == 0) tma_store_wait_read();
-#undef c7
-#undef c8a
-#undef c8b
 }
 
 } // namespace fast
