@@ -1453,6 +1453,17 @@ void launch_solo (cedr_b200_cdr& c, int cls) {
   }
 }
 
+// The side stream picks up after everything queued on the CDR's stream so far.
+void side_stream_fork (cedr_b200_cdr& c) {
+  if ( ! c.side_stream) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c.side_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+  }
+  CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
+  CUDA_CHECK(cudaStreamWaitEvent(c.side_stream, c.ev_fork, 0));
+}
+
 // QLT::run, cedr_qlt.cpp:618-640. phase < 0: everything (one rank: no exchange);
 // phase 0: up to the exchange message; phase 1: from the gathered messages on.
 void run_qlt (cedr_b200_cdr& c, int phase) {
@@ -1480,13 +1491,7 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
   for (int cls = 0; cls < CLS_CAAS && rhom_aside; ++cls)
     if ( ! c.cls_tracers[cls].empty() && ! via_x(cls)) rhom_aside = false;
   if (rhom_aside) {
-    if ( ! c.side_stream) {
-      CUDA_CHECK(cudaStreamCreateWithFlags(&c.side_stream, cudaStreamNonBlocking));
-      CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
-      CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
-    }
-    CUDA_CHECK(cudaEventRecord(c.ev_fork, c.stream));
-    CUDA_CHECK(cudaStreamWaitEvent(c.side_stream, c.ev_fork, 0));
+    side_stream_fork(c);
     const cudaStream_t main_stream = c.stream;
     c.stream = c.side_stream;
     try {
@@ -1496,7 +1501,19 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
     c.stream = main_stream;
     CUDA_CHECK(cudaEventRecord(c.ev_join, c.side_stream));
   }
-  if (phase <= 0 && ! rhom_aside) {
+  // Several ranks: the tier-0 rhom sweep (the block roots' rhom goes into the exchange
+  // message) runs beside the ranks' own up-sweeps in the same way.
+  bool rhom_aside_multi = multi && phase <= 0 && ! c.profiling && c.fast_ok &&
+    ! std::getenv("CEDR_B200_NO_SIDE_STREAM");
+  if (rhom_aside_multi) {
+    side_stream_fork(c);
+    const cudaStream_t main_stream = c.stream;
+    c.stream = c.side_stream;
+    try { run_rhom(c, 0, 1); } catch (...) { c.stream = main_stream; throw; }
+    c.stream = main_stream;
+    CUDA_CHECK(cudaEventRecord(c.ev_join, c.side_stream));
+  }
+  if (phase <= 0 && ! rhom_aside && ! rhom_aside_multi) {
     run_rhom(c, 0, multi ? 1 : ntiers);
     if ( ! multi) run_rhom_x(c);
   }
@@ -1508,6 +1525,7 @@ void run_qlt (cedr_b200_cdr& c, int phase) {
           launch_up(c, cls, 0);
           if (local_split(cls)) launch_mid(c, cls, false);
         }
+      if (rhom_aside_multi) CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
       if (c.p2p_on && phase < 0) exchange_p2p(c, true); else exchange_pack(c, true);
     }
   }
