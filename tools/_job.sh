@@ -1,11 +1,12 @@
-set -x
-CEDR_B200_TRANSPOSED_MIN=1 timeout 600 python -m pytest tests/test_multigpu.py -m gpu -q -rA 2>&1 | tail -9 > gpurun_out/r02b_pytest_multigpu_2gpu.log
-tail -8 gpurun_out/r02b_pytest_multigpu_2gpu.log
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "partition or rank_map or run_replayed" 2>&1 | tail -3
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r02b_bench_ne120_n2_noe2e.json 2> gpurun_out/r02b_bench_n2.err
+run () {
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/tmp_n8.json 2> gpurun_out/tmp_n8.err
 python - <<'PY'
 import json
-for l in open("gpurun_out/r02b_bench_ne120_n2_noe2e.json"):
+for l in open("gpurun_out/tmp_n8.json"):
     if l.startswith("{"):
-        d=json.loads(l); print(d["ms_per_step"], d["qlt"]["ms_per_run"], d["caas"]["ms_per_run"], d["output_digest"])
+        d=json.loads(l); print(d["n_gpus"], round(d["ms_per_step"],4), round(d["qlt"]["ms_per_run"],4), round(d["caas"]["ms_per_run"],4), d["output_digest"]["qlt"])
 PY
+}
+echo default; run
+echo no_side; CEDR_B200_NO_SIDE_STREAM=1 run
+echo down2; CEDR_B200_TRANSPOSED=0 run
