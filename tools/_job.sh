@@ -1,12 +1,5 @@
-run () {
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/tmp_n8.json 2> gpurun_out/tmp_n8.err
-python - <<'PY'
-import json
-for l in open("gpurun_out/tmp_n8.json"):
-    if l.startswith("{"):
-        d=json.loads(l); print(d["n_gpus"], round(d["ms_per_step"],4), round(d["qlt"]["ms_per_run"],4), round(d["caas"]["ms_per_run"],4), d["output_digest"]["qlt"])
-PY
-}
-echo default; run
-echo no_side; CEDR_B200_NO_SIDE_STREAM=1 run
-echo down2; CEDR_B200_TRANSPOSED=0 run
+CEDR_B200_TRANSPOSED_MIN=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fast_path_blocks_bitwise or default_path_full_size or subtree_partition or replayed_as_cuda_graph" 2>&1 | tail -3
+python tools/kernel_times.py qlt ne120x128x40 1280 | grep "mid\|down\|sum"
+for gy in 4 10 20 40; do echo gy=$gy; CEDR_B200_MID_GY=$gy python tools/kernel_times.py qlt ne120x128x40 1280 | grep "mid"; done
+python tools/kernel_times.py qlt ne120x128x40 5120 | grep "mid\|sum"
+python tools/time_run.py qlt ne30x72x40
