@@ -111,6 +111,10 @@ SYMBOLS = [
     ("cedr_b200_plan_probe", C.c_int, [C.c_int, C.c_int, C.c_int, _ip, _lp, C.c_int, _lp,
                                        _ip, _ip, _ip, _ip, _lp]),
     ("cedr_b200_make_1d_tree", C.c_int, [C.c_int, C.c_int, _ip, _lp]),
+    ("cedr_b200_merge_partial_trees", C.c_int, [C.c_int, _ip, _ip, _ip, _lp, _ip, C.c_int,
+                                                _ip, _ip, _lp, _ip]),
+    ("cedr_b200_allgather_host", C.c_int, [ALLGATHER_FN, _vp, C.c_int, _vp, _vp,
+                                           C.c_size_t]),
     ("cedr_b200_fill_headline", C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int, _vp, _vp,
                                           _vp, _vp, _vp, _vp]),
     ("cedr_b200_fill_headline_range", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int,
@@ -654,6 +658,46 @@ def make_1d_tree(ncells, imbalanced=False):
     _check(lib.cedr_b200_make_1d_tree(int(ncells), int(bool(imbalanced)),
                                       kids.ctypes.data_as(_ip), cellidx.ctypes.data_as(_lp)))
     return kids, cellidx, 0
+
+
+def merge_partial_trees(parts):
+    """Union of the ranks' partial trees (tree::Node::level, cedr_tree_caller.hpp:20-22).
+
+    `parts[p]` = (kids, cellidx, root, node_rank) of rank p: the global tree with the
+    subtrees that hold none of rank p's cells cut down to kid-less stubs. Returns
+    ((kids, cellidx, 0), node_rank) of the whole tree in pre-order, ready for QLT(...).
+    """
+    import numpy as np
+    lib = load_library()
+    nn = np.array([np.asarray(t[1]).size for t in parts], np.int32)
+    roots = np.array([int(t[2]) for t in parts], np.int32)
+    kids = np.concatenate([_as_i32(t[0]).reshape(-1) for t in parts])
+    cellidx = np.concatenate([np.asarray(t[1], np.int64).reshape(-1) for t in parts])
+    rank = np.concatenate([_as_i32(t[3]).reshape(-1) for t in parts])
+    cap = int(nn.sum())
+    ok, oc, orank = np.empty(2*cap, np.int32), np.empty(cap, np.int64), np.empty(cap, np.int32)
+    n = C.c_int(0)
+    _check(lib.cedr_b200_merge_partial_trees(
+        len(parts), nn.ctypes.data_as(_ip), roots.ctypes.data_as(_ip),
+        kids.ctypes.data_as(_ip), cellidx.ctypes.data_as(_lp), rank.ctypes.data_as(_ip),
+        cap, C.byref(n), ok.ctypes.data_as(_ip), oc.ctypes.data_as(_lp),
+        orank.ctypes.data_as(_ip)))
+    n = n.value
+    return (ok[:2*n].copy(), oc[:n].copy(), 0), orank[:n].copy()
+
+
+def assemble_partial_tree(tree, node_rank, group=None):
+    """Every rank passes its own partial tree; all get the merged whole tree back.
+
+    One setup-time all-gather of the parts over `group` (torch.distributed; any backend)
+    stands in for what the reference's level schedule gets from MPI at run time
+    (cedr_tree.cpp:71-76): the block plan needs the whole tree on every rank.
+    """
+    import torch.distributed as dist
+    kids, cellidx, root = tree
+    parts = [None]*dist.get_world_size(group)
+    dist.all_gather_object(parts, (kids, cellidx, int(root), node_rank), group=group)
+    return merge_partial_trees(parts)
 
 
 def partition_probe(ncells, rank, nranks, max_block_leaves=1024, imbalanced=False):

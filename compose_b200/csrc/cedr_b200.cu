@@ -2849,6 +2849,56 @@ int cedr_b200_make_1d_tree (int ncells, int imbalanced, int* kids_host,
   });
 }
 
+int cedr_b200_merge_partial_trees (int nparts, const int* part_nnodes, const int* part_root,
+                                   const int* kids, const int64_t* cellidx,
+                                   const int* node_rank, int cap_nodes, int* out_nnodes,
+                                   int* out_kids, int64_t* out_cellidx, int* out_rank) {
+  return guarded([&] {
+    cedr_b200_throw_if( ! part_nnodes || ! part_root || ! kids || ! cellidx || ! out_nnodes,
+                       "merge_partial_trees: null argument");
+    std::vector<int> k, r;
+    std::vector<int64_t> ci;
+    merge_partial_trees(nparts, part_nnodes, part_root, kids, cellidx, node_rank, k, ci, r);
+    *out_nnodes = static_cast<int>(ci.size());
+    // Size query: out arrays may be null; otherwise they must hold the merged tree.
+    if ( ! out_kids && ! out_cellidx && ! out_rank) return;
+    cedr_b200_throw_if(static_cast<int>(ci.size()) > cap_nodes,
+                       "merge_partial_trees: output arrays are too small");
+    if (out_kids) std::copy(k.begin(), k.end(), out_kids);
+    if (out_cellidx) std::copy(ci.begin(), ci.end(), out_cellidx);
+    if (out_rank) std::copy(r.begin(), r.end(), out_rank);
+  });
+}
+
+int cedr_b200_allgather_host (cedr_b200_allgather_fn fn, void* ctx, int nranks,
+                              const double* send_host, double* recv_host, size_t count) {
+  return guarded([&] {
+    cedr_b200_throw_if(nranks < 1 || ! send_host || ! recv_host, "allgather_host: bad argument");
+    if (nranks == 1) {
+      std::copy(send_host, send_host + count, recv_host);
+      return;
+    }
+    cedr_b200_throw_if( ! fn, "allgather_host: nranks > 1 needs the all-gather hook");
+    // The hook gathers device memory on a stream (it is the run()-time exchange's hook):
+    // stage through two scratch buffers on the legacy default stream. Setup-time only.
+    double* d = nullptr;
+    CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d), (1 + static_cast<size_t>(nranks))*count*
+                          sizeof(double)));
+    int e = 0;
+    cudaError_t ce = cudaMemcpy(d, send_host, count*sizeof(double), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) {
+      e = fn(ctx, d, d + count, count, nullptr);
+      if (e == 0) ce = cudaDeviceSynchronize();
+      if (e == 0 && ce == cudaSuccess)
+        ce = cudaMemcpy(recv_host, d + count, static_cast<size_t>(nranks)*count*sizeof(double),
+                        cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    cedr_b200_throw_if(e != 0, "allgather_host: the all-gather hook failed");
+    CUDA_CHECK(ce);
+  });
+}
+
 int cedr_b200_plan_probe (int ncells, int nnodes, int root, const int* kids,
                           const int64_t* cellidx, int max_block_leaves,
                           int64_t* lci2gci_host, int* ntiers,

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <mutex>
 #include <sstream>
@@ -271,6 +272,81 @@ void make_bisection_tree (int ncells, bool imbalanced, std::vector<int>& kids,
   kids.reserve(2*(2*static_cast<size_t>(ncells) - 1));
   cellidx.reserve(2*static_cast<size_t>(ncells) - 1);
   bisect(0, ncells, imbalanced, kids, cellidx);
+}
+
+void merge_partial_trees (int nparts, const int* nnodes, const int* root, const int* kids,
+                          const int64_t* cellidx, const int* rank,
+                          std::vector<int>& out_kids, std::vector<int64_t>& out_cellidx,
+                          std::vector<int>& out_rank) {
+  if (nparts < 1) fail("merge_partial_trees: need at least one part");
+  if (nparts > 1 && ! rank) fail("merge_partial_trees: node ranks are required");
+  std::vector<size_t> off(nparts + 1, 0);
+  for (int p = 0; p < nparts; ++p) {
+    if (nnodes[p] < 1) fail("merge_partial_trees: empty part");
+    if (root[p] < 0 || root[p] >= nnodes[p]) fail("merge_partial_trees: root out of range");
+    off[p+1] = off[p] + static_cast<size_t>(nnodes[p]);
+  }
+  std::vector<char> seen(off[nparts], 0);
+  out_kids.clear();
+  out_cellidx.clear();
+  out_rank.clear();
+
+  // One position of the global tree = the nodes the parts have there (global node ids
+  // into the concatenated arrays), plus the output slot waiting for this position's id.
+  struct Item { std::vector<size_t> views; int patch; };
+  std::vector<Item> stack(1);
+  stack[0].patch = -1;
+  for (int p = 0; p < nparts; ++p) stack[0].views.push_back(off[p] + root[p]);
+  std::vector<size_t> views, kid[2];
+  while ( ! stack.empty()) {
+    views.swap(stack.back().views);
+    const int patch = stack.back().patch;
+    stack.pop_back();
+    if (out_cellidx.size() >= static_cast<size_t>(std::numeric_limits<int>::max()/2))
+      fail("merge_partial_trees: tree too large");
+    const int me = static_cast<int>(out_cellidx.size());
+    if (patch >= 0) out_kids[patch] = me;
+    out_kids.push_back(-1);
+    out_kids.push_back(-1);
+    out_cellidx.push_back(-1);
+    out_rank.push_back(0);
+    kid[0].clear();
+    kid[1].clear();
+    long owner_view = -1;
+    for (size_t v : views) {
+      if (seen[v]) fail("merge_partial_trees: a part is not a tree (node reached twice)");
+      seen[v] = 1;
+      const int p = static_cast<int>(std::upper_bound(off.begin(), off.end(), v) -
+                                     off.begin()) - 1;
+      const int k0 = kids[2*v], k1 = kids[2*v+1];
+      if (k0 < 0 && k1 < 0) {
+        // A leaf, or the stub of a subtree this part has cut off.
+        if ( ! rank || rank[v] == p) owner_view = static_cast<long>(v);
+        continue;
+      }
+      if (k0 < 0 || k1 < 0)
+        fail("merge_partial_trees: an internal node must keep both kid slots "
+             "(cut a subtree down to a stub instead of dropping it)");
+      if (k0 >= nnodes[p] || k1 >= nnodes[p] || k0 == k1)
+        fail("merge_partial_trees: kid index out of range");
+      kid[0].push_back(off[p] + k0);
+      kid[1].push_back(off[p] + k1);
+    }
+    if (kid[0].empty()) {
+      if (owner_view < 0)
+        fail("merge_partial_trees: no part holds this leaf as its own (every rank's "
+             "partial tree must reach the cells it owns)");
+      out_cellidx[me] = cellidx[owner_view];
+      out_rank[me] = rank ? rank[owner_view] : 0;
+      if (out_cellidx[me] < 0) fail("merge_partial_trees: leaf without a cell index");
+    } else {
+      for (int k = 1; k >= 0; --k) {
+        stack.push_back(Item());
+        stack.back().views = kid[k];
+        stack.back().patch = 2*me + k;
+      }
+    }
+  }
 }
 
 void Plan::build (int ncells_, int nnodes, int root, const int* kids,

@@ -104,6 +104,22 @@ struct Plan {
 void make_bisection_tree(int ncells, bool imbalanced, std::vector<int>& kids,
                          std::vector<int64_t>& cellidx);
 
+// Union of the ranks' PARTIAL trees (tree::Node::level, cedr_tree_caller.hpp:20-22,
+// consumed at cedr_tree.cpp:71-76): each rank may hand over the global tree with every
+// subtree that holds none of its cells cut down to a stub (a node without kids whose
+// rank is not this rank's, cedr_tree.cpp:96-108). The reference never forms the whole
+// tree -- its level lists only need a rank's own nodes and their neighbours; the block
+// plan does need it (the tier sweeps above the block roots run on every rank), so the
+// parts are all-gathered once at setup and merged here. A node is identified by its
+// path from the root (kid slots are kept in the parts); a position is internal if any
+// part expands it, and a leaf's cell and rank are read from its owner's part. Part p is
+// `nnodes[p]` nodes at offset sum(nnodes[0..p)) of the concatenated arrays, kids
+// part-local, root = part-local node `root[p]`. Output in pre-order, root = 0.
+void merge_partial_trees(int nparts, const int* nnodes, const int* root, const int* kids,
+                         const int64_t* cellidx, const int* rank,
+                         std::vector<int>& out_kids, std::vector<int64_t>& out_cellidx,
+                         std::vector<int>& out_rank);
+
 } // namespace cedr_b200
 
 #endif

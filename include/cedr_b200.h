@@ -393,6 +393,26 @@ int cedr_b200_plan_probe(int ncells, int nnodes, int root, const int* kids,
 int cedr_b200_make_1d_tree(int ncells, int imbalanced, int* kids_host,
                            int64_t* cellidx_host);
 
+/* Partial trees (tree::Node::level, cedr_tree_caller.hpp:20-22, consumed at
+ * cedr_tree.cpp:71-76): a rank may hold the global tree with every subtree that contains
+ * none of its cells cut down to a stub (a kid-less node of another rank,
+ * cedr_tree.cpp:96-108). The block plan needs the whole tree on every rank, so the
+ * parts are gathered once at setup and merged by this call (host only): part p is
+ * part_nnodes[p] nodes at offset sum(part_nnodes[0..p)) of the concatenated flat arrays
+ * (layout of cedr_b200_qlt_create; kids are part-local; internal nodes keep both kid
+ * slots), part-local root part_root[p]; part p is rank p's. A position is internal if any
+ * part expands it; a leaf's cell and rank come from its owner's part. The merged tree is
+ * written in pre-order (root = node 0); pass null out arrays to query *out_nnodes. */
+int cedr_b200_merge_partial_trees(int nparts, const int* part_nnodes, const int* part_root,
+                                  const int* kids, const int64_t* cellidx,
+                                  const int* node_rank, int cap_nodes, int* out_nnodes,
+                                  int* out_kids, int64_t* out_cellidx, int* out_rank);
+/* Setup-time helper: run the all-gather hook (device buffers) on `count` HOST doubles per
+ * rank; recv_host holds nranks*count (rank-major). nranks == 1 copies. What Parallel's
+ * MPI_Comm gives the reference for free at setup (cedr_mpi.hpp:17-27). */
+int cedr_b200_allgather_host(cedr_b200_allgather_fn fn, void* ctx, int nranks,
+                             const double* send_host, double* recv_host, size_t count);
+
 /* Synthetic workload of SURVEY.md section 8(d), generated on the device:
  * splitmix64 stream seeded 0xCED20000 + config_id; fills rhom[ncells] and the
  * four [nt][lda] arrays. Bit-identical to compose_b200.workloads.headline(). */

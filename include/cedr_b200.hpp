@@ -31,6 +31,7 @@
 #ifndef CEDR_B200_HPP
 #define CEDR_B200_HPP
 
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
 #include <limits>
@@ -326,6 +327,9 @@ public:
     std::vector<int> kids, rank;
     std::vector<int64_t> cellidx;
     flatten(tree.get(), kids, cellidx, rank);
+    // tree::Node::level set: this rank passed only its part of the tree
+    // (cedr_tree_caller.hpp:20-22).
+    if (tree->level >= 0) assemble_partial_trees(p, kids, cellidx, rank);
     cedr_b200_cdr* h = nullptr;
     impl::check(cedr_b200_qlt_create(
                   &h, ncells, static_cast<int>(cellidx.size()), 0, kids.data(), cellidx.data(),
@@ -357,6 +361,55 @@ public:
   static void flatten_tree (const tree::Node* root, std::vector<int>& kids,
                             std::vector<int64_t>& cellidx, std::vector<int>& rank) {
     flatten(root, kids, cellidx, rank);
+  }
+
+  // Replace this rank's flattened partial tree by the union of all ranks' parts: two
+  // setup-time all-gathers through Parallel's hook (sizes, then the padded node tables as
+  // doubles -- every entry is an integer below 2^53) and cedr_b200_merge_partial_trees.
+  static void assemble_partial_trees (const mpi::Parallel::Ptr& p, std::vector<int>& kids,
+                                      std::vector<int64_t>& cellidx, std::vector<int>& rank) {
+    const int nr = p ? p->size() : 1;
+    cedr_b200_allgather_fn fn = p ? p->allgather() : nullptr;
+    void* ctx = p ? p->allgather_ctx() : nullptr;
+    const size_t n = cellidx.size();
+    std::vector<double> cnt(nr), mine(1, static_cast<double>(n));
+    impl::check(cedr_b200_allgather_host(fn, ctx, nr, mine.data(), cnt.data(), 1));
+    size_t nmax = 0, ntot = 0;
+    for (int r = 0; r < nr; ++r) {
+      nmax = std::max(nmax, static_cast<size_t>(cnt[r]));
+      ntot += static_cast<size_t>(cnt[r]);
+    }
+    mine.assign(4*nmax, -1.0);
+    for (size_t i = 0; i < n; ++i) {
+      mine[4*i] = kids[2*i];
+      mine[4*i+1] = kids[2*i+1];
+      mine[4*i+2] = static_cast<double>(cellidx[i]);
+      mine[4*i+3] = rank[i];
+    }
+    std::vector<double> all(4*nmax*nr);
+    impl::check(cedr_b200_allgather_host(fn, ctx, nr, mine.data(), all.data(), 4*nmax));
+    std::vector<int> pn(nr), proot(nr, 0), ak(2*ntot), ar(ntot);
+    std::vector<int64_t> ac(ntot);
+    for (size_t r = 0, o = 0; r < static_cast<size_t>(nr); ++r) {
+      pn[r] = static_cast<int>(cnt[r]);
+      const double* t = all.data() + 4*nmax*r;
+      for (int i = 0; i < pn[r]; ++i, ++o) {
+        ak[2*o] = static_cast<int>(t[4*i]);
+        ak[2*o+1] = static_cast<int>(t[4*i+1]);
+        ac[o] = static_cast<int64_t>(t[4*i+2]);
+        ar[o] = static_cast<int>(t[4*i+3]);
+      }
+    }
+    int nn = 0;
+    kids.assign(2*ntot, -1);
+    cellidx.assign(ntot, -1);
+    rank.assign(ntot, 0);
+    impl::check(cedr_b200_merge_partial_trees(nr, pn.data(), proot.data(), ak.data(), ac.data(),
+                                              ar.data(), static_cast<int>(ntot), &nn,
+                                              kids.data(), cellidx.data(), rank.data()));
+    kids.resize(2*static_cast<size_t>(nn));
+    cellidx.resize(nn);
+    rank.resize(nn);
   }
 
 private:

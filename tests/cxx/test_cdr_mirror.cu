@@ -201,6 +201,29 @@ int main () {
         }
       }
 
+  { // tree::Node::level set (cedr_tree_caller.hpp:20-22): the constructor takes the tree
+    // for this rank's PART, gathers the parts through Parallel's hook and merges them.
+    // On one rank the part is the whole tree; the multi-part merge is tested on the host
+    // (tests/test_host_logic.py, tests/test_multirank_host.py).
+    struct SetLevel {
+      static int go (tree::Node* nd) {
+        int l = 0;
+        for (int k = 0; k < nd->nkids; ++k) l = std::max(l, 1 + go(nd->kids[k].get()));
+        return nd->level = l;
+      }
+    };
+    for (const int n : {21, 1350}) {
+      const Problem p(n, {cst, st, ct, t_, ProblemType::shapepreserve, cst});
+      tree::Node::Ptr tree = tree::make_tree_over_1d_mesh(par, n, true);
+      SetLevel::go(tree.get());
+      QLTT q(par, n, tree, CDR::Options());
+      std::vector<Long> g;
+      q.get_owned_glblcells(g);
+      const std::vector<long long> gl(g.begin(), g.end());
+      REQUIRE(same_bits(run_device(q, p, gl), oracle_qlt(p, true, false)));
+    }
+  }
+
   for (const int n : {1, 4, 11, 1350, 5400}) {
     const Problem p(n, {cst, ProblemType::shapepreserve, cst, st});
     const std::vector<double> ref = oracle_caas(p);

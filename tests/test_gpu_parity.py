@@ -108,6 +108,31 @@ def test_qlt_random_trees_bitwise(oracle):
         assert np.array_equal(got, ref)
 
 
+def test_qlt_from_partial_trees_bitwise(oracle):
+    """tree::Node::level partial trees (cedr_tree_caller.hpp:20-22): three ranks' pruned
+    parts of a random tree under the pseudorandom map (cedr_tree.cpp:371-374), merged by
+    cedr_b200_merge_partial_trees, give the oracle's results on the caller's whole tree."""
+    import compose_b200 as cb
+    from gpu_util import run_qlt_gpu
+    from test_host_logic import prune_for_rank
+    rng = np.random.default_rng(23)
+    ncells, nranks = 700, 3
+    tree = random_tree(rng, ncells)
+    ci = np.arange(ncells)
+    rank_of_cell = ((ci + ci//nranks) % nranks).astype(np.int32)
+    rank_of_cell[100:400] = 2
+    parts = [prune_for_rank((tree.kids, tree.cellidx, tree.root), rank_of_cell, r, rng)
+             for r in range(nranks)]
+    assert all(p[1].size < tree.cellidx.size for p in parts)
+    whole, _ = cb.merge_partial_trees(parts)
+    ts, v = R.generate(ncells, seed=5)
+    pts = [t.problem_type for t in ts]
+    ref = oracle.qlt(tree, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev)
+    got, _ = run_qlt_gpu(ncells, pts, v.rhom, v.Qm_min, v.Qm, v.Qm_max, v.Qm_prev,
+                         tree=whole, max_block_leaves=64)
+    assert np.array_equal(got, ref)
+
+
 def test_qlt_headline_inputs_bitwise(oracle):
     """ne30-shaped tree (5,400 cells), a slice of the headline tracers, all `cst`."""
     from compose_b200 import workloads as W

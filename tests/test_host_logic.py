@@ -2,6 +2,7 @@
 plan (host C++) is self-consistent, and there is no CPU fallback."""
 import re
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -77,3 +78,131 @@ def test_plan_rejects_malformed_trees():
     with pytest.raises(cb.CedrError):
         cb.plan_probe(2, (np.array([1, -1, -1, -1, -1, -1], np.int32),
                           np.array([-1, 0, 1], np.int64), 0))   # one kid
+
+
+# ---- partial trees (tree::Node::level, cedr_tree_caller.hpp:20-22) --------------------
+
+def prune_for_rank(tree, leaf_rank_of_cell, me, rng=None):
+    """Rank `me`'s partial tree: every subtree without a cell of `me` becomes a stub.
+
+    Nodes are renumbered in a shuffled order (root not at 0) when `rng` is given, so
+    that the merge cannot rely on the parts' numbering. Returns (kids, cellidx, root,
+    node_rank)."""
+    kids, cellidx, root = tree
+    nn = cellidx.size
+    sys.setrecursionlimit(max(10000, 4*nn))
+    has_mine = np.zeros(nn, bool)
+    first_rank = np.zeros(nn, np.int32)
+
+    def scan(i):
+        if kids[2*i] < 0:
+            first_rank[i] = leaf_rank_of_cell[cellidx[i]]
+            has_mine[i] = first_rank[i] == me
+            return
+        scan(kids[2*i]); scan(kids[2*i + 1])
+        has_mine[i] = has_mine[kids[2*i]] or has_mine[kids[2*i + 1]]
+        first_rank[i] = first_rank[kids[2*i]]
+
+    scan(root)
+    keep = []
+
+    def collect(i, parent_kept):
+        keep.append(i)
+        if kids[2*i] >= 0 and has_mine[i]:
+            collect(kids[2*i], True); collect(kids[2*i + 1], True)
+
+    collect(root, True)
+    order = np.array(keep)
+    if rng is not None:
+        order = order[rng.permutation(order.size)]
+    new = {int(o): j for j, o in enumerate(order)}
+    pk = np.full(2*order.size, -1, np.int32)
+    pc = np.full(order.size, -1, np.int64)
+    pr = np.zeros(order.size, np.int32)
+    for o, j in new.items():
+        if kids[2*o] >= 0 and has_mine[o]:
+            pk[2*j], pk[2*j + 1] = new[int(kids[2*o])], new[int(kids[2*o + 1])]
+            pr[j] = me if rng is None else int(first_rank[o])
+        elif kids[2*o] >= 0:
+            pr[j] = first_rank[o]           # a stub: some other rank, no cell
+            pc[j] = 1000000 + o             # the reference uses a stub's cellidx as an id
+        else:
+            pc[j] = cellidx[o]
+            pr[j] = leaf_rank_of_cell[cellidx[o]]
+    return pk, pc, new[int(root)], pr
+
+
+def preorder(tree, node_rank):
+    kids, cellidx, root = tree
+    ok, oc, orank, stack = [], [], [], [(int(root), -1)]
+    while stack:
+        i, patch = stack.pop()
+        me = len(oc)
+        if patch >= 0:
+            ok[patch] = me
+        ok.extend([-1, -1]); oc.append(int(cellidx[i])); orank.append(0)
+        if kids[2*i] < 0:
+            orank[me] = int(node_rank[i])
+        else:
+            oc[me] = -1
+            stack.append((int(kids[2*i + 1]), 2*me + 1))
+            stack.append((int(kids[2*i]), 2*me))
+    return np.array(ok, np.int32), np.array(oc, np.int64), np.array(orank, np.int32)
+
+
+@pytest.mark.parametrize("ncells,nranks,maps", [(1, 1, "contig"), (2, 2, "contig"),
+                                                (37, 3, "contig"), (200, 4, "random"),
+                                                (200, 7, "pseudo"), (5400, 8, "contig")])
+def test_partial_trees_merge_to_the_whole_tree(ncells, nranks, maps):
+    from test_oracle_vs_ref import random_tree
+    rng = np.random.default_rng(ncells + nranks)
+    rt = random_tree(rng, ncells)
+    for tree in (cb.make_1d_tree(ncells), cb.make_1d_tree(ncells, True),
+                 (rt.kids, rt.cellidx, rt.root)):
+        kids, cellidx, root = tree
+        if maps == "contig":       # cedr_tree.cpp:368-369
+            rank_of_cell = np.minimum(np.arange(ncells)//max(1, ncells//nranks), nranks - 1)
+        elif maps == "pseudo":     # cedr_tree.cpp:371-374
+            ci = np.arange(ncells)
+            rank_of_cell = (ci + ci//nranks) % nranks
+        else:
+            rank_of_cell = rng.integers(0, nranks, ncells)
+            rank_of_cell[:nranks] = np.arange(nranks)
+        rank_of_cell = rank_of_cell.astype(np.int32)
+        node_rank = np.where(cellidx >= 0, rank_of_cell[np.maximum(cellidx, 0)], 0)
+        parts = [prune_for_rank(tree, rank_of_cell, r, rng) for r in range(nranks)]
+        if nranks > 1 and maps == "contig" and ncells >= 37:
+            assert max(p[1].size for p in parts) < cellidx.size    # really partial
+        (mk, mc, mroot), mrank = cb.merge_partial_trees(parts)
+        ek, ec, er = preorder(tree, node_rank)
+        assert mroot == 0
+        assert np.array_equal(mk, ek) and np.array_equal(mc, ec) and np.array_equal(mrank, er)
+        # and the plan takes it: same leaf order as from the caller's whole tree
+        a = cb.plan_probe(ncells, (mk, mc, 0), 64)
+        b = cb.plan_probe(ncells, tree, 64)
+        assert np.array_equal(a["lci2gci"], b["lci2gci"]) and a["idsum"] == b["idsum"]
+
+
+def test_partial_trees_merge_rejects_bad_parts():
+    tree = cb.make_1d_tree(8)
+    rank_of_cell = (np.arange(8)//4).astype(np.int32)
+    p0 = prune_for_rank(tree, rank_of_cell, 0)
+    p1 = prune_for_rank(tree, rank_of_cell, 1)
+    cb.merge_partial_trees([p0, p1])
+    # nobody expands rank 1's subtree: its stub passes for a leaf, and the plan rejects
+    # the tree (8 cells need 15 nodes)
+    (mk, mc, _), _ = cb.merge_partial_trees([p0, p0])
+    with pytest.raises(cb.CedrError):
+        cb.plan_probe(8, (mk, mc, 0), 64)
+    k, c, r, nr = (np.array(a).copy() if not np.isscalar(a) else a for a in p1)
+    nr[(k[0::2] < 0) & (nr == 1)] = 2              # rank 1's leaves claimed by nobody
+    with pytest.raises(cb.CedrError, match="holds this leaf as its own"):
+        cb.merge_partial_trees([p0, (k, c, r, nr)])
+    k, c, r, nr = (np.array(a).copy() if not np.isscalar(a) else a for a in p1)
+    k[2*r + 1] = -1                                # root keeps one kid slot only
+    with pytest.raises(cb.CedrError, match="both kid slots"):
+        cb.merge_partial_trees([p0, (k, c, r, nr)])
+    k, c, r, nr = (np.array(a).copy() if not np.isscalar(a) else a for a in p1)
+    k[2*r] = r                                     # a cycle
+    with pytest.raises(cb.CedrError):
+        cb.merge_partial_trees([p0, (k, c, r, nr)])

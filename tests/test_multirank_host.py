@@ -87,3 +87,48 @@ def test_exchange_pattern_gloo_world2(ncells, mbl):
     for rank, total, missing in out:
         assert not missing
         assert total == ncells*(ncells - 1)/2
+
+
+def _partial_worker(rank, world, port, ncells, q):
+    import torch.distributed as dist
+    import compose_b200 as cb
+    from test_host_logic import prune_for_rank, preorder
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tree = cb.make_1d_tree(ncells, True)
+        ci = np.arange(ncells)
+        rank_of_cell = ((ci + ci//world) % world).astype(np.int32)   # cedr_tree.cpp:371-374
+        rank_of_cell[:ncells//2] = 0     # ... with a long run of rank 0, so parts get cut
+        rank_of_cell[ncells//2] = 1
+        kids, cellidx, root, node_rank = prune_for_rank(tree, rank_of_cell, rank,
+                                                        np.random.default_rng(rank))
+        whole, whole_rank = cb.assemble_partial_tree((kids, cellidx, root), node_rank)
+        full_rank = np.where(tree[1] >= 0, rank_of_cell[np.maximum(tree[1], 0)], 0)
+        ek, ec, er = preorder(tree, full_rank)
+        same = (np.array_equal(whole[0], ek) and np.array_equal(whole[1], ec) and
+                np.array_equal(whole_rank, er))
+        q.put((rank, bool(same), int(cellidx.size), int(ec.size)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partial_trees_assembled_over_gloo_world2():
+    """tree::Node::level partial trees (cedr_tree_caller.hpp:20-22): each rank hands over
+    its pruned part; after the setup-time gather both hold the caller's whole tree."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_partial_worker, args=(r, 2, port, 300, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, same, npart, nfull in out:
+        assert same
+        if rank == 1:
+            assert npart < nfull      # rank 1's part really was cut
