@@ -495,9 +495,11 @@ def main():
             import numpy as np
             y0 = np.linspace(0.1, 0.9, 112)
             y0[-1] = y0[0]
-            for g in (False, True):
-                _, us = c.transport1d_cycle(351, y0, use_graph=g)
-                small["%s_t1d_step_us_%s" % (kind, "graph" if g else "launches")] = us
+            # ... and as ONE launch for the whole cycle (a persistent CTA, t1d_cycle_kernel).
+            for g, tag in ((False, "launches"), (True, "graph"), (2, "one_launch")):
+                # (twice, the faster: a kernel's first launch loads its module)
+                us = min(c.transport1d_cycle(351, y0, use_graph=g)[1] for _ in range(2))
+                small["%s_t1d_step_us_%s" % (kind, tag)] = us
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None

@@ -301,14 +301,17 @@ class CDR:
 
     def transport1d_cycle(self, nsteps, y0, use_graph=True):
         """Problem1D::cycle (cedr_test_1d_transport.cpp:231-254) on the device for tracer 0.
-        y0: numpy [ncells + 1]. Returns (yf, device microseconds per step)."""
+        y0: numpy [ncells + 1]. Returns (yf, device microseconds per step). use_graph:
+        False = three launches per step, True = replayed from a CUDA graph, 2 = the whole
+        cycle in one launch (one block of <= 256 cells, one tracer)."""
         import numpy as np
         y0 = np.ascontiguousarray(y0, dtype=np.float64)
         yf = np.empty_like(y0)
         ms = C.c_float(0)
         _check(self._lib.cedr_b200_transport1d_cycle(
             self._h, int(nsteps), y0.ctypes.data_as(_dp), yf.ctypes.data_as(_dp),
-            int(bool(use_graph)), C.byref(ms)))
+            2 if use_graph == 2 and use_graph is not True else int(bool(use_graph)),
+            C.byref(ms)))
         return yf, 1e3*ms.value
 
     def run(self):

@@ -2630,7 +2630,31 @@ int cedr_b200_transport1d_cycle (cedr_b200_cdr* c, int nsteps, const double* y0_
       CUDA_CHECK(cudaEventCreate(&e0));
       CUDA_CHECK(cudaEventCreate(&e1));
       int done = 0;
-      if (use_graph && nsteps >= 2) {
+      if (use_graph == 2) {
+        // The whole cycle in one launch (t1d_cycle_kernel).
+        cedr_b200_throw_if( ! solo_ok(*c) || c->trcr_prob.size() != 1,
+                           "transport1d: the one-launch cycle takes a single block of at "
+                           "most 256 cells with one tracer");
+        const SweepArgs sa = base_args(*c, cls, 0);
+        const size_t nn = 2*static_cast<size_t>(c->plan.tiers[0].max_nl);
+        const size_t smem = sizeof(double)*(2*(static_cast<size_t>(n) + 2) + 5*nn + 2) +
+          sizeof(dev::NodeConst)*(nn/2) + sizeof(int)*(3*(nn/2) + 2);
+        CUDA_CHECK(cudaEventRecord(e0, own));
+        double* const yo = d_y[nsteps & 1].p;
+        switch (cls) {
+        case CLS_CST: t1d_cycle_kernel<CLS_CST><<<1, kThreads, smem, own>>>(
+            sa, c->solo_block, a, d_y[0].p, yo, nsteps); break;
+        case CLS_NN: t1d_cycle_kernel<CLS_NN><<<1, kThreads, smem, own>>>(
+            sa, c->solo_block, a, d_y[0].p, yo, nsteps); break;
+        case CLS_CNN: t1d_cycle_kernel<CLS_CNN><<<1, kThreads, smem, own>>>(
+            sa, c->solo_block, a, d_y[0].p, yo, nsteps); break;
+        default: t1d_cycle_kernel<CLS_CAAS><<<1, kThreads, smem, own>>>(
+            sa, c->solo_block, a, d_y[0].p, yo, nsteps); break;
+        }
+        CUDA_CHECK(cudaGetLastError());
+        c->last_launches = 1;
+        done = nsteps;
+      } else if (use_graph && nsteps >= 2) {
         // Two steps (y0 -> y1 -> y0) per graph launch: launch-bound work, replayed.
         CUDA_CHECK(cudaStreamBeginCapture(own, cudaStreamCaptureModeThreadLocal));
         step(0);

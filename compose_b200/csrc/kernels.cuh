@@ -811,11 +811,10 @@ struct T1dArgs {
   const double* out;    // results: QLT out row 0 / CAAS Qm row
 };
 
-__global__ void __launch_bounds__(128)
-t1d_interp_set_kernel (const T1dArgs a, const double* __restrict__ y, double* __restrict__ yi) {
-  const int j = blockIdx.x*blockDim.x + threadIdx.x;
+// Point j of one step (j = ncells is the periodic image: interpolated, not set).
+__device__ __forceinline__ void
+t1d_interp_set_point (const T1dArgs& a, const double* const y, double* const yi, const int j) {
   const int nc = a.ncells;
-  if (j > nc) return;
   const double* const x = a.xcp;
   const int i = a.tgt_i[j], ip1 = i + 1;
   auto slope = [&] (const int k) { return (y[k + 1] - y[k])/(x[k + 1] - x[k]); };
@@ -861,11 +860,88 @@ t1d_interp_set_kernel (const T1dArgs a, const double* __restrict__ y, double* __
 }
 
 __global__ void __launch_bounds__(128)
+t1d_interp_set_kernel (const T1dArgs a, const double* __restrict__ y, double* __restrict__ yi) {
+  const int j = blockIdx.x*blockDim.x + threadIdx.x;
+  if (j > a.ncells) return;
+  t1d_interp_set_point(a, y, yi, j);
+}
+
+__global__ void __launch_bounds__(128)
 t1d_get_kernel (const T1dArgs a, double* __restrict__ yi) {
   const int j = blockIdx.x*blockDim.x + threadIdx.x;
   if (j > a.ncells) return;
   const int c = j == a.ncells ? 0 : j;
   yi[j] = a.out[a.lci[c]]/a.area[c];
+}
+
+// The whole cycle in ONE launch, for problems solo_kernel takes (a single block of at most
+// 256 leaves) with one tracer: a persistent CTA keeps the two time levels of y in shared
+// memory and runs, per step, the same three phases -- t1d_interp_set_point for every point,
+// solo_kernel's body (rhom sums and node constants, the block's sweeps, or CAAS's sums and
+// adjustment), the read-back of t1d_get_kernel -- separated by block barriers instead of
+// kernel boundaries. The many-tiny-calls pattern is launch-latency bound on a GPU; this
+// form pays the latency once per cycle. Same operations on the same operands: the bits of
+// the three-launch form. Shared memory: 2 x (ncells + 1) doubles (padded to even), then
+// solo_kernel's layout.
+template <int CLS>
+__global__ void __launch_bounds__(256)
+t1d_cycle_kernel (const SweepArgs a, const BlockDev B, const T1dArgs ta,
+                  const double* const y_in, double* const y_out, const int nsteps) {
+  extern __shared__ double sm_all[];
+  const int ncp = ta.ncells + 1, ncp2 = ncp + (ncp & 1);
+  double* const ys0 = sm_all;
+  double* const ys1 = ys0 + ncp2;
+  double* const sm = ys1 + ncp2;
+  const int t = a.tracers[0];
+  const int nn = B.nl + B.ni, tid = threadIdx.x, nth = blockDim.x;
+  double* const rh = sm + 4*nn;
+  dev::NodeConst* const nc = reinterpret_cast<dev::NodeConst*>(rh + nn + (nn & 1));
+  int* const tabs = reinterpret_cast<int*>(nc + B.ni);
+  for (int i = tid; i < B.ni; i += nth) {
+    tabs[i] = a.kid0[B.kid_off + i];
+    tabs[B.ni + i] = a.kid1[B.kid_off + i];
+  }
+  for (int i = tid; i <= B.nlev; i += nth) tabs[2*B.ni + i] = a.lvlptr[B.lvlptr_off + i];
+  for (int j = tid; j < ncp; j += nth) ys0[j] = y_in[j];
+  __syncthreads();
+  for (int s = 0; s < nsteps; ++s) {
+    const double* const y = (s & 1) ? ys1 : ys0;
+    double* const yi = (s & 1) ? ys0 : ys1;
+    for (int j = tid; j < ncp; j += nth) t1d_interp_set_point(ta, y, yi, j);
+    __syncthreads();   // the rows in global memory, written and read by this CTA alone
+    if (CLS == CLS_CAAS) {
+      sweep_block<CLS_CAAS, MODE_TOP>(a, 0, t, sm, nullptr, nullptr, nullptr, &B, tabs);
+      __syncthreads();
+      // CAAS::finish_locally (cedr_caas.cpp:211-253), as in solo_kernel.
+      const double mode = a.caas_scal[2*t], fac = a.caas_scal[2*t+1];
+      const double* const rlo = a.rows.row(0, t) + B.leaf0;
+      const double* const rhi = a.rows.row(2, t) + B.leaf0;
+      double* const rq = const_cast<double*>(a.rows.row(1, t)) + B.leaf0;
+      for (int i = tid; i < B.nl; i += nth) {
+        const double lo = rlo[i], hi = rhi[i];
+        double q = dev::rmin(hi, dev::rmax(lo, rq[i]));
+        if (mode < 0) { q += fac*(q - lo); q = dev::rmax(lo, q); }
+        else if (mode > 0) { q += fac*(hi - q); q = dev::rmin(hi, q); }
+        rq[i] = q;
+      }
+    } else {
+      // rhom does not change over the cycle: its sums and the node constants are formed in
+      // the first step and stay in shared memory.
+      sweep_block<CLS, MODE_TOP>(a, 0, t, sm, nc, s == 0 ? rh : nullptr,
+                                 s == 0 ? nc : nullptr, &B, tabs);
+    }
+    __syncthreads();
+    // get_Qm: QLT's solved leaf masses are still in shared memory (sweep_block's f3, what
+    // it has just stored to `out`); CAAS's are in its Qm row.
+    const double* const res = CLS == CLS_CAAS ? ta.out : sm + 3*nn - B.leaf0;
+    for (int j = tid; j < ncp; j += nth) {
+      const int c = j == ta.ncells ? 0 : j;
+      yi[j] = res[ta.lci[c]]/ta.area[c];
+    }
+    __syncthreads();
+  }
+  const double* const yf = (nsteps & 1) ? ys1 : ys0;
+  for (int j = tid; j < ncp; j += nth) y_out[j] = yf[j];
 }
 
 // Synthetic workload of SURVEY.md 8(d): splitmix64, U = (z >> 11) * 2^-53.

@@ -295,8 +295,12 @@ int cedr_b200_local_solve(int method, int nprob, int n, const double* w, const d
  * the 1-D mesh tree of ncells cells, or a CAAS of ncells cells; uniform mesh): every step is
  * the periodic cubic interpolation at the departure points fused with the caller side of
  * run_cdr (bounds over the domain of dependence, set_Qm), CDR::run, and get_Qm / area --
- * three launches. With use_graph the steps are captured once in a CUDA graph and replayed
- * (the many-tiny-calls pattern of BASELINE.json's config 5). y0_host / yf_host hold
+ * three launches. With use_graph = 1 the steps are captured once in a CUDA graph and
+ * replayed (the many-tiny-calls pattern of BASELINE.json's config 5); with use_graph = 2
+ * the whole cycle is ONE launch: a persistent CTA runs the same three phases per step with
+ * block barriers in place of kernel boundaries (problems of a single block of at most 256
+ * cells with one tracer, e.g. the reference's 111-cell test; an error otherwise). Results
+ * are identical in all three forms. y0_host / yf_host hold
  * ncells + 1 values (the last is the periodic image of the first). ms_per_step (may be
  * NULL) receives the device time per step. rhom is set to the cell areas. */
 int cedr_b200_transport1d_cycle(cedr_b200_cdr* cdr, int nsteps, const double* y0_host,

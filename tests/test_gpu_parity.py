@@ -1254,12 +1254,13 @@ def test_local_batched_solvers_bitwise(oracle, n):
               xlo=d["xlo"], xhi=d["xhi"], w=d["w"], a=d["a"])
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("use_graph", [False, True, 2])
 def test_transport1d_device_harness_bitwise(oracle, use_graph):
     """BASELINE.json config 5 entirely on the device (cedr_b200_transport1d_cycle): the 351
     steps of cedr_test_1d_transport.cpp on 111 cells -- interpolation + set_Qm, CDR::run,
-    get_Qm per step, optionally replayed from a CUDA graph -- must end on the same bits as
-    the host loop driving the oracle, for qltnn, qlt and caas."""
+    get_Qm per step, optionally replayed from a CUDA graph, or (2) the whole cycle as one
+    launch of a persistent CTA -- must end on the same bits as the host loop driving the
+    oracle, for qltnn, qlt and caas."""
     import compose_b200 as cb
     import transport1d as T
     from test_oracle_golden import t1d_runners
