@@ -257,7 +257,7 @@ struct cedr_b200_cdr {
   // run() as a replayed CUDA graph (cedr_b200_set_graph): one per exchange-buffer parity.
   struct RunGraph { cudaGraphExec_t exec = nullptr; int launches = 0; };
   RunGraph graph[2];
-  int graph_mode = -1;         // -1: where it pays (multi-rank p2p), 0: never, 1: whenever possible
+  int graph_mode = -1;         // -1: where it pays (multi-rank p2p; short one-rank runs), 0: never, 1: whenever possible
   int graph_plain_runs = 0;    // plain run() calls since the last reset (the first ones stay plain)
   cudaStream_t cap_stream = nullptr;   // capture happens here (the caller's may be stream 0)
   void graph_reset () {
@@ -1767,7 +1767,12 @@ bool graph_eligible (const cedr_b200_cdr& c) {
   if (c.profiling || c.repl || c.is_bfb || c.ring_ok || solo_ok(c)) return false;
   if (c.is_caas && c.caas_sum_mode != CEDR_B200_CAAS_SUM_TREE) return false;
   if (c.nranks > 1 && ! c.p2p_on) return false;
-  return c.graph_mode == 1 || c.nranks > 1;
+  if (c.graph_mode == 1 || c.nranks > 1) return true;
+  // Auto, one rank: short runs, where the gaps between run()'s launches are a visible share
+  // (ne30 x 2,880 tracers: 0.338 -> 0.322 ms; x 320: 0.095 -> 0.080 ms; ne120 x 1,280:
+  // no difference, profiles/r02c_graph_ab.txt).
+  return static_cast<long long>(c.nlcl)*static_cast<long long>(c.trcr_prob.size()) <=
+    static_cast<long long>(env_int("CEDR_B200_GRAPH_AUTO_MAX", 32000000));
 }
 
 void run_graphed (cedr_b200_cdr& c) {
@@ -2496,6 +2501,7 @@ int cedr_b200_bind_arrays (cedr_b200_cdr* c, int64_t lda, const double* qm_min, 
     if ( ! qm) {          // unbind
       c->bound = cedr_b200_cdr::Bound();
       upload_rowaddr(*c);
+      c->graph_reset();   // the output array is a launch argument of the captured kernels
       return;
     }
     cedr_b200_throw_if(c->is_bfb, "bind_arrays is for QLT and CAAS");

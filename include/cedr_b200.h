@@ -311,7 +311,8 @@ int cedr_b200_transport1d_cycle(cedr_b200_cdr* cdr, int nsteps, const double* y0
 /* run() as a replayed CUDA graph: its launches are captured once (per exchange-buffer parity)
  * and replayed, so a run() of a dozen small kernels costs one launch on the host and no
  * gaps between kernels on the device. mode -1 (default): where it pays, i.e. multi-rank
- * runs over the peer-to-peer exchange; 0: never; 1: whenever run() is pure stream work (no
+ * runs over the peer-to-peer exchange and one-rank runs of at most 3.2e7 cell x tracer
+ * updates (ne30 x 72 x 40 is 1.6e7); 0: never; 1: whenever run() is pure stream work (no
  * profiling, no all-gather hook or UserAllReducer, not the ring kernel, not the one-launch
  * tiny-problem path). The first run() after setup or after a change of bindings stays
  * plain. Results are identical either way. (No reference counterpart: the reference's

@@ -1119,6 +1119,73 @@ def test_run_replayed_as_cuda_graph_bitwise(oracle, kind, bound):
     c.synchronize()
 
 
+@pytest.mark.parametrize("kind", ["qlt", "caas"])
+def test_run_graph_auto_mode_bind_and_unbind(oracle, kind, monkeypatch):
+    """Graph mode -1 (default) replays short one-rank runs by itself; binding and UNBINDING
+    the caller's arrays drop the captured graph (its kernels carry the output array as an
+    argument); a CDR above the auto threshold stays on plain launches."""
+    import torch
+    import compose_b200 as cb
+    from compose_b200 import workloads as W
+    ncells, nt = 5400, 10
+    pts = [7]*nt
+    tree = oracle.bisection_tree(ncells)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+    def make():
+        c = cb.QLT(ncells) if kind == "qlt" else cb.CAAS(ncells)
+        for p in pts:
+            c.declare_tracer(p)
+        c.end_tracer_declarations()
+        c.finish_setup()
+        return c
+
+    def reference(step):
+        rhom, lo, q, hi, prev = W.headline(ncells, nt, 60 + step)
+        ref = (oracle.qlt(tree, pts, rhom, lo, q, hi, prev) if kind == "qlt"
+               else oracle.caas(ncells, pts, lo, q, hi, prev, tree=tree))
+        return rhom, lo, q, hi, prev, ref
+
+    c = make()
+    arrs = [torch.empty((nt, ncells), dtype=torch.float64, device="cuda") for _ in range(5)]
+    lo_d, q_d, hi_d, prev_d, out_d = arrs
+    for step in range(9):
+        rhom, lo, q, hi, prev, ref = reference(step)
+        c.set_rhom(dev(rhom))
+        phase = step//3                 # own buffers, bound arrays, own buffers again
+        if step == 3:
+            if kind == "qlt":
+                c.bind_arrays(q_d, lo_d, hi_d, prev_d, out=out_d)
+            else:
+                c.bind_arrays(q_d, lo_d, hi_d, prev_d)
+        if step == 6:
+            c.bind_arrays(None, None, None)
+        if phase == 1:
+            for d, h in zip((lo_d, q_d, hi_d, prev_d), (lo, q, hi, prev)):
+                d.copy_(dev(h))
+            out_d.fill_(-1.0)
+        else:
+            c.set_Qm(dev(q), dev(lo), dev(hi), dev(prev))
+        c.run()
+        c.synchronize()
+        if phase == 1:
+            got = (out_d if kind == "qlt" else q_d).cpu().numpy()
+        else:
+            got = c.get_Qm().cpu().numpy()
+        assert np.array_equal(got, ref), step
+        assert c.uses_graph() == (step % 3 >= 1), step
+    monkeypatch.setenv("CEDR_B200_GRAPH_AUTO_MAX", str(ncells*nt - 1))
+    c = make()
+    rhom, lo, q, hi, prev, ref = reference(0)
+    c.set_rhom(dev(rhom))
+    for _ in range(3):
+        c.set_Qm(dev(q), dev(lo), dev(hi), dev(prev))
+        c.run()
+    c.synchronize()
+    assert not c.uses_graph()
+    assert np.array_equal(c.get_Qm().cpu().numpy(), ref)
+
+
 # ---------------------------------------------------------------- zero-copy binding (8f-1)
 
 @pytest.mark.parametrize("ncells", [111, 1000, 5400])
