@@ -206,3 +206,20 @@ def test_partial_trees_merge_rejects_bad_parts():
     k[2*r] = r                                     # a cycle
     with pytest.raises(cb.CedrError):
         cb.merge_partial_trees([p0, (k, c, r, nr)])
+
+
+def test_allgather_host_one_rank_and_missing_hook():
+    """cedr_b200_allgather_host: one rank is a copy (no device needed); several ranks
+    without the all-gather hook is an error, not a silent local copy."""
+    import ctypes as C
+    lib = cb.load_library()
+    send = np.arange(5, dtype=np.float64)
+    recv = np.zeros(5)
+    null_fn = cb.ALLGATHER_FN()
+    assert lib.cedr_b200_allgather_host(null_fn, None, 1, send.ctypes.data_as(C.c_void_p),
+                                        recv.ctypes.data_as(C.c_void_p), 5) == 0
+    assert np.array_equal(send, recv)
+    recv2 = np.zeros(10)
+    assert lib.cedr_b200_allgather_host(null_fn, None, 2, send.ctypes.data_as(C.c_void_p),
+                                        recv2.ctypes.data_as(C.c_void_p), 5) != 0
+    assert b"all-gather hook" in lib.cedr_b200_last_error()
